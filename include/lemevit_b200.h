@@ -1,0 +1,130 @@
+/* liblemevit_b200 — C ABI of the Blackwell-native LeMeViT backbone forward pass.
+ *
+ * The reference (ViTAE-Transformer/LeMeViT) has no C/FFI boundary of its own: its hot path is the
+ * Python `LeMeViT.forward` / `forward_features` (models/lemevit.py:809-836) and the mmseg/mmdet
+ * backbone `forward` (semantic_segmentation/mmseg/models/backbones/lemevit.py:800-827), reached
+ * through `timm.create_model` / `BACKBONES.register_module()`.  This header is the boundary a
+ * binding for that path targets: plain pointers and sizes, no torch types.  `lemevit_b200/_native.py`
+ * is the ctypes binding; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all buffers;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - every function returns LMV_OK (0) or a negative LMV_ERR_* code; `lmv_last_error()` returns a
+ *     thread-local message for the last failure;
+ *   - the library is re-entrant per (plan, stream); a plan must not be used from two threads at once;
+ *   - there is NO CPU fallback: every entry point launches sm_100a kernels or fails.
+ */
+#ifndef LEMEVIT_B200_H_
+#define LEMEVIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMV_OK 0
+#define LMV_ERR_INVALID (-1)     /* bad argument / shape / alignment                                  */
+#define LMV_ERR_UNSUPPORTED (-2) /* configuration outside what the kernels implement                  */
+#define LMV_ERR_CUDA (-3)        /* a CUDA runtime / driver call failed                               */
+#define LMV_ERR_OOM (-4)         /* CUDA out of memory (message contains "CUDA out of memory")        */
+
+#define LMV_DTYPE_BF16 0
+#define LMV_DTYPE_F32 1
+
+#define LMV_MAX_STAGES 8
+
+/* Mirrors the structural kwargs of LeMeViT.__init__ (models/lemevit.py:664-687). */
+typedef struct lmv_config {
+  int num_stages;                  /* len(attn_type), 5 for every published variant                   */
+  int depth[LMV_MAX_STAGES];       /* blocks per stage                                                */
+  int embed_dim[LMV_MAX_STAGES];   /* channels per stage                                              */
+  int mlp_hidden[LMV_MAX_STAGES];  /* int(mlp_ratio * embed_dim)                                      */
+  char attn_type[LMV_MAX_STAGES];  /* 'C', 'D' or 'S' (models/lemevit.py:652-660)                     */
+  int head_dim;                    /* 32                                                              */
+  int queries_len;                 /* meta tokens M, 16                                               */
+  int num_classes;                 /* 0 => no head                                                    */
+  int in_chans;                    /* 3                                                               */
+  int backbone;                    /* 0: classification model; 1: mmseg/mmdet/CD backbone copies
+                                      (S-stage does not update meta tokens, returns 4 feature maps)   */
+} lmv_config;
+
+typedef struct lmv_tensor {
+  const void* data; /* device pointer, 16-byte aligned */
+  int64_t numel;
+  int dtype;        /* LMV_DTYPE_* */
+} lmv_tensor;
+
+typedef struct lmv_plan lmv_plan; /* opaque: packed-weight table + cached launch schedules */
+
+const char* lmv_last_error(void);
+int lmv_version(void);
+
+/* ---- whole-model path --------------------------------------------------------------------------
+ * Packed weights: the folded/bf16 tensors produced by lemevit_b200/pack.py, in the order documented
+ * there (and checked here tensor by tensor: count, numel, dtype).  The plan only stores the
+ * pointers; the caller keeps the buffers alive. */
+int lmv_packed_tensor_count(const lmv_config* cfg);
+int lmv_plan_create(const lmv_config* cfg, const lmv_tensor* packed, int n_packed, lmv_plan** out);
+void lmv_plan_destroy(lmv_plan* plan);
+/* images processed per pass through the network (0 = whole batch at once); smaller chunks keep the
+ * producer->consumer activations L2-resident. */
+int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
+/* bring-up switch: 1 routes every GEMM / attention through the plain SIMT cross-check kernels. */
+int lmv_plan_set_debug_simt(lmv_plan* plan, int enable);
+size_t lmv_workspace_bytes(const lmv_plan* plan, int batch, int H, int W);
+/* number of kernel launches one forward of this shape issues (for bench.py's gpu_launches). */
+int lmv_launch_count(lmv_plan* plan, int batch, int H, int W);
+
+/* replaces LeMeViT.forward (models/lemevit.py:831-836): x[B,in_chans,H,W] NCHW (bf16 or f32)
+ * -> logits[B,num_classes] (bf16 or f32, per logits_dtype). */
+int lmv_forward_cls(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,
+                    size_t workspace_bytes, void* logits, int logits_dtype, void* stream);
+/* replaces the backbone copies' forward (semantic_segmentation/.../lemevit.py:822-827):
+ * -> outs[k] = x after stage k+1 as contiguous NCHW [B, embed_dim[k+1], H/s, W/s], k = 0..3. */
+int lmv_forward_features(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,
+                         size_t workspace_bytes, void* const* outs, int n_outs, int out_dtype, void* stream);
+
+/* ---- per-kernel entry points (unit tests, ncu) --------------------------------------------------*/
+/* nn.Linear (+GELU) (+residual): out[M,N] = act(A[M,K] W[N,K]^T + bias) + residual.  tcgen05 path. */
+int lmv_linear(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, void* out,
+               int ldc, int M, int N, int K, int act_gelu, int out_dtype, int force_tile_n, void* stream);
+/* same contract on the SIMT cross-check kernel */
+int lmv_linear_simt(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
+                    void* out, int ldc, int M, int N, int K, int act_gelu, int out_dtype, void* stream);
+/* x + dwconv3x3(x) followed by LayerNorm without affine (models/lemevit.py:546,589,619 + :513).
+ * tokens: [B, T, C] bf16, the first N = H*W rows of each image are the H x W map, rows N..T-1 (meta
+ * tokens) get LayerNorm only.  resid_out (nullable) receives x + dw(x); norm_out the normalised rows. */
+int lmv_posembed_layernorm(const void* tokens, const float* dw_weight /*[9][C], centre tap +1*/,
+                           const float* dw_bias, void* resid_out, void* norm_out, int B, int H, int W, int T, int C,
+                           float eps, void* stream);
+/* LayerNorm over rows [R, C] bf16; gamma/beta nullable (no affine); optional GELU afterwards;
+ * out row r -> (r / grp_rows) * grp_stride + grp_off + r % grp_rows when grp_rows > 0. */
+int lmv_layernorm(const void* in, void* out, const float* gamma, const float* beta, int R, int C, float eps,
+                  int act_gelu, int grp_rows, int grp_stride, int grp_off, void* stream);
+/* softmax(scale * Q K^T) V per (image, head), head_dim 32.  Element (b, row, h, d) of Q lives at
+ * q + b*q_bs + row*q_rs + h*32 + d (strides in elements), likewise K, V, out.
+ * impl: 0 = best available (tcgen05 where implemented), 1 = SIMT cross-check kernel. */
+int lmv_attention(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
+                  long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
+                  float scale, int impl, void* stream);
+/* patch gather for the first stem conv 3x3/s2/p1 (models/lemevit.py:699): x NCHW (f32|bf16) ->
+ * out[B*Ho*Wo, Kp] bf16 with k = ci*9 + ky*3 + kx, zero padded to Kp = round_up(9*Cin, 8); the conv
+ * itself (+ folded BN + GELU, :700-701) is then lmv_linear on the tcgen05 GEMM. */
+int lmv_stem_im2col(const void* x, int x_dtype, void* out, int B, int Cin, int H, int W, void* stream);
+/* im2col for conv 3x3/s2/p1 on NHWC bf16 tokens [B, T, C] (first H*W rows): out[B*Ho*Wo, 9*C] */
+int lmv_im2col_3x3s2(const void* in, void* out, int B, int H, int W, int T, int C, void* stream);
+/* classification tail (models/lemevit.py:815-827): feat[b] = bn_scale*mean_n(x[b]) + bn_shift + mean_m(LN(c[b])) */
+int lmv_tail(const void* x, long long x_bs, int N, const void* c, long long c_bs, int M, int C, const float* bn_scale,
+             const float* bn_shift, const float* ln_gamma, const float* ln_beta, float eps, void* feat, int B,
+             void* stream);
+/* token-major [B, T, C] bf16 (first H*W rows) -> NCHW [B, C, H, W] (bf16 or f32) */
+int lmv_tokens_to_nchw(const void* tokens, void* out, int B, int H, int W, int T, int C, int out_dtype,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEMEVIT_B200_H_ */

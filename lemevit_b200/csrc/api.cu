@@ -1,0 +1,768 @@
+// C ABI (include/lemevit_b200.h): plan = packed-weight table + cached launch schedules; the whole
+// forward of LeMeViT (reference models/lemevit.py:809-836 and the backbone copies' forward,
+// semantic_segmentation/mmseg/models/backbones/lemevit.py:800-827) is a list of kernel launches on
+// the caller's stream, built once per (batch, H, W, workspace) and replayed afterwards — which also
+// makes it CUDA-graph capturable by the host.
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <tuple>
+#include <vector>
+
+#include "common.h"
+#include "kernels.h"
+
+namespace lmv {
+
+// ------------------------------------------------------------------------------------------------
+// error reporting / driver entry point
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(LMV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdims[5], gstrides[5];
+  cuuint32_t gbox[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstrides[i - 1] = strides_bytes[i - 1];
+  }
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides,
+                  gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu] stride %llu box [%u,%u]",
+             (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0);
+    return fail(LMV_ERR_CUDA, buf);
+  }
+  return LMV_OK;
+}
+
+int device_sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct BlockW {
+  const float *dw_w, *dw_b;
+  // 'C': a = q, b = kv, p1 = proj.  'D': a = qkv1, b = qkv2, p1 = proj_x, p2 = proj_c.  'S': a = qkv, p1 = proj.
+  const bf16 *wa, *wb, *wp1, *wp2;
+  const float *ba, *bb, *bp1, *bp2;
+  const bf16 *w1, *w2;
+  const float *b1, *b2;
+};
+struct StageW {
+  const bf16* ds_w = nullptr;
+  const float* ds_b = nullptr;
+  const bf16 *md_w0 = nullptr, *md_w3 = nullptr;
+  const float *md_b0 = nullptr, *md_g1 = nullptr, *md_be1 = nullptr, *md_b3 = nullptr, *md_g4 = nullptr, *md_be4 = nullptr;
+  std::vector<BlockW> blocks;
+};
+
+typedef std::function<int(cudaStream_t)> Launch;
+
+struct IoSlots {
+  const void* x = nullptr;
+  void* logits = nullptr;
+  void* outs[LMV_MAX_STAGES] = {nullptr};
+};
+
+struct Schedule {
+  std::vector<Launch> ops;
+  std::unique_ptr<IoSlots> io{new IoSlots()};
+};
+
+}  // namespace lmv
+
+struct lmv_plan {
+  lmv_config cfg;
+  const lmv::bf16 *stem1_w, *stem2_w, *c0_init, *head_w;
+  const float *stem1_b, *stem2_b, *bn_scale, *bn_shift, *lnc_g, *lnc_b, *head_b;
+  std::vector<lmv::StageW> stages;
+  int chunk = 0;
+  int debug_simt = 0;
+  std::map<std::tuple<int, int, int, const void*, int, int, int>, std::unique_ptr<lmv::Schedule>> cache;
+};
+
+namespace lmv {
+
+static inline int kp0(const lmv_config& c) { return ((c.in_chans * 9 + 7) / 8) * 8; }
+
+// walks the packed-tensor order; when `t` is null only counts
+struct PackWalker {
+  const lmv_tensor* t;
+  int n, i = 0;
+  std::string err;
+  const void* take(int64_t numel, int dtype, const char* what) {
+    if (!t) { ++i; return nullptr; }
+    if (i >= n) { if (err.empty()) err = std::string("packed weights: missing tensor ") + what; ++i; return nullptr; }
+    const lmv_tensor& e = t[i];
+    if (err.empty()) {
+      char buf[200];
+      if (e.numel != numel || e.dtype != dtype) {
+        snprintf(buf, sizeof(buf), "packed weights: entry %d (%s) expects numel %lld dtype %d, got numel %lld dtype %d", i,
+                 what, (long long)numel, dtype, (long long)e.numel, e.dtype);
+        err = buf;
+      } else if (!e.data || (reinterpret_cast<uintptr_t>(e.data) & 15)) {
+        snprintf(buf, sizeof(buf), "packed weights: entry %d (%s) is null or not 16-byte aligned", i, what);
+        err = buf;
+      }
+    }
+    ++i;
+    return e.data;
+  }
+  const bf16* h(int64_t numel, const char* what) { return static_cast<const bf16*>(take(numel, LMV_DTYPE_BF16, what)); }
+  const float* f(int64_t numel, const char* what) { return static_cast<const float*>(take(numel, LMV_DTYPE_F32, what)); }
+};
+
+static int validate_config(const lmv_config& c) {
+  LMV_REQUIRE(c.num_stages >= 1 && c.num_stages <= LMV_MAX_STAGES, "config: num_stages out of range");
+  LMV_REQUIRE(c.head_dim == 32, "config: only head_dim == 32 is implemented (all published variants)");
+  LMV_REQUIRE(c.queries_len > 0 && c.queries_len % 8 == 0 && c.queries_len <= 128, "config: queries_len must be a multiple of 8, <= 128");
+  LMV_REQUIRE(c.in_chans >= 1, "config: in_chans");
+  for (int i = 0; i < c.num_stages; ++i) {
+    // reference error conventions: AssertionError on dim % num_heads (models/lemevit.py:168,233,437)
+    LMV_REQUIRE(c.embed_dim[i] > 0 && c.embed_dim[i] % c.head_dim == 0, "config: dim not divisible by num_heads");
+    LMV_REQUIRE(c.embed_dim[i] <= 512, "config: embed_dim > 512 not implemented");
+    LMV_REQUIRE(c.mlp_hidden[i] > 0 && c.mlp_hidden[i] % 8 == 0, "config: mlp hidden must be a multiple of 8");
+    LMV_REQUIRE(c.depth[i] >= 0, "config: depth");
+    if (!(c.attn_type[i] == 'C' || c.attn_type[i] == 'D' || c.attn_type[i] == 'S'))
+      return fail(LMV_ERR_UNSUPPORTED, "Attention type does not exit");  // reference message models/lemevit.py:660
+  }
+  LMV_REQUIRE(c.embed_dim[0] % 16 == 0, "config: embed_dim[0] must be a multiple of 16");
+  return LMV_OK;
+}
+
+static void walk(const lmv_config& c, PackWalker& w, lmv_plan* plan) {
+  const int C0 = c.embed_dim[0], M = c.queries_len;
+  const bf16* p;
+  const float* q;
+  p = w.h((int64_t)(C0 / 2) * kp0(c), "stem1_w"); if (plan) plan->stem1_w = p;
+  q = w.f(C0 / 2, "stem1_b"); if (plan) plan->stem1_b = q;
+  p = w.h((int64_t)C0 * 9 * (C0 / 2), "stem2_w"); if (plan) plan->stem2_w = p;
+  q = w.f(C0, "stem2_b"); if (plan) plan->stem2_b = q;
+  p = w.h((int64_t)M * C0, "c0_init"); if (plan) plan->c0_init = p;
+  if (plan) plan->stages.resize(c.num_stages);
+  for (int i = 0; i < c.num_stages; ++i) {
+    StageW tmp;
+    StageW& s = plan ? plan->stages[i] : tmp;
+    const int C = c.embed_dim[i], Hd = c.mlp_hidden[i];
+    if (i > 0) {
+      const int Cp = c.embed_dim[i - 1];
+      if (c.attn_type[i - 1] != 'C') {
+        s.ds_w = w.h((int64_t)C * 9 * Cp, "ds_w");
+        s.ds_b = w.f(C, "ds_b");
+      }
+      s.md_w0 = w.h((int64_t)4 * Cp * Cp, "md_w0");
+      s.md_b0 = w.f(4 * Cp, "md_b0");
+      s.md_g1 = w.f(4 * Cp, "md_g1");
+      s.md_be1 = w.f(4 * Cp, "md_be1");
+      s.md_w3 = w.h((int64_t)C * 4 * Cp, "md_w3");
+      s.md_b3 = w.f(C, "md_b3");
+      s.md_g4 = w.f(C, "md_g4");
+      s.md_be4 = w.f(C, "md_be4");
+    }
+    s.blocks.resize(c.depth[i]);
+    for (int j = 0; j < c.depth[i]; ++j) {
+      BlockW& b = s.blocks[j];
+      memset(&b, 0, sizeof(b));
+      b.dw_w = w.f(9 * C, "dw_w");
+      b.dw_b = w.f(C, "dw_b");
+      switch (c.attn_type[i]) {
+        case 'C':
+          b.wa = w.h((int64_t)C * C, "q_w"); b.ba = w.f(C, "q_b");
+          b.wb = w.h((int64_t)2 * C * C, "kv_w"); b.bb = w.f(2 * C, "kv_b");
+          b.wp1 = w.h((int64_t)C * C, "proj_w"); b.bp1 = w.f(C, "proj_b");
+          break;
+        case 'D':
+          b.wa = w.h((int64_t)3 * C * C, "qkv1_w"); b.ba = w.f(3 * C, "qkv1_b");
+          b.wb = w.h((int64_t)3 * C * C, "qkv2_w"); b.bb = w.f(3 * C, "qkv2_b");
+          b.wp1 = w.h((int64_t)C * C, "proj_x_w"); b.bp1 = w.f(C, "proj_x_b");
+          b.wp2 = w.h((int64_t)C * C, "proj_c_w"); b.bp2 = w.f(C, "proj_c_b");
+          break;
+        default:
+          b.wa = w.h((int64_t)3 * C * C, "qkv_w"); b.ba = w.f(3 * C, "qkv_b");
+          b.wp1 = w.h((int64_t)C * C, "proj_w"); b.bp1 = w.f(C, "proj_b");
+      }
+      b.w1 = w.h((int64_t)Hd * C, "mlp0_w"); b.b1 = w.f(Hd, "mlp0_b");
+      b.w2 = w.h((int64_t)C * Hd, "mlp3_w"); b.b2 = w.f(C, "mlp3_b");
+    }
+  }
+  if (!c.backbone) {
+    const int CL = c.embed_dim[c.num_stages - 1];
+    q = w.f(CL, "bn_scale"); if (plan) plan->bn_scale = q;
+    q = w.f(CL, "bn_shift"); if (plan) plan->bn_shift = q;
+    q = w.f(CL, "norm_c_g"); if (plan) plan->lnc_g = q;
+    q = w.f(CL, "norm_c_b"); if (plan) plan->lnc_b = q;
+    if (c.num_classes > 0) {
+      p = w.h((int64_t)c.num_classes * CL, "head_w"); if (plan) plan->head_w = p;
+      q = w.f(c.num_classes, "head_b"); if (plan) plan->head_b = q;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry + workspace
+// ------------------------------------------------------------------------------------------------
+struct Geo {
+  int H[LMV_MAX_STAGES], W[LMV_MAX_STAGES], N[LMV_MAX_STAGES], T[LMV_MAX_STAGES];
+  bool unified[LMV_MAX_STAGES], c_alive[LMV_MAX_STAGES];
+  int H1, W1;  // after the first stem conv
+};
+
+static int geometry(const lmv_config& c, int H, int W, Geo* g) {
+  LMV_REQUIRE(H >= 4 && W >= 4, "input smaller than 4x4");
+  g->H1 = (H + 1) / 2; g->W1 = (W + 1) / 2;
+  int h = (g->H1 + 1) / 2, w = (g->W1 + 1) / 2;
+  // meta tokens matter at stage i iff some stage >= i consumes them
+  // (backbone copies: 'S' blocks leave c untouched, so c is dead after the last C/D stage)
+  bool alive = !c.backbone;
+  for (int i = c.num_stages - 1; i >= 0; --i) {
+    if (c.attn_type[i] != 'S') alive = true;
+    g->c_alive[i] = alive;
+  }
+  for (int i = 0; i < c.num_stages; ++i) {
+    if (i > 0 && c.attn_type[i - 1] != 'C') { h = (h + 1) / 2; w = (w + 1) / 2; }
+    g->H[i] = h; g->W[i] = w; g->N[i] = h * w;
+    g->unified[i] = (c.attn_type[i] == 'S') && !c.backbone;
+    g->T[i] = g->N[i] + (g->unified[i] ? c.queries_len : 0);
+    if (i > 0 && c.attn_type[i - 1] == 'C' && g->unified[i])
+      return fail(LMV_ERR_UNSUPPORTED, "an 'S' stage directly after a 'C' stage is not implemented");
+  }
+  return LMV_OK;
+}
+
+struct WsLayout {
+  size_t patches, stem1, x0, x1, xn, qkv, hid, ca, cb, cn, cqkv, chid, ctmp, feat, total;
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+static void ws_layout(const lmv_config& c, const Geo& g, int B, WsLayout* L) {
+  const int C0 = c.embed_dim[0], M = c.queries_len;
+  size_t patches = (size_t)B * g.H1 * g.W1 * kp0(c);
+  patches = std::max(patches, (size_t)B * g.N[0] * 9 * (C0 / 2));
+  size_t x = 0, qkv = 0, hid = 0, cmax = 0, chid = 0;
+  for (int i = 0; i < c.num_stages; ++i) {
+    const size_t rows = (size_t)B * g.T[i];
+    x = std::max(x, rows * c.embed_dim[i]);
+    qkv = std::max(qkv, rows * 3 * c.embed_dim[i]);
+    hid = std::max(hid, rows * c.mlp_hidden[i]);
+    cmax = std::max(cmax, (size_t)c.embed_dim[i]);
+    chid = std::max(chid, (size_t)c.mlp_hidden[i]);
+    if (i > 0) {
+      chid = std::max(chid, (size_t)4 * c.embed_dim[i - 1]);
+      if (c.attn_type[i - 1] != 'C') patches = std::max(patches, (size_t)B * g.N[i] * 9 * c.embed_dim[i - 1]);
+    }
+  }
+  size_t off = 0;
+  auto take = [&](size_t elems) { size_t o = off; off += align_up(elems * 2); return o; };
+  L->patches = take(patches);
+  L->stem1 = take((size_t)B * g.H1 * g.W1 * (C0 / 2));
+  L->x0 = take(x); L->x1 = take(x); L->xn = take(x);
+  L->qkv = take(qkv); L->hid = take(hid);
+  const size_t crow = (size_t)B * M;
+  L->ca = take(crow * cmax); L->cb = take(crow * cmax); L->cn = take(crow * cmax); L->ctmp = take(crow * cmax);
+  L->cqkv = take(crow * 3 * cmax); L->chid = take(crow * chid);
+  L->feat = take((size_t)B * cmax);
+  L->total = off;
+}
+
+// ------------------------------------------------------------------------------------------------
+// schedule builder
+// ------------------------------------------------------------------------------------------------
+struct Builder {
+  lmv_plan* plan;
+  Schedule* sc;
+  int rc = LMV_OK;
+  bool simt;
+
+  void gemm(GemmArgs a) {
+    if (rc) return;
+    if (simt) {
+      sc->ops.push_back([a](cudaStream_t s) { return gemm_simt_run(a, s); });
+      return;
+    }
+    GemmOp op;
+    rc = gemm_prepare(a, &op);
+    if (rc) return;
+    sc->ops.push_back([op](cudaStream_t s) { return gemm_run(op, s); });
+  }
+  void linear(const bf16* A, int lda, const bf16* Wt, const float* bias, int M, int N, int K, bf16* out, int ldc,
+              int gelu = 0, const bf16* resid = nullptr, int grp_rows = 0, int grp_stride = 0) {
+    GemmArgs a;
+    a.A = A; a.lda = lda; a.W = Wt; a.ldw = K; a.M = M; a.N = N; a.K = K;
+    a.bias = bias; a.act = gelu; a.residual = resid; a.out = out; a.ldc = ldc;
+    a.grp_rows = grp_rows; a.grp_stride = grp_stride;
+    gemm(a);
+  }
+  void posln(const bf16* tok, const float* dw_w, const float* dw_b, bf16* resid, bf16* norm, int B, int H, int W, int T,
+             int C) {
+    if (rc) return;
+    PosLnArgs a{tok, dw_w, dw_b, resid, norm, B, H, W, T, C, 1e-6f};
+    sc->ops.push_back([a](cudaStream_t s) { return posembed_ln_run(a, s); });
+  }
+  void ln(const bf16* in, bf16* out, const float* g, const float* b, int R, int C, float eps, int gelu = 0,
+          int grp_rows = 0, int grp_stride = 0, int grp_off = 0) {
+    if (rc) return;
+    LnArgs a{in, out, g, b, R, C, eps, gelu, grp_rows, grp_stride, grp_off};
+    sc->ops.push_back([a](cudaStream_t s) { return layernorm_run(a, s); });
+  }
+  void attn(const bf16* q, long long q_bs, int q_rs, const bf16* k, const bf16* v, long long kv_bs, int kv_rs, bf16* out,
+            long long o_bs, int o_rs, int B, int heads, int Lq, int Lk, float scale) {
+    if (rc) return;
+    AttnArgs a;
+    a.q = q; a.k = k; a.v = v; a.out = out;
+    a.q_bs = q_bs; a.k_bs = kv_bs; a.v_bs = kv_bs; a.o_bs = o_bs;
+    a.q_rs = q_rs; a.k_rs = kv_rs; a.v_rs = kv_rs; a.o_rs = o_rs;
+    a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
+    const bool tc = !simt && attention_tc_supported(a);
+    sc->ops.push_back([a, tc](cudaStream_t s) { return tc ? attention_tc_run(a, s) : attention_simt_run(a, s); });
+  }
+};
+
+static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int x_dtype, int out_dtype, Schedule* sc) {
+  const lmv_config& c = plan->cfg;
+  Geo g;
+  int rc = geometry(c, H, W, &g);
+  if (rc) return rc;
+  WsLayout L;
+  ws_layout(c, g, B, &L);
+  auto P = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
+  bf16 *patches = P(L.patches), *stem1 = P(L.stem1), *xn = P(L.xn), *qkv = P(L.qkv), *hid = P(L.hid);
+  bf16* xbuf[2] = {P(L.x0), P(L.x1)};
+  bf16* cbuf[2] = {P(L.ca), P(L.cb)};
+  bf16 *cn = P(L.cn), *ctmp = P(L.ctmp), *cqkv = P(L.cqkv), *chid = P(L.chid), *feat = P(L.feat);
+  IoSlots* io = sc->io.get();
+  Builder b{plan, sc, LMV_OK, plan->debug_simt != 0};
+  const int M = c.queries_len, C0 = c.embed_dim[0], S = c.num_stages;
+
+  // ---- stem (models/lemevit.py:698-704): conv3x3/s2 + BN + GELU + conv3x3/s2 + BN, both on the GEMM
+  {
+    StemArgs sa{nullptr, x_dtype, patches, B, c.in_chans, H, W};
+    sc->ops.push_back([sa, io](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_im2col_run(a, s); });
+    b.linear(patches, kp0(c), plan->stem1_w, plan->stem1_b, B * g.H1 * g.W1, C0 / 2, kp0(c), stem1, C0 / 2, /*gelu=*/1);
+    Im2colArgs ia{stem1, patches, B, g.H1, g.W1, g.H1 * g.W1, C0 / 2};
+    sc->ops.push_back([ia](cudaStream_t s) { return im2col_run(ia, s); });
+  }
+  int cur = 0, ccur = 0;
+  {
+    const bool uni = g.unified[0];
+    b.linear(patches, 9 * (C0 / 2), plan->stem2_w, plan->stem2_b, B * g.N[0], C0, 9 * (C0 / 2), xbuf[cur], C0, 0, nullptr,
+             uni ? g.N[0] : 0, uni ? g.T[0] : 0);
+  }
+
+  for (int i = 0; i < S && !b.rc; ++i) {
+    const StageW& sw = plan->stages[i];
+    const int C = c.embed_dim[i], Hd = c.mlp_hidden[i], N = g.N[i], T = g.T[i], heads = C / c.head_dim;
+    const bool uni = g.unified[i];
+    const char kind = c.attn_type[i];
+    // ---- x downsample (models/lemevit.py:711-717)
+    const bf16* c_prev_unified = nullptr;  // where the previous stage left c if it was unified
+    if (i > 0) {
+      const int Cp = c.embed_dim[i - 1];
+      if (g.unified[i - 1]) c_prev_unified = xbuf[cur];
+      if (c.attn_type[i - 1] != 'C') {
+        Im2colArgs ia{xbuf[cur], patches, B, g.H[i - 1], g.W[i - 1], g.T[i - 1], Cp};
+        sc->ops.push_back([ia](cudaStream_t s) { return im2col_run(ia, s); });
+        b.linear(patches, 9 * Cp, sw.ds_w, sw.ds_b, B * N, C, 9 * Cp, xbuf[cur ^ 1], C, 0, nullptr, uni ? N : 0,
+                 uni ? T : 0);
+        cur ^= 1;
+      }
+    }
+    // ---- meta-token path into this stage (models/lemevit.py:729-745, :833)
+    if (g.c_alive[i]) {
+      if (i == 0) {
+        // meta_ds_0(meta_tokens) is batch-invariant: folded at pack time into c0_init
+        bf16* dst = uni ? xbuf[cur] + (size_t)N * C : cbuf[ccur];
+        const long long bs = uni ? (long long)T * C : (long long)M * C;
+        const bf16* src = plan->c0_init;
+        sc->ops.push_back([src, dst, M, C, B, bs](cudaStream_t s) { return broadcast_rows_run(src, dst, M, C, B, bs, s); });
+      } else {
+        const int Cp = c.embed_dim[i - 1];
+        const bf16* cprev = cbuf[ccur];
+        if (c_prev_unified) {
+          const bf16* src = c_prev_unified;
+          bf16* dst = cbuf[ccur];
+          const int Np = g.N[i - 1], Tp = g.T[i - 1];
+          sc->ops.push_back([src, dst, B, M, Cp, Np, Tp](cudaStream_t s) { return gather_rows_run(src, dst, B * M, Cp, M, Tp, Np, s); });
+        }
+        b.linear(cprev, Cp, sw.md_w0, sw.md_b0, B * M, 4 * Cp, Cp, chid, 4 * Cp);
+        b.ln(chid, chid, sw.md_g1, sw.md_be1, B * M, 4 * Cp, 1e-5f, /*gelu=*/1);
+        b.linear(chid, 4 * Cp, sw.md_w3, sw.md_b3, B * M, C, 4 * Cp, ctmp, C);
+        if (uni) b.ln(ctmp, xbuf[cur], sw.md_g4, sw.md_be4, B * M, C, 1e-5f, 0, M, T, N);
+        else { b.ln(ctmp, cbuf[ccur ^ 1], sw.md_g4, sw.md_be4, B * M, C, 1e-5f); ccur ^= 1; }
+      }
+    }
+    bf16* cc = cbuf[ccur];
+    // ---- blocks
+    for (int j = 0; j < c.depth[i] && !b.rc; ++j) {
+      const BlockW& bw = sw.blocks[j];
+      if (kind == 'C') {
+        // forward_with_c (models/lemevit.py:584-613) + CrossAttention (:477-486); x is returned unchanged
+        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, nullptr, xn, B, g.H[i], g.W[i], T, C);
+        b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
+        b.linear(cn, C, bw.wa, bw.ba, B * M, C, C, cqkv, C);
+        b.linear(xn, C, bw.wb, bw.bb, B * N, 2 * C, C, qkv, 2 * C);
+        b.attn(cqkv, (long long)M * C, C, qkv, qkv + C, (long long)N * 2 * C, 2 * C, cn, (long long)M * C, C, B, heads, M, N,
+               1.0f / sqrtf((float)c.head_dim));
+        b.linear(cn, C, bw.wp1, bw.bp1, B * M, C, C, cc, C, 0, cc);
+        b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
+        b.linear(cn, C, bw.w1, bw.b1, B * M, Hd, C, chid, Hd, 1);
+        b.linear(chid, Hd, bw.w2, bw.b2, B * M, C, Hd, cc, C, 0, cc);
+      } else if (kind == 'D') {
+        // forward_with_xc (models/lemevit.py:542-582) + DualCrossAttention (:252-256,288-302)
+        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], xn, B, g.H[i], g.W[i], T, C);
+        cur ^= 1;
+        bf16* x = xbuf[cur];
+        b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
+        b.linear(xn, C, bw.wa, bw.ba, B * N, 3 * C, C, qkv, 3 * C);
+        b.linear(cn, C, bw.wb, bw.bb, B * M, 3 * C, C, cqkv, 3 * C);
+        const double scale = 1.0 / std::sqrt((double)C);                       // :235 full channel dim
+        const double scale_x = std::log((double)M) / std::log((double)N) * scale;  // :255 math.log(M, N)
+        b.attn(qkv, (long long)N * 3 * C, 3 * C, cqkv + C, cqkv + 2 * C, (long long)M * 3 * C, 3 * C, xn, (long long)N * C, C,
+               B, heads, N, M, (float)scale_x);
+        b.attn(cqkv, (long long)M * 3 * C, 3 * C, qkv + C, qkv + 2 * C, (long long)N * 3 * C, 3 * C, cn, (long long)M * C, C,
+               B, heads, M, N, (float)scale);
+        b.linear(xn, C, bw.wp1, bw.bp1, B * N, C, C, x, C, 0, x);
+        b.linear(cn, C, bw.wp2, bw.bp2, B * M, C, C, cc, C, 0, cc);
+        b.posln(x, nullptr, nullptr, nullptr, xn, B, g.H[i], g.W[i], T, C);
+        b.linear(xn, C, bw.w1, bw.b1, B * N, Hd, C, hid, Hd, 1);
+        b.linear(hid, Hd, bw.w2, bw.b2, B * N, C, Hd, x, C, 0, x);
+        b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
+        b.linear(cn, C, bw.w1, bw.b1, B * M, Hd, C, chid, Hd, 1);
+        b.linear(chid, Hd, bw.w2, bw.b2, B * M, C, Hd, cc, C, 0, cc);
+      } else {
+        // forward_with_x (models/lemevit.py:615-650) + StandardAttention (:199-205); image and meta tokens
+        // share norm1/attn/norm2/mlp, so they travel in one [B, N+M, C] buffer (classification model only)
+        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], xn, B, g.H[i], g.W[i], T, C);
+        cur ^= 1;
+        bf16* x = xbuf[cur];
+        b.linear(xn, C, bw.wa, bw.ba, B * T, 3 * C, C, qkv, 3 * C);
+        const float sc_ = 1.0f / sqrtf((float)c.head_dim);
+        b.attn(qkv, (long long)T * 3 * C, 3 * C, qkv + C, qkv + 2 * C, (long long)T * 3 * C, 3 * C, xn, (long long)T * C, C, B,
+               heads, N, N, sc_);
+        if (uni) {
+          const size_t ro = (size_t)N * 3 * C;
+          b.attn(qkv + ro, (long long)T * 3 * C, 3 * C, qkv + ro + C, qkv + ro + 2 * C, (long long)T * 3 * C, 3 * C,
+                 xn + (size_t)N * C, (long long)T * C, C, B, heads, M, M, sc_);
+        }
+        b.linear(xn, C, bw.wp1, bw.bp1, B * T, C, C, x, C, 0, x);
+        b.posln(x, nullptr, nullptr, nullptr, xn, B, g.H[i], g.W[i], T, C);
+        b.linear(xn, C, bw.w1, bw.b1, B * T, Hd, C, hid, Hd, 1);
+        b.linear(hid, Hd, bw.w2, bw.b2, B * T, C, Hd, x, C, 0, x);
+      }
+    }
+    // ---- backbone outputs: x after stages 1..S-1 as NCHW (semantic_segmentation/.../lemevit.py:800-820)
+    if (c.backbone && i >= 1) {
+      ToNchwArgs ta{xbuf[cur], nullptr, B, g.H[i], g.W[i], T, C, out_dtype};
+      const int slot = i - 1;
+      sc->ops.push_back([ta, io, slot](cudaStream_t s) { ToNchwArgs a = ta; a.out = io->outs[slot]; return tokens_to_nchw_run(a, s); });
+    }
+  }
+  if (b.rc) return b.rc;
+  if (!c.backbone) {
+    // ---- tail + head (models/lemevit.py:815-836)
+    const int i = S - 1, C = c.embed_dim[i];
+    TailArgs ta;
+    ta.x = xbuf[cur]; ta.x_bs = (long long)g.T[i] * C; ta.N = g.N[i];
+    if (g.unified[i]) { ta.c = xbuf[cur] + (size_t)g.N[i] * C; ta.c_bs = (long long)g.T[i] * C; }
+    else { ta.c = cbuf[ccur]; ta.c_bs = (long long)M * C; }
+    ta.M = M; ta.C = C;
+    ta.bn_scale = plan->bn_scale; ta.bn_shift = plan->bn_shift; ta.ln_gamma = plan->lnc_g; ta.ln_beta = plan->lnc_b;
+    ta.eps = 1e-5f; ta.feat = feat; ta.B = B;
+    sc->ops.push_back([ta](cudaStream_t s) { return tail_run(ta, s); });
+    if (c.num_classes > 0) {
+      GemmArgs ga;
+      ga.A = feat; ga.lda = C; ga.W = plan->head_w; ga.ldw = C; ga.M = B; ga.N = c.num_classes; ga.K = C;
+      ga.bias = plan->head_b; ga.ldc = c.num_classes; ga.out_fp32 = (out_dtype == LMV_DTYPE_F32);
+      const bool simt = plan->debug_simt != 0;
+      // the logits pointer changes per call/chunk: the tensor maps only cover A and W, so patch `out`
+      if (simt) {
+        sc->ops.push_back([ga, io](cudaStream_t s) { GemmArgs a = ga; a.out = io->logits; return gemm_simt_run(a, s); });
+      } else {
+        ga.out = feat;  // placeholder for validation; replaced at launch
+        GemmOp op;
+        rc = gemm_prepare(ga, &op);
+        if (rc) return rc;
+        sc->ops.push_back([op, io](cudaStream_t s) { GemmOp o = op; o.p.out = io->logits; return gemm_run(o, s); });
+      }
+    } else {
+      return fail(LMV_ERR_UNSUPPORTED, "num_classes == 0 (features only) is not implemented for the classification model");
+    }
+  }
+  return LMV_OK;
+}
+
+static int get_schedule(lmv_plan* plan, int B, int H, int W, void* ws, size_t ws_bytes, int x_dtype, int out_dtype,
+                        Schedule** out) {
+  Geo g;
+  int rc = geometry(plan->cfg, H, W, &g);
+  if (rc) return rc;
+  WsLayout L;
+  ws_layout(plan->cfg, g, B, &L);
+  if (ws_bytes < L.total) return fail(LMV_ERR_INVALID, "workspace too small: need " + std::to_string(L.total) + " bytes");
+  LMV_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  auto key = std::make_tuple(B, H, W, (const void*)ws, x_dtype, out_dtype, plan->debug_simt);
+  auto it = plan->cache.find(key);
+  if (it == plan->cache.end()) {
+    if (plan->cache.size() >= 16) plan->cache.clear();
+    std::unique_ptr<Schedule> sc(new Schedule());
+    rc = build_schedule(plan, B, H, W, static_cast<uint8_t*>(ws), x_dtype, out_dtype, sc.get());
+    if (rc) return rc;
+    it = plan->cache.emplace(key, std::move(sc)).first;
+  }
+  *out = it->second.get();
+  return LMV_OK;
+}
+
+static int run_forward(lmv_plan* plan, const void* x, int x_dtype, int B, int H, int W, void* ws, size_t ws_bytes,
+                       void* logits, void* const* outs, int n_outs, int out_dtype, cudaStream_t stream) {
+  LMV_REQUIRE(plan && x && B > 0, "forward: null plan/input or empty batch");
+  LMV_REQUIRE(x_dtype == LMV_DTYPE_BF16 || x_dtype == LMV_DTYPE_F32, "forward: x dtype");
+  LMV_REQUIRE(out_dtype == LMV_DTYPE_BF16 || out_dtype == LMV_DTYPE_F32, "forward: output dtype");
+  const lmv_config& c = plan->cfg;
+  const int chunk = (plan->chunk > 0 && plan->chunk < B) ? plan->chunk : B;
+  const size_t xe = x_dtype == LMV_DTYPE_F32 ? 4 : 2, oe = out_dtype == LMV_DTYPE_F32 ? 4 : 2;
+  Geo g;
+  int rc = geometry(c, H, W, &g);
+  if (rc) return rc;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int bc = std::min(chunk, B - b0);
+    Schedule* sc = nullptr;
+    rc = get_schedule(plan, bc, H, W, ws, ws_bytes, x_dtype, out_dtype, &sc);
+    if (rc) return rc;
+    sc->io->x = static_cast<const uint8_t*>(x) + (size_t)b0 * c.in_chans * H * W * xe;
+    if (logits) sc->io->logits = static_cast<uint8_t*>(logits) + (size_t)b0 * c.num_classes * oe;
+    for (int k = 0; k < n_outs; ++k)
+      sc->io->outs[k] = static_cast<uint8_t*>(outs[k]) + (size_t)b0 * c.embed_dim[k + 1] * g.N[k + 1] * oe;
+    for (auto& op : sc->ops) {
+      rc = op(stream);
+      if (rc) return rc;
+    }
+  }
+  return LMV_OK;
+}
+
+}  // namespace lmv
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+using namespace lmv;
+
+extern "C" {
+
+const char* lmv_last_error(void) { return g_err.c_str(); }
+int lmv_version(void) { return 100; }
+
+int lmv_packed_tensor_count(const lmv_config* cfg) {
+  if (!cfg) return fail(LMV_ERR_INVALID, "null config");
+  int rc = validate_config(*cfg);
+  if (rc) return rc;
+  PackWalker w{nullptr, 0};
+  walk(*cfg, w, nullptr);
+  return w.i;
+}
+
+int lmv_plan_create(const lmv_config* cfg, const lmv_tensor* packed, int n_packed, lmv_plan** out) {
+  if (!cfg || !packed || !out) return fail(LMV_ERR_INVALID, "plan_create: null argument");
+  int rc = validate_config(*cfg);
+  if (rc) return rc;
+  std::unique_ptr<lmv_plan> plan(new lmv_plan());
+  plan->cfg = *cfg;
+  plan->head_w = nullptr; plan->head_b = nullptr;
+  PackWalker w{packed, n_packed};
+  walk(*cfg, w, plan.get());
+  if (!w.err.empty()) return fail(LMV_ERR_INVALID, w.err);
+  if (w.i != n_packed) return fail(LMV_ERR_INVALID, "packed weights: expected " + std::to_string(w.i) + " tensors, got " + std::to_string(n_packed));
+  *out = plan.release();
+  return LMV_OK;
+}
+
+void lmv_plan_destroy(lmv_plan* plan) { delete plan; }
+
+int lmv_plan_set_chunk(lmv_plan* plan, int n) {
+  if (!plan || n < 0) return fail(LMV_ERR_INVALID, "set_chunk: bad argument");
+  plan->chunk = n;
+  return LMV_OK;
+}
+int lmv_plan_set_debug_simt(lmv_plan* plan, int enable) {
+  if (!plan) return fail(LMV_ERR_INVALID, "null plan");
+  plan->debug_simt = enable ? 1 : 0;
+  return LMV_OK;
+}
+
+size_t lmv_workspace_bytes(const lmv_plan* plan, int batch, int H, int W) {
+  if (!plan || batch <= 0) return 0;
+  Geo g;
+  if (geometry(plan->cfg, H, W, &g)) return 0;
+  const int chunk = (plan->chunk > 0 && plan->chunk < batch) ? plan->chunk : batch;
+  WsLayout L;
+  ws_layout(plan->cfg, g, chunk, &L);
+  return L.total;
+}
+
+int lmv_launch_count(lmv_plan* plan, int batch, int H, int W) {
+  if (!plan || batch <= 0) return fail(LMV_ERR_INVALID, "launch_count: bad argument");
+  const int chunk = (plan->chunk > 0 && plan->chunk < batch) ? plan->chunk : batch;
+  int total = 0;
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int bc = std::min(chunk, batch - b0);
+    for (auto& kv : plan->cache)
+      if (std::get<0>(kv.first) == bc && std::get<1>(kv.first) == H && std::get<2>(kv.first) == W) {
+        total += (int)kv.second->ops.size();
+        goto next;
+      }
+    return fail(LMV_ERR_INVALID, "launch_count: run a forward of this shape first");
+  next:;
+  }
+  return total;
+}
+
+int lmv_forward_cls(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,
+                    size_t workspace_bytes, void* logits, int logits_dtype, void* stream) {
+  if (!plan || plan->cfg.backbone) return fail(LMV_ERR_INVALID, "forward_cls: plan was created for the backbone variant");
+  if (!logits) return fail(LMV_ERR_INVALID, "forward_cls: null logits");
+  return run_forward(plan, x, x_dtype, batch, H, W, workspace, workspace_bytes, logits, nullptr, 0, logits_dtype,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int lmv_forward_features(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,
+                         size_t workspace_bytes, void* const* outs, int n_outs, int out_dtype, void* stream) {
+  if (!plan || !plan->cfg.backbone) return fail(LMV_ERR_INVALID, "forward_features: plan was created for the classification variant");
+  if (!outs || n_outs != plan->cfg.num_stages - 1) return fail(LMV_ERR_INVALID, "forward_features: expects num_stages-1 output maps");
+  for (int k = 0; k < n_outs; ++k)
+    if (!outs[k]) return fail(LMV_ERR_INVALID, "forward_features: null output");
+  return run_forward(plan, x, x_dtype, batch, H, W, workspace, workspace_bytes, nullptr, outs, n_outs, out_dtype,
+                     static_cast<cudaStream_t>(stream));
+}
+
+// ---- per-kernel entry points -------------------------------------------------------------------
+static GemmArgs make_gemm_args(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
+                               void* out, int ldc, int M, int N, int K, int act_gelu, int out_dtype) {
+  GemmArgs a;
+  a.A = static_cast<const bf16*>(A); a.lda = lda; a.W = static_cast<const bf16*>(W); a.ldw = ldw;
+  a.M = M; a.N = N; a.K = K; a.bias = bias; a.act = act_gelu ? 1 : 0;
+  a.residual = static_cast<const bf16*>(residual); a.out = out; a.ldc = ldc; a.out_fp32 = out_dtype == LMV_DTYPE_F32;
+  return a;
+}
+
+int lmv_linear(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, void* out,
+               int ldc, int M, int N, int K, int act_gelu, int out_dtype, int force_tile_n, void* stream) {
+  GemmArgs a = make_gemm_args(A, lda, W, ldw, bias, residual, out, ldc, M, N, K, act_gelu, out_dtype);
+  a.force_bn = force_tile_n;
+  GemmOp op;
+  int rc = gemm_prepare(a, &op);
+  if (rc) return rc;
+  return gemm_run(op, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_linear_simt(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
+                    void* out, int ldc, int M, int N, int K, int act_gelu, int out_dtype, void* stream) {
+  GemmArgs a = make_gemm_args(A, lda, W, ldw, bias, residual, out, ldc, M, N, K, act_gelu, out_dtype);
+  if (!a.A || !a.W || !a.out || M <= 0 || N <= 0 || K <= 0) return fail(LMV_ERR_INVALID, "linear_simt: bad argument");
+  return gemm_simt_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_posembed_layernorm(const void* tokens, const float* dw_weight, const float* dw_bias, void* resid_out,
+                           void* norm_out, int B, int H, int W, int T, int C, float eps, void* stream) {
+  if (!tokens || (!resid_out && !norm_out)) return fail(LMV_ERR_INVALID, "posembed_layernorm: null pointer");
+  PosLnArgs a{static_cast<const bf16*>(tokens), dw_weight, dw_bias, static_cast<bf16*>(resid_out),
+              static_cast<bf16*>(norm_out), B, H, W, T, C, eps};
+  return posembed_ln_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_layernorm(const void* in, void* out, const float* gamma, const float* beta, int R, int C, float eps,
+                  int act_gelu, int grp_rows, int grp_stride, int grp_off, void* stream) {
+  if (!in || !out || ((gamma == nullptr) != (beta == nullptr))) return fail(LMV_ERR_INVALID, "layernorm: bad pointers");
+  LnArgs a{static_cast<const bf16*>(in), static_cast<bf16*>(out), gamma, beta, R, C, eps, act_gelu, grp_rows, grp_stride, grp_off};
+  return layernorm_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_attention(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
+                  long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
+                  float scale, int impl, void* stream) {
+  if (!q || !k || !v || !out) return fail(LMV_ERR_INVALID, "attention: null pointer");
+  AttnArgs a;
+  a.q = static_cast<const bf16*>(q); a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v);
+  a.out = static_cast<bf16*>(out);
+  a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs; a.o_bs = o_bs;
+  a.q_rs = q_rs; a.k_rs = k_rs; a.v_rs = v_rs; a.o_rs = o_rs;
+  a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
+  if (impl == 0 && attention_tc_supported(a)) return attention_tc_run(a, static_cast<cudaStream_t>(stream));
+  if (impl == 2) return attention_tc_supported(a) ? attention_tc_run(a, static_cast<cudaStream_t>(stream))
+                                                  : fail(LMV_ERR_UNSUPPORTED, "attention: shape not supported by the tcgen05 kernel");
+  return attention_simt_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_stem_im2col(const void* x, int x_dtype, void* out, int B, int Cin, int H, int W, void* stream) {
+  if (!x || !out) return fail(LMV_ERR_INVALID, "stem_im2col: null pointer");
+  StemArgs a{x, x_dtype, static_cast<bf16*>(out), B, Cin, H, W};
+  return stem_im2col_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_im2col_3x3s2(const void* in, void* out, int B, int H, int W, int T, int C, void* stream) {
+  if (!in || !out) return fail(LMV_ERR_INVALID, "im2col: null pointer");
+  Im2colArgs a{static_cast<const bf16*>(in), static_cast<bf16*>(out), B, H, W, T, C};
+  return im2col_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_tail(const void* x, long long x_bs, int N, const void* c, long long c_bs, int M, int C, const float* bn_scale,
+             const float* bn_shift, const float* ln_gamma, const float* ln_beta, float eps, void* feat, int B,
+             void* stream) {
+  if (!x || !c || !feat || !bn_scale || !bn_shift || !ln_gamma || !ln_beta) return fail(LMV_ERR_INVALID, "tail: null pointer");
+  TailArgs a;
+  a.x = static_cast<const bf16*>(x); a.x_bs = x_bs; a.N = N; a.c = static_cast<const bf16*>(c); a.c_bs = c_bs; a.M = M;
+  a.C = C; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.ln_gamma = ln_gamma; a.ln_beta = ln_beta; a.eps = eps;
+  a.feat = static_cast<bf16*>(feat); a.B = B;
+  return tail_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_tokens_to_nchw(const void* tokens, void* out, int B, int H, int W, int T, int C, int out_dtype, void* stream) {
+  if (!tokens || !out) return fail(LMV_ERR_INVALID, "tokens_to_nchw: null pointer");
+  ToNchwArgs a{static_cast<const bf16*>(tokens), out, B, H, W, T, C, out_dtype};
+  return tokens_to_nchw_run(a, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

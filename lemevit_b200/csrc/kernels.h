@@ -1,0 +1,83 @@
+// Internal launchers of the non-GEMM kernels (tokens.cu, attention.cu).
+#pragma once
+#include "common.h"
+
+namespace lmv {
+
+struct PosLnArgs {
+  const bf16* tokens;   // [B, T, C]
+  const float* dw_w;    // [9][C] (centre tap already +1) or null => no conv (LayerNorm only)
+  const float* dw_b;    // [C]
+  bf16* resid_out;      // nullable, [B, T, C]
+  bf16* norm_out;       // nullable, [B, T, C]
+  int B, H, W, T, C;
+  float eps;
+};
+int posembed_ln_run(const PosLnArgs& a, cudaStream_t s);
+
+struct LnArgs {
+  const bf16* in;       // [R, C]
+  bf16* out;
+  const float* gamma;   // nullable
+  const float* beta;    // nullable
+  int R, C;
+  float eps;
+  int act_gelu;
+  int grp_rows, grp_stride, grp_off;  // output row remap (grp_rows == 0: identity)
+};
+int layernorm_run(const LnArgs& a, cudaStream_t s);
+
+struct AttnArgs {
+  const bf16 *q, *k, *v;
+  bf16* out;
+  long long q_bs, k_bs, v_bs, o_bs;  // per-image strides (elements)
+  int q_rs, k_rs, v_rs, o_rs;        // per-row strides (elements)
+  int B, heads, Lq, Lk;
+  float scale;
+};
+int attention_simt_run(const AttnArgs& a, cudaStream_t s);
+int attention_tc_run(const AttnArgs& a, cudaStream_t s);      // tcgen05 self/cross attention (attention.cu)
+bool attention_tc_supported(const AttnArgs& a);
+
+struct StemArgs {
+  const void* x;  // NCHW, f32 or bf16
+  int x_dtype;
+  bf16* out;      // patches [B*Ho*Wo, Kp], Kp = round_up(9*Cin, 8), k = ci*9 + ky*3 + kx
+  int B, Cin, H, W;
+};
+int stem_im2col_run(const StemArgs& a, cudaStream_t s);
+
+struct Im2colArgs {
+  const bf16* in;  // [B, T, C], first H*W rows of each image
+  bf16* out;       // [B*Ho*Wo, 9*C]
+  int B, H, W, T, C;
+};
+int im2col_run(const Im2colArgs& a, cudaStream_t s);
+
+struct TailArgs {
+  const bf16* x; long long x_bs; int N;
+  const bf16* c; long long c_bs; int M;
+  int C;
+  const float *bn_scale, *bn_shift, *ln_gamma, *ln_beta;
+  float eps;
+  bf16* feat;  // [B, C]
+  int B;
+};
+int tail_run(const TailArgs& a, cudaStream_t s);
+
+struct ToNchwArgs {
+  const bf16* tokens;  // [B, T, C]
+  void* out;           // [B, C, H, W]
+  int B, H, W, T, C, out_dtype;
+};
+int tokens_to_nchw_run(const ToNchwArgs& a, cudaStream_t s);
+
+// c[b, m, :] = c0[m, :]   (meta_tokens.repeat(B,1,1), models/lemevit.py:833, after the folded meta_ds_0)
+int broadcast_rows_run(const bf16* src, bf16* dst, int rows, int C, int B, long long dst_bs, cudaStream_t s);
+
+// dst[r, :] = src[(r / grp_rows) * grp_stride + grp_off + r % grp_rows, :]   (gather meta-token rows
+// out of a unified [B, N+M, C] token buffer)
+int gather_rows_run(const bf16* src, bf16* dst, int rows, int C, int grp_rows, int grp_stride, int grp_off,
+                    cudaStream_t s);
+
+}  // namespace lmv

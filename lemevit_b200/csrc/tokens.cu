@@ -1,0 +1,366 @@
+// Memory-bound kernels of the LeMeViT forward: positional depthwise conv + LayerNorm, LayerNorm,
+// im2col for the strided 3x3 convolutions (which then run on the tcgen05 GEMM), the classification
+// tail and the NCHW export of the backbone feature maps.  All activations are token-major
+// [B, T, C] bf16 (NHWC); the reference's NCHW<->token rearranges (models/lemevit.py:548,579) vanish.
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace lmv {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// x + dwconv3x3(x)  ->  LayerNorm (no affine; gamma/beta are folded into the consuming linear)
+// reference: LeMeBlock pos_embed (models/lemevit.py:510 at :546,589,619) + norm1 (:513)
+// one warp per token; lane l owns channel pairs l, l+32, ...  (C <= 512)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPairs = 8;
+
+__global__ void __launch_bounds__(256)
+posembed_ln_kernel(PosLnArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= (long long)a.B * a.T) return;
+  const int b = (int)(row / a.T), t = (int)(row % a.T);
+  const int C = a.C, npairs = C >> 1;
+  const bf16* img = a.tokens + (long long)b * a.T * C;
+  float2 val[kMaxPairs];
+  const bool conv = (a.dw_w != nullptr) && (t < a.H * a.W);
+  if (conv) {
+    const int y = t / a.W, x = t % a.W;
+#pragma unroll
+    for (int i = 0; i < kMaxPairs; ++i) {
+      const int p = lane + 32 * i;
+      val[i] = (p < npairs) ? __ldg(reinterpret_cast<const float2*>(a.dw_b) + p) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= a.H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= a.W) continue;
+        const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(img + (long long)(yy * a.W + xx) * C);
+        const float2* wt = reinterpret_cast<const float2*>(a.dw_w + (ky * 3 + kx) * C);
+#pragma unroll
+        for (int i = 0; i < kMaxPairs; ++i) {
+          const int p = lane + 32 * i;
+          if (p < npairs) {
+            const float2 v = __bfloat1622float2(src[p]);
+            const float2 w = __ldg(wt + p);
+            val[i].x = fmaf(v.x, w.x, val[i].x);
+            val[i].y = fmaf(v.y, w.y, val[i].y);
+          }
+        }
+      }
+    }
+  } else {
+    const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(img + (long long)t * C);
+#pragma unroll
+    for (int i = 0; i < kMaxPairs; ++i) {
+      const int p = lane + 32 * i;
+      val[i] = (p < npairs) ? __bfloat1622float2(src[p]) : make_float2(0.f, 0.f);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPairs; ++i) s += val[i].x + val[i].y;   // out-of-range pairs hold zeros
+  const float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPairs; ++i) {
+    if (lane + 32 * i < npairs) {
+      const float dx = val[i].x - mean, dy = val[i].y - mean;
+      ss += dx * dx + dy * dy;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)C + a.eps);
+  const long long off = row * C;
+#pragma unroll
+  for (int i = 0; i < kMaxPairs; ++i) {
+    const int p = lane + 32 * i;
+    if (p < npairs) {
+      if (a.resid_out) reinterpret_cast<__nv_bfloat162*>(a.resid_out + off)[p] = __floats2bfloat162_rn(val[i].x, val[i].y);
+      if (a.norm_out)
+        reinterpret_cast<__nv_bfloat162*>(a.norm_out + off)[p] =
+            __floats2bfloat162_rn((val[i].x - mean) * rstd, (val[i].y - mean) * rstd);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic LayerNorm over rows (any even C): warp per row, three L1-resident passes.
+// reference: nn.LayerNorm call sites models/lemevit.py:513,525,731,734,774
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+layernorm_kernel(LnArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= a.R) return;
+  const int npairs = a.C >> 1;
+  const __nv_bfloat162* src = reinterpret_cast<const __nv_bfloat162*>(a.in + row * a.C);
+  float s = 0.f;
+  for (int p = lane; p < npairs; p += 32) {
+    const float2 v = __bfloat1622float2(src[p]);
+    s += v.x + v.y;
+  }
+  const float mean = warp_sum(s) / (float)a.C;
+  float ss = 0.f;
+  for (int p = lane; p < npairs; p += 32) {
+    const float2 v = __bfloat1622float2(src[p]);
+    const float dx = v.x - mean, dy = v.y - mean;
+    ss += dx * dx + dy * dy;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)a.C + a.eps);
+  long long orow = row;
+  if (a.grp_rows > 0) orow = (row / a.grp_rows) * a.grp_stride + a.grp_off + (row % a.grp_rows);
+  __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(a.out + orow * a.C);
+  for (int p = lane; p < npairs; p += 32) {
+    float2 v = __bfloat1622float2(src[p]);
+    v.x = (v.x - mean) * rstd;
+    v.y = (v.y - mean) * rstd;
+    if (a.gamma) {
+      const float2 g = __ldg(reinterpret_cast<const float2*>(a.gamma) + p);
+      const float2 be = __ldg(reinterpret_cast<const float2*>(a.beta) + p);
+      v.x = fmaf(v.x, g.x, be.x);
+      v.y = fmaf(v.y, g.y, be.y);
+    }
+    if (a.act_gelu) {
+      v.x = gelu_erf(v.x);
+      v.y = gelu_erf(v.y);
+    }
+    dst[p] = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem im2col: x NCHW (f32|bf16) -> patches [B*Ho*Wo, Kp] bf16, k = ci*9 + ky*3 + kx, zero padded to Kp
+// reference: first stem conv nn.Conv2d(in_chans, C0/2, 3, 2, 1) (models/lemevit.py:699)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_as_float<bf16>(const bf16* p) { return __bfloat162float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const T* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int H, int W, int Ho, int Wo,
+                   int Kp) {
+  // one thread per (output pixel, group of 8 k values)
+  const int groups = Kp >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * Ho * Wo * groups;
+  if (idx >= total) return;
+  const int g = (int)(idx % groups);
+  const long long pix = idx / groups;
+  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    float val = 0.f;
+    if (k < Cin * 9) {
+      const int ci = k / 9, r = k % 9, ky = r / 3, kx = r % 3;
+      const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = ld_as_float<T>(x + (((long long)b * Cin + ci) * H + iy) * W + ix);
+    }
+    v[j] = val;
+  }
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(out + pix * Kp)[g] = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for conv3x3 stride 2 pad 1 on token-major activations: out[(b,oy,ox), tap*C + ci]
+// reference: stem conv 2 and downsample convs (models/lemevit.py:702,715)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_3x3s2_kernel(Im2colArgs a, int Ho, int Wo) {
+  const int vecs = a.C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)a.B * Ho * Wo * 9 * vecs;
+  if (idx >= total) return;
+  const int vec = (int)(idx % vecs);
+  const int tap = (int)((idx / vecs) % 9);
+  const long long pix = idx / (9 * vecs);
+  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+  const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+  uint4 u = make_uint4(0u, 0u, 0u, 0u);
+  if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+    u = __ldg(reinterpret_cast<const uint4*>(a.in + ((long long)b * a.T + (long long)iy * a.W + ix) * a.C) + vec);
+  reinterpret_cast<uint4*>(a.out + pix * (9LL * a.C) + (long long)tap * a.C)[vec] = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// classification tail: BN(eval) -> spatial mean, LN(c) -> token mean, sum  (models/lemevit.py:815-827)
+// mean(BN(x)) == BN_affine(mean(x)); one CTA per image.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tail_kernel(TailArgs a) {
+  extern __shared__ float sm[];  // mu[M], rstd[M]
+  float* mu = sm;
+  float* rs = sm + a.M;
+  const int b = blockIdx.x;
+  const bf16* x = a.x + (long long)b * a.x_bs;
+  const bf16* c = a.c + (long long)b * a.c_bs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int m = warp; m < a.M; m += nwarps) {
+    const bf16* r = c + (long long)m * a.C;
+    float s = 0.f;
+    for (int ch = lane; ch < a.C; ch += 32) s += __bfloat162float(r[ch]);
+    const float mean = warp_sum(s) / (float)a.C;
+    float ss = 0.f;
+    for (int ch = lane; ch < a.C; ch += 32) {
+      const float d = __bfloat162float(r[ch]) - mean;
+      ss += d * d;
+    }
+    const float var = warp_sum(ss) / (float)a.C;
+    if (lane == 0) { mu[m] = mean; rs[m] = rsqrtf(var + a.eps); }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < a.C; ch += blockDim.x) {
+    float sx = 0.f;
+    for (int n = 0; n < a.N; ++n) sx += __bfloat162float(x[(long long)n * a.C + ch]);
+    float sc = 0.f;
+    for (int m = 0; m < a.M; ++m) sc += (__bfloat162float(c[(long long)m * a.C + ch]) - mu[m]) * rs[m];
+    const float f = a.bn_scale[ch] * (sx / (float)a.N) + a.bn_shift[ch] + a.ln_gamma[ch] * (sc / (float)a.M) + a.ln_beta[ch];
+    a.feat[(long long)b * a.C + ch] = __float2bfloat16(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// token-major -> NCHW (backbone outputs, semantic_segmentation/.../lemevit.py:800-820)
+// ------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(256)
+tokens_to_nchw_kernel(const bf16* __restrict__ tok, TO* __restrict__ out, int N, int T, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* src = tok + (long long)b * T * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, ch = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (n < N && ch < C) ? __bfloat162float(src[(long long)n * C + ch]) : 0.f;
+  }
+  __syncthreads();
+  TO* dst = out + (long long)b * C * N;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i, n = n0 + threadIdx.x;
+    if (n < N && ch < C) dst[(long long)ch * N + n] = (TO)tile[threadIdx.x][i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+broadcast_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int per_image_vecs, int B, long long dst_bs) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * per_image_vecs) return;
+  const int b = (int)(idx / per_image_vecs), v = (int)(idx % per_image_vecs);
+  reinterpret_cast<uint4*>(dst + (long long)b * dst_bs)[v] = __ldg(reinterpret_cast<const uint4*>(src) + v);
+}
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int rows, int vecs, int C, int grp_rows,
+                   int grp_stride, int grp_off) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * vecs) return;
+  const int r = (int)(idx / vecs), v = (int)(idx % vecs);
+  const long long srow = (long long)(r / grp_rows) * grp_stride + grp_off + (r % grp_rows);
+  reinterpret_cast<uint4*>(dst + (long long)r * C)[v] = __ldg(reinterpret_cast<const uint4*>(src + srow * C) + v);
+}
+
+inline unsigned blocks_for(long long total, int per_block) { return (unsigned)((total + per_block - 1) / per_block); }
+
+}  // namespace
+
+int posembed_ln_run(const PosLnArgs& a, cudaStream_t s) {
+  LMV_REQUIRE(a.C % 2 == 0 && a.C <= 64 * kMaxPairs, "posembed_layernorm: C must be even and <= 512");
+  LMV_REQUIRE(a.T >= (a.dw_w ? a.H * a.W : 0), "posembed_layernorm: T < H*W");
+  const long long rows = (long long)a.B * a.T;
+  if (rows == 0) return LMV_OK;
+  posembed_ln_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(a);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int layernorm_run(const LnArgs& a, cudaStream_t s) {
+  LMV_REQUIRE(a.C % 2 == 0, "layernorm: C must be even");
+  if (a.R == 0) return LMV_OK;
+  layernorm_kernel<<<blocks_for(a.R, 8), 256, 0, s>>>(a);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int stem_im2col_run(const StemArgs& a, cudaStream_t s) {
+  const int Ho = (a.H + 1) / 2, Wo = (a.W + 1) / 2;
+  const int Kp = ((a.Cin * 9 + 7) / 8) * 8;
+  const long long total = (long long)a.B * Ho * Wo * (Kp / 8);
+  if (total == 0) return LMV_OK;
+  if (a.x_dtype == LMV_DTYPE_F32)
+    stem_im2col_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>((const float*)a.x, a.out, a.B, a.Cin, a.H, a.W, Ho, Wo, Kp);
+  else
+    stem_im2col_kernel<bf16><<<blocks_for(total, 256), 256, 0, s>>>((const bf16*)a.x, a.out, a.B, a.Cin, a.H, a.W, Ho, Wo, Kp);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int im2col_run(const Im2colArgs& a, cudaStream_t s) {
+  LMV_REQUIRE(a.C % 8 == 0, "im2col: C must be a multiple of 8");
+  const int Ho = (a.H + 1) / 2, Wo = (a.W + 1) / 2;
+  const long long total = (long long)a.B * Ho * Wo * 9 * (a.C / 8);
+  if (total == 0) return LMV_OK;
+  im2col_3x3s2_kernel<<<blocks_for(total, 256), 256, 0, s>>>(a, Ho, Wo);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int tail_run(const TailArgs& a, cudaStream_t s) {
+  if (a.B == 0) return LMV_OK;
+  tail_kernel<<<a.B, 256, 2 * a.M * sizeof(float), s>>>(a);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int tokens_to_nchw_run(const ToNchwArgs& a, cudaStream_t s) {
+  const int N = a.H * a.W;
+  if (a.B == 0 || N == 0) return LMV_OK;
+  dim3 grid((N + 31) / 32, (a.C + 31) / 32, a.B), block(32, 8);
+  if (a.out_dtype == LMV_DTYPE_F32)
+    tokens_to_nchw_kernel<float><<<grid, block, 0, s>>>(a.tokens, (float*)a.out, N, a.T, a.C);
+  else
+    tokens_to_nchw_kernel<bf16><<<grid, block, 0, s>>>(a.tokens, (bf16*)a.out, N, a.T, a.C);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int broadcast_rows_run(const bf16* src, bf16* dst, int rows, int C, int B, long long dst_bs, cudaStream_t s) {
+  LMV_REQUIRE((rows * C) % 8 == 0 && dst_bs % 8 == 0, "broadcast_rows: sizes must be multiples of 8 elements");
+  const int vecs = rows * C / 8;
+  const long long total = (long long)B * vecs;
+  if (total == 0) return LMV_OK;
+  broadcast_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, dst, vecs, B, dst_bs);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int gather_rows_run(const bf16* src, bf16* dst, int rows, int C, int grp_rows, int grp_stride, int grp_off,
+                    cudaStream_t s) {
+  LMV_REQUIRE(C % 8 == 0 && grp_rows > 0, "gather_rows: C must be a multiple of 8");
+  const long long total = (long long)rows * (C / 8);
+  if (total == 0) return LMV_OK;
+  gather_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, dst, rows, C / 8, C, grp_rows, grp_stride, grp_off);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+}  // namespace lmv

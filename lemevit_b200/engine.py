@@ -1,0 +1,162 @@
+"""Host-side runtime of the native forward: owns the packed weights, the native plan, the workspace
+and (optionally) CUDA graphs.  PyTorch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native
+from .pack import pack_state_dict
+
+_TORCH2LMV = {torch.bfloat16: _native.DTYPE_BF16, torch.float32: _native.DTYPE_F32}
+
+
+def require_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            "lemevit_b200 runs on CUDA (sm_100a) only: the forward pass is a set of hand-written Blackwell "
+            "kernels and there is deliberately no CPU fallback. Move the model and input to a B200.")
+
+
+class Engine:
+    """One engine per (module, device).  Not thread-safe; one engine per thread/replica."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], *, depth, embed_dim, mlp_ratios, attn_type, head_dim,
+                 queries_len, num_classes, in_chans, backbone: bool, device: torch.device, chunk: int = 0):
+        self.lib = _native.load()
+        self.device = torch.device(device)
+        self.backbone = bool(backbone)
+        self.embed_dim = list(embed_dim)
+        self.num_classes = int(num_classes)
+        self.in_chans = int(in_chans)
+        mlp_hidden = [int(r * d) for r, d in zip(mlp_ratios, embed_dim)]
+        self.cfg = _native.make_config(depth, embed_dim, mlp_hidden, attn_type, head_dim, queries_len,
+                                       num_classes, in_chans, backbone)
+        with torch.cuda.device(self.device):
+            self.packed: List[torch.Tensor] = pack_state_dict(
+                sd, depth=depth, embed_dim=embed_dim, attn_type=attn_type, in_chans=in_chans,
+                num_classes=num_classes, backbone=backbone, device=self.device)
+        n = len(self.packed)
+        arr = (_native.Tensor * n)()
+        for i, t in enumerate(self.packed):
+            arr[i].data = t.data_ptr()
+            arr[i].numel = t.numel()
+            arr[i].dtype = _TORCH2LMV[t.dtype]
+        self._plan = C.c_void_p()
+        _native.check(self.lib.lmv_plan_create(C.byref(self.cfg), arr, n, C.byref(self._plan)))
+        self._ws: Optional[torch.Tensor] = None
+        self._graphs: Dict[Tuple, Tuple] = {}
+        self.chunk = 0
+        if chunk:
+            self.set_chunk(chunk)
+
+    # -- lifecycle ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_plan", None) is not None and self._plan.value:
+            self.lib.lmv_plan_destroy(self._plan)
+            self._plan = C.c_void_p()
+        self._graphs.clear()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_chunk(self, images_per_chunk: int):
+        _native.check(self.lib.lmv_plan_set_chunk(self._plan, int(images_per_chunk)))
+        self.chunk = int(images_per_chunk)
+        self._graphs.clear()
+
+    def set_debug_simt(self, enable: bool):
+        _native.check(self.lib.lmv_plan_set_debug_simt(self._plan, int(bool(enable))))
+        self._graphs.clear()
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _workspace(self, B: int, H: int, W: int) -> torch.Tensor:
+        need = int(self.lib.lmv_workspace_bytes(self._plan, B, H, W))
+        if need == 0:
+            raise RuntimeError(f"lemevit_b200: unsupported input shape {B}x{H}x{W}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)  # torch OOM -> RuntimeError "out of memory"
+        return self._ws
+
+    def _prep_input(self, x: torch.Tensor) -> torch.Tensor:
+        require_cuda(x)
+        if x.dim() != 4 or x.shape[1] != self.in_chans:
+            raise RuntimeError(f"expected input [B, {self.in_chans}, H, W], got {tuple(x.shape)}")
+        if x.dtype not in _TORCH2LMV:
+            x = x.to(torch.bfloat16)
+        return x.contiguous()      # NCHW; channels_last inputs are re-laid out here (benchmark.py --channels-last)
+
+    def launch_count(self, B: int, H: int, W: int) -> int:
+        n = int(self.lib.lmv_launch_count(self._plan, B, H, W))
+        if n < 0:
+            _native.check(n)
+        return n
+
+    def out_shapes(self, B: int, H: int, W: int) -> List[Tuple[int, int, int, int]]:
+        h, w = (H + 1) // 2, (W + 1) // 2
+        h, w = (h + 1) // 2, (w + 1) // 2
+        shapes = []
+        at = self.cfg.attn_type
+        for i in range(self.cfg.num_stages):
+            if i > 0 and at[i - 1:i] != b"C":
+                h, w = (h + 1) // 2, (w + 1) // 2
+            if i >= 1:
+                shapes.append((B, self.embed_dim[i], h, w))
+        return shapes
+
+    # -- forward -----------------------------------------------------------------------------------
+    def forward_cls(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = self._prep_input(x)
+        B, _, H, W = x.shape
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, H, W)
+            if out is None:
+                out = torch.empty((B, self.num_classes), dtype=out_dtype, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self.lib.lmv_forward_cls(self._plan, x.data_ptr(), _TORCH2LMV[x.dtype], B, H, W, ws.data_ptr(),
+                                                   ws.numel(), out.data_ptr(), _TORCH2LMV[out.dtype], stream))
+        return out
+
+    def forward_features(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32,
+                         outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+        x = self._prep_input(x)
+        B, _, H, W = x.shape
+        with torch.cuda.device(self.device):
+            ws = self._workspace(B, H, W)
+            if outs is None:
+                outs = [torch.empty(s, dtype=out_dtype, device=self.device) for s in self.out_shapes(B, H, W)]
+            ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self.lib.lmv_forward_features(self._plan, x.data_ptr(), _TORCH2LMV[x.dtype], B, H, W,
+                                                        ws.data_ptr(), ws.numel(), ptrs, len(outs),
+                                                        _TORCH2LMV[outs[0].dtype], stream))
+        return list(outs)
+
+    # -- CUDA-graph replay of a fixed-shape forward ----------------------------------------------------
+    def graphed(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32):
+        """Capture the forward for x's shape once; returns (static_input, static_output(s), replay_fn)."""
+        x = self._prep_input(x)
+        key = (tuple(x.shape), x.dtype, out_dtype)
+        if key not in self._graphs:
+            static_x = x.clone()
+            fwd = self.forward_features if self.backbone else self.forward_cls
+            with torch.cuda.device(self.device):
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    for _ in range(2):      # warm-up: builds the native schedule, sets kernel attributes
+                        static_out = fwd(static_x, out_dtype)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    static_out = fwd(static_x, out_dtype)
+            self._graphs[key] = (static_x, static_out, g)
+        static_x, static_out, g = self._graphs[key]
+        return static_x, static_out, g.replay

@@ -1,0 +1,100 @@
+"""Helpers for the -m gpu tests: raw-pointer calls into the C ABI on torch-owned device buffers."""
+import ctypes as C
+import math
+
+import torch
+
+from lemevit_b200 import _native
+
+BF16, F32 = _native.DTYPE_BF16, _native.DTYPE_F32
+
+
+def lib():
+    return _native.load()
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ok(rc):
+    _native.check(rc)
+
+
+def bf(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  — the metric of the stated tolerances."""
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def describe_mismatch(got, ref, tol):
+    """Structure of an error pattern (helps decode descriptor / swizzle bugs from one GPU run)."""
+    err = (got.double() - ref.double()).abs()
+    bad = err > tol * ref.abs().max()
+    rows = bad.any(dim=1).nonzero().flatten()
+    cols = bad.any(dim=0).nonzero().flatten()
+    msg = [f"bad elems {int(bad.sum())}/{bad.numel()}  max err {float(err.max()):.4g}  ref max {float(ref.abs().max()):.4g}"]
+    if rows.numel():
+        msg.append(f"bad rows: first {rows[:12].tolist()} ... count {rows.numel()} (mod 8 hist {torch.bincount(rows % 8, minlength=8).tolist()})")
+        msg.append(f"bad cols: first {cols[:12].tolist()} ... count {cols.numel()} (mod 64 //8 hist {torch.bincount((cols % 64) // 8, minlength=8).tolist()})")
+        r0 = int(rows[0])
+        msg.append(f"row {r0} got {got[r0, :8].float().tolist()} ref {ref[r0, :8].float().tolist()}")
+    return "\n".join(msg)
+
+
+def linear(A, W, bias=None, residual=None, gelu=False, out_dtype=torch.bfloat16, simt=False, force_bn=0, ldc=None, out=None):
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((M, N if ldc is None else ldc), dtype=out_dtype, device=A.device)
+    ldc = out.stride(0)
+    od = BF16 if out.dtype == torch.bfloat16 else F32
+    L = lib()
+    if simt:
+        ok(L.lmv_linear_simt(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(residual), ptr(out), ldc, M, N, K, int(gelu), od, stream()))
+    else:
+        ok(L.lmv_linear(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(residual), ptr(out), ldc, M, N, K, int(gelu), od, force_bn, stream()))
+    return out
+
+
+def ref_linear(A, W, bias=None, residual=None, gelu=False):
+    y = A.float() @ W.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if gelu:
+        y = 0.5 * y * (1.0 + torch.erf(y / math.sqrt(2.0)))
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+def attention(q, k, v, scale, impl=0):
+    """q [B, Lq, h, 32], k/v [B, Lk, h, 32] (any strides with unit innermost stride) -> [B, Lq, h*32]."""
+    B, Lq, h, d = q.shape
+    Lk = k.shape[1]
+    out = torch.empty((B, Lq, h * d), dtype=torch.bfloat16, device=q.device)
+    for t in (q, k, v):
+        assert t.stride(3) == 1 and t.stride(2) == d
+    ok(lib().lmv_attention(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v), v.stride(0), v.stride(1),
+                           ptr(out), out.stride(0), out.stride(1), B, h, Lq, Lk, float(scale), impl, stream()))
+    return out
+
+
+def ref_attention(q, k, v, scale):
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    p = torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1)
+    o = (p @ vf).permute(0, 2, 1, 3)
+    return o.reshape(o.shape[0], o.shape[1], -1)

@@ -1,0 +1,220 @@
+"""Per-kernel parity on the GPU (B200): each native kernel, called through the C ABI, against a plain
+PyTorch fp32 restatement of the same op on the same bf16 inputs.  Tolerances:
+per-kernel max-abs-err / max|ref| <= 1e-2 and cosine >= 0.9999 — bf16 outputs carry 2^-9 relative rounding."""
+import math
+
+import pytest
+import torch
+
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.manual_seed(0)
+    yield
+    torch.cuda.synchronize()
+
+
+def _rand(*shape, scale=1.0):
+    return G.bf(torch.randn(*shape, device="cuda") * scale)
+
+
+# ---- GEMM --------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    # (M, N, K) — every (N, K) family the three variants use, plus ragged edges
+    (128, 32, 64), (128, 128, 64), (256, 256, 128), (300, 96, 96), (1000, 288, 96), (777, 192, 192),
+    (512, 384, 96), (640, 576, 192), (200, 768, 192), (424, 1152, 384), (424, 1536, 384), (424, 384, 1536),
+    (98, 2048, 512), (98, 512, 2048), (4096, 48, 32), (3136, 96, 432), (784, 192, 864), (196, 384, 1728),
+    (49, 512, 3456), (32, 1000, 512), (7, 51, 320), (130, 320, 1280), (130, 960, 320), (1, 64, 8),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_linear_tcgen05_matches_fp32(M, N, K):
+    A, W = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    ref = G.ref_linear(A, W, bias)
+    out = G.linear(A, W, bias, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert G.rel_err(out, ref) < 2e-3, G.describe_mismatch(out, ref, 2e-3)     # fp32 out: only accumulation-order error
+    out16 = G.linear(A, W, bias)
+    assert G.rel_err(out16, ref) < TOL and G.cosine(out16, ref) > 0.9999
+
+
+@pytest.mark.parametrize("force_bn", [32, 64, 96, 128, 160, 192, 224, 256])
+def test_linear_every_tile_width(force_bn):
+    M, N, K = 384, 512, 256
+    A, W = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    ref = G.ref_linear(A, W)
+    out = G.linear(A, W, out_dtype=torch.float32, force_bn=force_bn)
+    assert G.rel_err(out, ref) < 2e-3, G.describe_mismatch(out, ref, 2e-3)
+
+
+def test_linear_epilogue_gelu_residual_inplace():
+    M, N, K = 1000, 384, 1536
+    A, W = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    res = _rand(M, N)
+    ref = G.ref_linear(A, W, bias, residual=res)
+    out = res.clone()
+    G.linear(A, W, bias, residual=out, out=out)                      # residual stream updated in place
+    assert G.rel_err(out, ref) < TOL
+    ref_g = G.ref_linear(A, W, bias, gelu=True)
+    out_g = G.linear(A, W, bias, gelu=True)
+    assert G.rel_err(out_g, ref_g) < TOL and G.cosine(out_g, ref_g) > 0.9999
+
+
+def test_linear_many_tiles_persistent_loop():
+    # > 148 * 2 tiles: exercises the smem-ring and TMEM double-buffer phase wrap-around
+    M, N, K = 128 * 40, 1024, 320
+    A, W = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    ref = G.ref_linear(A, W)
+    out = G.linear(A, W, out_dtype=torch.float32)
+    assert G.rel_err(out, ref) < 2e-3, G.describe_mismatch(out, ref, 2e-3)
+
+
+def test_linear_strided_operands_and_simt_crosscheck():
+    M, N, K = 333, 160, 96
+    big = _rand(M, 3 * K)
+    A = big[:, K:2 * K]                                              # lda = 3K
+    W = _rand(N, K, scale=K ** -0.5)
+    ref = G.ref_linear(A, W)
+    assert G.rel_err(G.linear(A, W, out_dtype=torch.float32), ref) < 2e-3
+    assert G.rel_err(G.linear(A, W, out_dtype=torch.float32, simt=True), ref) < 2e-3
+
+
+def test_linear_rejects_bad_arguments():
+    A, W = _rand(16, 12), _rand(8, 12)                               # K % 8 != 0
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        G.linear(A, W)
+
+
+# ---- positional conv + LayerNorm / LayerNorm --------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,C,M", [(2, 14, 14, 384, 16), (3, 7, 5, 64, 0), (2, 28, 28, 192, 0), (1, 9, 11, 512, 16)])
+def test_posembed_layernorm(B, H, W, C, M):
+    T = H * W + M
+    tok = _rand(B, T, C)
+    dw = torch.randn(C, 1, 3, 3, device="cuda") * 0.2
+    db = torch.randn(C, device="cuda") * 0.1
+    dw_packed = dw.reshape(C, 9).t().contiguous().clone()
+    dw_packed[4] += 1.0
+    resid = torch.empty_like(tok)
+    norm = torch.empty_like(tok)
+    L = G.lib()
+    G.ok(L.lmv_posembed_layernorm(G.ptr(tok), G.ptr(dw_packed), G.ptr(db), G.ptr(resid), G.ptr(norm), B, H, W, T, C, 1e-6, G.stream()))
+    x = tok[:, :H * W].float().transpose(1, 2).reshape(B, C, H, W)
+    xt = (x + torch.nn.functional.conv2d(x, dw, db, padding=1, groups=C)).flatten(2).transpose(1, 2)
+    full = torch.cat([xt, tok[:, H * W:].float()], dim=1)
+    ref_n = torch.nn.functional.layer_norm(full, (C,), eps=1e-6)
+    assert G.rel_err(resid, full) < TOL
+    assert G.rel_err(norm, ref_n) < TOL and G.cosine(norm, ref_n) > 0.9999
+    # LayerNorm-only mode (no conv), norm output only
+    norm2 = torch.empty_like(tok)
+    G.ok(L.lmv_posembed_layernorm(G.ptr(tok), None, None, None, G.ptr(norm2), B, H, W, T, C, 1e-6, G.stream()))
+    assert G.rel_err(norm2, torch.nn.functional.layer_norm(tok.float(), (C,), eps=1e-6)) < TOL
+
+
+@pytest.mark.parametrize("R,C,gelu,affine", [(64, 2048, True, True), (33, 96, False, False), (512, 384, False, True)])
+def test_layernorm(R, C, gelu, affine):
+    x = _rand(R, C)
+    g = 1 + 0.2 * torch.randn(C, device="cuda") if affine else None
+    b = 0.1 * torch.randn(C, device="cuda") if affine else None
+    out = torch.empty_like(x)
+    G.ok(G.lib().lmv_layernorm(G.ptr(x), G.ptr(out), G.ptr(g), G.ptr(b), R, C, 1e-5, int(gelu), 0, 0, 0, G.stream()))
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), g, b, eps=1e-5)
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    assert G.rel_err(out, ref) < TOL
+
+
+def test_layernorm_row_remap_into_unified_buffer():
+    B, M, N, C = 3, 16, 49, 64
+    T = N + M
+    x = _rand(B * M, C)
+    dst = torch.zeros(B, T, C, dtype=torch.bfloat16, device="cuda")
+    G.ok(G.lib().lmv_layernorm(G.ptr(x), G.ptr(dst), None, None, B * M, C, 1e-5, 0, M, T, N, G.stream()))
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), eps=1e-5).reshape(B, M, C)
+    assert G.rel_err(dst[:, N:], ref) < TOL
+    assert float(dst[:, :N].abs().max()) == 0.0
+
+
+# ---- im2col + conv on the GEMM -----------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_conv_via_im2col_gemm(dtype):
+    B, Cin, H, W, Co = 2, 3, 64, 48, 48
+    x = torch.randn(B, Cin, H, W, device="cuda").to(dtype)
+    w = torch.randn(Co, Cin, 3, 3, device="cuda") * 0.2
+    b = torch.randn(Co, device="cuda") * 0.1
+    Ho, Wo, Kp = H // 2, W // 2, 32
+    patches = torch.empty(B * Ho * Wo, Kp, dtype=torch.bfloat16, device="cuda")
+    G.ok(G.lib().lmv_stem_im2col(G.ptr(x), G.F32 if dtype == torch.float32 else G.BF16, G.ptr(patches), B, Cin, H, W, G.stream()))
+    wp = torch.zeros(Co, Kp, device="cuda")
+    wp[:, :27] = w.reshape(Co, 27)
+    out = G.linear(patches, G.bf(wp), b, gelu=True)
+    ref = torch.nn.functional.gelu(torch.nn.functional.conv2d(x.float(), G.bf(w).float(), b, stride=2, padding=1))
+    ref = ref.permute(0, 2, 3, 1).reshape(B * Ho * Wo, Co)
+    assert G.rel_err(out, ref) < TOL
+
+
+@pytest.mark.parametrize("B,H,W,C,Co,extra", [(2, 28, 28, 48, 96, 0), (2, 14, 14, 192, 384, 16), (1, 7, 9, 64, 128, 0)])
+def test_conv3x3s2_via_im2col_gemm(B, H, W, C, Co, extra):
+    T = H * W + extra
+    tok = _rand(B, T, C)
+    w = torch.randn(Co, C, 3, 3, device="cuda") * (9 * C) ** -0.5
+    b = torch.randn(Co, device="cuda") * 0.1
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    patches = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.bfloat16, device="cuda")
+    G.ok(G.lib().lmv_im2col_3x3s2(G.ptr(tok), G.ptr(patches), B, H, W, T, C, G.stream()))
+    wp = G.bf(w.permute(0, 2, 3, 1).reshape(Co, 9 * C))
+    out = G.linear(patches, wp, b)
+    x = tok[:, :H * W].float().transpose(1, 2).reshape(B, C, H, W)
+    ref = torch.nn.functional.conv2d(x, G.bf(w).float(), b, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+    assert G.rel_err(out, ref) < TOL
+
+
+# ---- attention ----------------------------------------------------------------------------------------
+ATTN_CASES = [
+    # (B, heads, Lq, Lk)   — S blocks (196/49, and 16x16 meta), D x-branch (N x 16), D/C c-branch (16 x N)
+    (2, 6, 196, 196), (2, 10, 49, 49), (3, 12, 16, 16), (2, 3, 784, 16), (2, 3, 16, 784), (1, 2, 16, 3136),
+    (1, 4, 1024, 1024), (2, 2, 50, 77),
+]
+
+
+@pytest.mark.parametrize("B,h,Lq,Lk", ATTN_CASES)
+@pytest.mark.parametrize("impl", [1, 0])
+def test_attention(B, h, Lq, Lk, impl):
+    C = h * 32
+    qkv_q = _rand(B, Lq, 3 * C)
+    qkv_k = _rand(B, Lk, 3 * C)
+    q = qkv_q[:, :, :C].unflatten(2, (h, 32))
+    k = qkv_k[:, :, C:2 * C].unflatten(2, (h, 32))
+    v = qkv_k[:, :, 2 * C:].unflatten(2, (h, 32))
+    scale = 0.3
+    out = G.attention(q, k, v, scale, impl=impl)
+    ref = G.ref_attention(q, k, v, scale)
+    assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999
+
+
+# ---- tail / export ------------------------------------------------------------------------------------
+def test_tail_and_nchw_export():
+    B, N, M, C = 3, 49, 16, 320
+    T = N + M
+    tok = _rand(B, T, C)
+    bs, bb = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+    g, be = 1 + 0.2 * torch.randn(C, device="cuda"), 0.1 * torch.randn(C, device="cuda")
+    feat = torch.empty(B, C, dtype=torch.bfloat16, device="cuda")
+    L = G.lib()
+    G.ok(L.lmv_tail(G.ptr(tok), T * C, N, G.ptr(tok[:, N:]), T * C, M, C, G.ptr(bs), G.ptr(bb), G.ptr(g), G.ptr(be), 1e-5, G.ptr(feat), B, G.stream()))
+    x, c = tok[:, :N].float(), tok[:, N:].float()
+    ref = bs * x.mean(1) + bb + torch.nn.functional.layer_norm(c, (C,), g, be, eps=1e-5).mean(1)
+    assert G.rel_err(feat, ref) < TOL
+    for dt, code in ((torch.float32, G.F32), (torch.bfloat16, G.BF16)):
+        out = torch.empty(B, C, 7, 7, dtype=dt, device="cuda")
+        G.ok(L.lmv_tokens_to_nchw(G.ptr(tok), G.ptr(out), B, 7, 7, T, C, code, G.stream()))
+        assert torch.equal(out.float(), x.transpose(1, 2).reshape(B, C, 7, 7))       # pure data movement: bit exact
