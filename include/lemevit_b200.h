@@ -78,6 +78,21 @@ size_t lmv_workspace_bytes(const lmv_plan* plan, int batch, int H, int W);
 /* number of kernel launches one forward of this shape issues (for bench.py's gpu_launches). */
 int lmv_launch_count(lmv_plan* plan, int batch, int H, int W);
 
+/* per-kernel-class device timing: when enabled, every forward records a CUDA event between consecutive
+ * launches on the caller's stream; lmv_plan_get_profile waits for them and returns the totals accumulated since
+ * profiling was enabled (returns the number of entries written, or a negative error). */
+typedef struct lmv_profile_entry {
+  const char* name;      /* kernel class, e.g. "gemm_tcgen05" */
+  long long launches;
+  double device_ms;      /* sum of CUDA-event durations */
+  double flops;          /* sum of algorithmic FLOPs (2 x MAC) of those launches */
+  double bytes;          /* sum of algorithmic bytes (compulsory reads + writes) */
+} lmv_profile_entry;
+int lmv_plan_set_profile(lmv_plan* plan, int enable);
+int lmv_plan_get_profile(lmv_plan* plan, lmv_profile_entry* out, int max_entries);
+/* human-readable per-launch-shape table of the same data (tuning aid); returns the untruncated length */
+int lmv_plan_profile_report(lmv_plan* plan, char* buf, int buf_bytes);
+
 /* replaces LeMeViT.forward (models/lemevit.py:831-836): x[B,in_chans,H,W] NCHW (bf16 or f32)
  * -> logits[B,num_classes] (bf16 or f32, per logits_dtype). */
 int lmv_forward_cls(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,

@@ -32,6 +32,11 @@ class Config(C.Structure):
     ]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("launches", C.c_longlong), ("device_ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 class Tensor(C.Structure):
     _fields_ = [("data", C.c_void_p), ("numel", C.c_int64), ("dtype", C.c_int)]
 
@@ -47,6 +52,9 @@ SIGNATURES = {
     "lmv_plan_destroy": (None, [_vp]),
     "lmv_plan_set_chunk": (_i, [_vp, _i]),
     "lmv_plan_set_debug_simt": (_i, [_vp, _i]),
+    "lmv_plan_set_profile": (_i, [_vp, _i]),
+    "lmv_plan_get_profile": (_i, [_vp, _vp, _i]),
+    "lmv_plan_profile_report": (_i, [_vp, C.c_char_p, _i]),
     "lmv_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "lmv_launch_count": (_i, [_vp, _i, _i, _i]),
     "lmv_forward_cls": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _i, _vp]),

@@ -101,6 +101,17 @@ struct StageW {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
+enum OpClass { OP_GEMM = 0, OP_ATTN_TC, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
+static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "attention_tcgen05", "attention_simt",
+                                                          "posembed_layernorm", "layernorm", "im2col", "misc"};
+struct OpRec {
+  Launch fn;
+  std::string desc;
+  int cls;
+  double flops;   // algorithmic FLOPs (2 x MAC) of this launch
+  double bytes;   // algorithmic bytes (compulsory reads + writes) of this launch
+};
+
 struct IoSlots {
   const void* x = nullptr;
   void* logits = nullptr;
@@ -108,8 +119,19 @@ struct IoSlots {
 };
 
 struct Schedule {
-  std::vector<Launch> ops;
+  std::vector<OpRec> ops;
   std::unique_ptr<IoSlots> io{new IoSlots()};
+  void push(Launch fn, int cls = OP_MISC, double flops = 0, double bytes = 0, std::string desc = std::string()) {
+    if (desc.empty()) desc = kOpClassNames[cls];
+    ops.push_back(OpRec{std::move(fn), std::move(desc), cls, flops, bytes});
+  }
+};
+
+struct ProfDetail { double ms = 0, flops = 0, bytes = 0; long long n = 0; };
+struct ProfAcc {
+  std::map<std::string, ProfDetail> detail;
+  double ms[OP_NUM_CLASSES] = {0}, flops[OP_NUM_CLASSES] = {0}, bytes[OP_NUM_CLASSES] = {0};
+  long long launches[OP_NUM_CLASSES] = {0};
 };
 
 }  // namespace lmv
@@ -121,6 +143,10 @@ struct lmv_plan {
   std::vector<lmv::StageW> stages;
   int chunk = 0;
   int debug_simt = 0;
+  int profile = 0;
+  std::vector<cudaEvent_t> events;          // profile mode: one event between consecutive launches
+  std::vector<const lmv::OpRec*> pending;   // ops whose events have not been harvested yet
+  lmv::ProfAcc acc;
   std::map<std::tuple<int, int, int, const void*, int, int, int>, std::unique_ptr<lmv::Schedule>> cache;
 };
 
@@ -319,14 +345,18 @@ struct Builder {
 
   void gemm(GemmArgs a) {
     if (rc) return;
+    const double fl = 2.0 * a.M * a.N * a.K;
+    const double by = 2.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N * (a.residual ? 2 : 1));
     if (simt) {
-      sc->ops.push_back([a](cudaStream_t s) { return gemm_simt_run(a, s); });
+      sc->push([a](cudaStream_t s) { return gemm_simt_run(a, s); }, OP_MISC, fl, by);
       return;
     }
     GemmOp op;
     rc = gemm_prepare(a, &op);
     if (rc) return;
-    sc->ops.push_back([op](cudaStream_t s) { return gemm_run(op, s); });
+    char d[160];
+    snprintf(d, sizeof(d), "gemm M=%d N=%d K=%d BN=%d%s%s", a.M, a.N, a.K, op.p.BN, a.act ? " gelu" : "", a.residual ? " res" : "");
+    sc->push([op](cudaStream_t s) { return gemm_run(op, s); }, OP_GEMM, fl, by, d);
   }
   void linear(const bf16* A, int lda, const bf16* Wt, const float* bias, int M, int N, int K, bf16* out, int ldc,
               int gelu = 0, const bf16* resid = nullptr, int grp_rows = 0, int grp_stride = 0) {
@@ -340,13 +370,17 @@ struct Builder {
              int C) {
     if (rc) return;
     PosLnArgs a{tok, dw_w, dw_b, resid, norm, B, H, W, T, C, 1e-6f};
-    sc->ops.push_back([a](cudaStream_t s) { return posembed_ln_run(a, s); });
+    const double rows = (double)B * T;
+    char d[160];
+    snprintf(d, sizeof(d), "posln rows=%d C=%d conv=%d resid=%d", B * T, C, dw_w ? 1 : 0, resid ? 1 : 0);
+    sc->push([a](cudaStream_t s) { return posembed_ln_run(a, s); }, OP_POSLN, dw_w ? 18.0 * B * H * W * C : 0.0,
+             2.0 * rows * C * (1 + (resid ? 1 : 0) + (norm ? 1 : 0)), d);
   }
   void ln(const bf16* in, bf16* out, const float* g, const float* b, int R, int C, float eps, int gelu = 0,
           int grp_rows = 0, int grp_stride = 0, int grp_off = 0) {
     if (rc) return;
     LnArgs a{in, out, g, b, R, C, eps, gelu, grp_rows, grp_stride, grp_off};
-    sc->ops.push_back([a](cudaStream_t s) { return layernorm_run(a, s); });
+    sc->push([a](cudaStream_t s) { return layernorm_run(a, s); }, OP_LN, 0.0, 4.0 * R * C);
   }
   void attn(const bf16* q, long long q_bs, int q_rs, const bf16* k, const bf16* v, long long kv_bs, int kv_rs, bf16* out,
             long long o_bs, int o_rs, int B, int heads, int Lq, int Lk, float scale) {
@@ -357,7 +391,12 @@ struct Builder {
     a.q_rs = q_rs; a.k_rs = kv_rs; a.v_rs = kv_rs; a.o_rs = o_rs;
     a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
     const bool tc = !simt && attention_tc_supported(a);
-    sc->ops.push_back([a, tc](cudaStream_t s) { return tc ? attention_tc_run(a, s) : attention_simt_run(a, s); });
+    const double fl = 4.0 * B * heads * (double)Lq * Lk * 32;
+    const double by = 2.0 * B * heads * 32.0 * (2.0 * Lq + 2.0 * Lk);
+    sc->push([a, tc](cudaStream_t s) { return tc ? attention_tc_run(a, s) : attention_simt_run(a, s); },
+             tc ? OP_ATTN_TC : OP_ATTN_SIMT, fl, by,
+             std::string(tc ? "attn_tc" : "attn_simt") + " B=" + std::to_string(B) + " h=" + std::to_string(heads) + " Lq=" +
+                 std::to_string(Lq) + " Lk=" + std::to_string(Lk));
   }
 };
 
@@ -380,10 +419,12 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
   // ---- stem (models/lemevit.py:698-704): conv3x3/s2 + BN + GELU + conv3x3/s2 + BN, both on the GEMM
   {
     StemArgs sa{nullptr, x_dtype, patches, B, c.in_chans, H, W};
-    sc->ops.push_back([sa, io](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_im2col_run(a, s); });
+    sc->push([sa, io](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_im2col_run(a, s); }, OP_IM2COL, 0.0,
+             (double)B * c.in_chans * H * W * (x_dtype == LMV_DTYPE_F32 ? 4 : 2) + 2.0 * B * g.H1 * g.W1 * kp0(c));
     b.linear(patches, kp0(c), plan->stem1_w, plan->stem1_b, B * g.H1 * g.W1, C0 / 2, kp0(c), stem1, C0 / 2, /*gelu=*/1);
     Im2colArgs ia{stem1, patches, B, g.H1, g.W1, g.H1 * g.W1, C0 / 2};
-    sc->ops.push_back([ia](cudaStream_t s) { return im2col_run(ia, s); });
+    sc->push([ia](cudaStream_t s) { return im2col_run(ia, s); }, OP_IM2COL, 0.0,
+             2.0 * B * (C0 / 2) * ((double)g.H1 * g.W1 + 9.0 * g.N[0]));
   }
   int cur = 0, ccur = 0;
   {
@@ -404,7 +445,8 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
       if (g.unified[i - 1]) c_prev_unified = xbuf[cur];
       if (c.attn_type[i - 1] != 'C') {
         Im2colArgs ia{xbuf[cur], patches, B, g.H[i - 1], g.W[i - 1], g.T[i - 1], Cp};
-        sc->ops.push_back([ia](cudaStream_t s) { return im2col_run(ia, s); });
+        sc->push([ia](cudaStream_t s) { return im2col_run(ia, s); }, OP_IM2COL, 0.0,
+                 2.0 * B * Cp * ((double)g.N[i - 1] + 9.0 * N));
         b.linear(patches, 9 * Cp, sw.ds_w, sw.ds_b, B * N, C, 9 * Cp, xbuf[cur ^ 1], C, 0, nullptr, uni ? N : 0,
                  uni ? T : 0);
         cur ^= 1;
@@ -417,7 +459,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         bf16* dst = uni ? xbuf[cur] + (size_t)N * C : cbuf[ccur];
         const long long bs = uni ? (long long)T * C : (long long)M * C;
         const bf16* src = plan->c0_init;
-        sc->ops.push_back([src, dst, M, C, B, bs](cudaStream_t s) { return broadcast_rows_run(src, dst, M, C, B, bs, s); });
+        sc->push([src, dst, M, C, B, bs](cudaStream_t s) { return broadcast_rows_run(src, dst, M, C, B, bs, s); });
       } else {
         const int Cp = c.embed_dim[i - 1];
         const bf16* cprev = cbuf[ccur];
@@ -425,7 +467,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
           const bf16* src = c_prev_unified;
           bf16* dst = cbuf[ccur];
           const int Np = g.N[i - 1], Tp = g.T[i - 1];
-          sc->ops.push_back([src, dst, B, M, Cp, Np, Tp](cudaStream_t s) { return gather_rows_run(src, dst, B * M, Cp, M, Tp, Np, s); });
+          sc->push([src, dst, B, M, Cp, Np, Tp](cudaStream_t s) { return gather_rows_run(src, dst, B * M, Cp, M, Tp, Np, s); });
         }
         b.linear(cprev, Cp, sw.md_w0, sw.md_b0, B * M, 4 * Cp, Cp, chid, 4 * Cp);
         b.ln(chid, chid, sw.md_g1, sw.md_be1, B * M, 4 * Cp, 1e-5f, /*gelu=*/1);
@@ -497,7 +539,8 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
     if (c.backbone && i >= 1) {
       ToNchwArgs ta{xbuf[cur], nullptr, B, g.H[i], g.W[i], T, C, out_dtype};
       const int slot = i - 1;
-      sc->ops.push_back([ta, io, slot](cudaStream_t s) { ToNchwArgs a = ta; a.out = io->outs[slot]; return tokens_to_nchw_run(a, s); });
+      sc->push([ta, io, slot](cudaStream_t s) { ToNchwArgs a = ta; a.out = io->outs[slot]; return tokens_to_nchw_run(a, s); },
+               OP_MISC, 0.0, (2.0 + (out_dtype == LMV_DTYPE_F32 ? 4 : 2)) * B * N * C);
     }
   }
   if (b.rc) return b.rc;
@@ -511,21 +554,22 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
     ta.M = M; ta.C = C;
     ta.bn_scale = plan->bn_scale; ta.bn_shift = plan->bn_shift; ta.ln_gamma = plan->lnc_g; ta.ln_beta = plan->lnc_b;
     ta.eps = 1e-5f; ta.feat = feat; ta.B = B;
-    sc->ops.push_back([ta](cudaStream_t s) { return tail_run(ta, s); });
+    sc->push([ta](cudaStream_t s) { return tail_run(ta, s); });
     if (c.num_classes > 0) {
       GemmArgs ga;
       ga.A = feat; ga.lda = C; ga.W = plan->head_w; ga.ldw = C; ga.M = B; ga.N = c.num_classes; ga.K = C;
       ga.bias = plan->head_b; ga.ldc = c.num_classes; ga.out_fp32 = (out_dtype == LMV_DTYPE_F32);
       const bool simt = plan->debug_simt != 0;
       // the logits pointer changes per call/chunk: the tensor maps only cover A and W, so patch `out`
+      const double hfl = 2.0 * B * c.num_classes * C;
       if (simt) {
-        sc->ops.push_back([ga, io](cudaStream_t s) { GemmArgs a = ga; a.out = io->logits; return gemm_simt_run(a, s); });
+        sc->push([ga, io](cudaStream_t s) { GemmArgs a = ga; a.out = io->logits; return gemm_simt_run(a, s); }, OP_MISC, hfl, 0);
       } else {
         ga.out = feat;  // placeholder for validation; replaced at launch
         GemmOp op;
         rc = gemm_prepare(ga, &op);
         if (rc) return rc;
-        sc->ops.push_back([op, io](cudaStream_t s) { GemmOp o = op; o.p.out = io->logits; return gemm_run(o, s); });
+        sc->push([op, io](cudaStream_t s) { GemmOp o = op; o.p.out = io->logits; return gemm_run(o, s); }, OP_GEMM, hfl, 0);
       }
     } else {
       return fail(LMV_ERR_UNSUPPORTED, "num_classes == 0 (features only) is not implemented for the classification model");
@@ -533,6 +577,8 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
   }
   return LMV_OK;
 }
+
+static int harvest_profile(lmv_plan* plan);
 
 static int get_schedule(lmv_plan* plan, int B, int H, int W, void* ws, size_t ws_bytes, int x_dtype, int out_dtype,
                         Schedule** out) {
@@ -546,13 +592,36 @@ static int get_schedule(lmv_plan* plan, int B, int H, int W, void* ws, size_t ws
   auto key = std::make_tuple(B, H, W, (const void*)ws, x_dtype, out_dtype, plan->debug_simt);
   auto it = plan->cache.find(key);
   if (it == plan->cache.end()) {
-    if (plan->cache.size() >= 16) plan->cache.clear();
+    if (plan->cache.size() >= 16) {
+      rc = harvest_profile(plan);
+      if (rc) return rc;
+      plan->cache.clear();
+    }
     std::unique_ptr<Schedule> sc(new Schedule());
     rc = build_schedule(plan, B, H, W, static_cast<uint8_t*>(ws), x_dtype, out_dtype, sc.get());
     if (rc) return rc;
     it = plan->cache.emplace(key, std::move(sc)).first;
   }
   *out = it->second.get();
+  return LMV_OK;
+}
+
+// profile mode: fold the event timings of the previous profiled pass into the per-class accumulators
+static int harvest_profile(lmv_plan* plan) {
+  if (plan->pending.empty()) return LMV_OK;
+  LMV_CUDA_OK(cudaEventSynchronize(plan->events[plan->pending.size()]));
+  for (size_t k = 0; k < plan->pending.size(); ++k) {
+    float ms = 0.f;
+    LMV_CUDA_OK(cudaEventElapsedTime(&ms, plan->events[k], plan->events[k + 1]));
+    const OpRec* op = plan->pending[k];
+    plan->acc.ms[op->cls] += ms;
+    plan->acc.flops[op->cls] += op->flops;
+    plan->acc.bytes[op->cls] += op->bytes;
+    plan->acc.launches[op->cls] += 1;
+    ProfDetail& d = plan->acc.detail[op->desc];
+    d.ms += ms; d.flops += op->flops; d.bytes += op->bytes; d.n += 1;
+  }
+  plan->pending.clear();
   return LMV_OK;
 }
 
@@ -576,9 +645,26 @@ static int run_forward(lmv_plan* plan, const void* x, int x_dtype, int B, int H,
     if (logits) sc->io->logits = static_cast<uint8_t*>(logits) + (size_t)b0 * c.num_classes * oe;
     for (int k = 0; k < n_outs; ++k)
       sc->io->outs[k] = static_cast<uint8_t*>(outs[k]) + (size_t)b0 * c.embed_dim[k + 1] * g.N[k + 1] * oe;
-    for (auto& op : sc->ops) {
-      rc = op(stream);
+    if (!plan->profile) {
+      for (auto& op : sc->ops) {
+        rc = op.fn(stream);
+        if (rc) return rc;
+      }
+    } else {
+      rc = harvest_profile(plan);
       if (rc) return rc;
+      while (plan->events.size() < sc->ops.size() + 1) {
+        cudaEvent_t e;
+        LMV_CUDA_OK(cudaEventCreate(&e));
+        plan->events.push_back(e);
+      }
+      LMV_CUDA_OK(cudaEventRecord(plan->events[0], stream));
+      for (size_t k = 0; k < sc->ops.size(); ++k) {
+        rc = sc->ops[k].fn(stream);
+        if (rc) return rc;
+        LMV_CUDA_OK(cudaEventRecord(plan->events[k + 1], stream));
+        plan->pending.push_back(&sc->ops[k]);
+      }
     }
   }
   return LMV_OK;
@@ -620,7 +706,53 @@ int lmv_plan_create(const lmv_config* cfg, const lmv_tensor* packed, int n_packe
   return LMV_OK;
 }
 
-void lmv_plan_destroy(lmv_plan* plan) { delete plan; }
+void lmv_plan_destroy(lmv_plan* plan) {
+  if (!plan) return;
+  for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
+  delete plan;
+}
+
+int lmv_plan_set_profile(lmv_plan* plan, int enable) {
+  if (!plan) return fail(LMV_ERR_INVALID, "null plan");
+  int rc = harvest_profile(plan);
+  if (rc) return rc;
+  plan->profile = enable ? 1 : 0;
+  if (enable) plan->acc = ProfAcc();
+  return LMV_OK;
+}
+
+int lmv_plan_profile_report(lmv_plan* plan, char* buf, int buf_bytes) {
+  if (!plan || !buf || buf_bytes <= 0) return fail(LMV_ERR_INVALID, "profile_report: bad argument");
+  int rc = harvest_profile(plan);
+  if (rc) return rc;
+  std::string out;
+  char line[320];
+  for (auto& kv : plan->acc.detail) {
+    const ProfDetail& d = kv.second;
+    snprintf(line, sizeof(line), "%-52s n=%-5lld ms=%9.3f avg_us=%9.2f TFLOPs=%8.1f GBs=%8.1f\n", kv.first.c_str(), d.n, d.ms,
+             d.ms / d.n * 1e3, d.flops / d.ms * 1e-9, d.bytes / d.ms * 1e-6);
+    out += line;
+  }
+  snprintf(buf, buf_bytes, "%s", out.c_str());
+  return (int)out.size();
+}
+
+int lmv_plan_get_profile(lmv_plan* plan, lmv_profile_entry* out, int max_entries) {
+  if (!plan || !out) return fail(LMV_ERR_INVALID, "get_profile: null argument");
+  int rc = harvest_profile(plan);
+  if (rc) return rc;
+  int n = 0;
+  for (int c = 0; c < OP_NUM_CLASSES && n < max_entries; ++c) {
+    if (!plan->acc.launches[c]) continue;
+    out[n].name = kOpClassNames[c];
+    out[n].launches = plan->acc.launches[c];
+    out[n].device_ms = plan->acc.ms[c];
+    out[n].flops = plan->acc.flops[c];
+    out[n].bytes = plan->acc.bytes[c];
+    ++n;
+  }
+  return n;
+}
 
 int lmv_plan_set_chunk(lmv_plan* plan, int n) {
   if (!plan || n < 0) return fail(LMV_ERR_INVALID, "set_chunk: bad argument");

@@ -74,6 +74,25 @@ class Engine:
         _native.check(self.lib.lmv_plan_set_debug_simt(self._plan, int(bool(enable))))
         self._graphs.clear()
 
+    def set_profile(self, enable: bool):
+        """Per-kernel-class CUDA-event timing of every following forward (see lmv_plan_set_profile)."""
+        _native.check(self.lib.lmv_plan_set_profile(self._plan, int(bool(enable))))
+
+    def get_profile(self):
+        arr = (_native.ProfileEntry * 16)()
+        n = int(self.lib.lmv_plan_get_profile(self._plan, arr, 16))
+        if n < 0:
+            _native.check(n)
+        return [dict(name=arr[i].name.decode(), launches=arr[i].launches, device_ms=arr[i].device_ms, flops=arr[i].flops,
+                     bytes=arr[i].bytes) for i in range(n)]
+
+    def profile_report(self) -> str:
+        buf = C.create_string_buffer(1 << 16)
+        n = int(self.lib.lmv_plan_profile_report(self._plan, buf, len(buf)))
+        if n < 0:
+            _native.check(n)
+        return buf.value.decode()
+
     # -- helpers -----------------------------------------------------------------------------------
     def _workspace(self, B: int, H: int, W: int) -> torch.Tensor:
         need = int(self.lib.lmv_workspace_bytes(self._plan, B, H, W))

@@ -41,6 +41,14 @@ with torch.no_grad():
     gflop = O.algorithmic_flops_per_image(O.VARIANTS[name], res, res) / 1e9
     print(json.dumps({"model": name, "batch": B, "chunk": chunk, "graph": use_graph, "ms": ms, "wall_ms": wall, "img_s": B / ms * 1e3,
                       "tflops": B * gflop / ms, "launches": eng.launch_count(B, res, res)}))
+    if "--ops" in sys.argv:
+        eng.set_profile(True)
+        for _ in range(3):
+            m(x)
+        print(eng.profile_report())
+        for e in eng.get_profile():
+            print(e)
+        eng.set_profile(False)
     if prof:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
