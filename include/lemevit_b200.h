@@ -106,15 +106,30 @@ int lmv_forward_features(lmv_plan* plan, const void* x, int x_dtype, int batch, 
 /* nn.Linear (+GELU) (+residual): out[M,N] = act(A[M,K] W[N,K]^T + bias) + residual.  tcgen05 path. */
 int lmv_linear(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, void* out,
                int ldc, int M, int N, int K, int act_gelu, int out_dtype, int force_tile_n, void* stream);
-/* same contract on the SIMT cross-check kernel */
+/* lmv_linear with the two fused LayerNorm hooks of the block schedule:
+ *   ln_stats  [M][ln_parts][2] fp32: partial (sum_k a, sum_k a^2) pairs of every A row (added up by the kernel),
+ *             ln_colsum [N] fp32 (sum_k W[n,k]), ln_eps:
+ *             out = act(LayerNorm_noaffine(A) W^T + bias) computed as r (A W^T - mu colsum) + bias in the epilogue
+ *             (norm1 -> q/kv/qkv*, norm2 -> mlp.0, models/lemevit.py:560-564,600-601,632-635; gamma/beta are folded
+ *             into W/bias at pack time);
+ *   stats_out [rows][parts][2] fp32 with parts = lmv_linear_stats_parts(N, use_simt): partial (sum_n out, sum_n out^2)
+ *             of every stored output row — plain stores, deterministic; needs N % 32 == 0 and a dense bf16 output.
+ * use_simt != 0 runs the same contract on the SIMT cross-check kernels. */
+int lmv_linear_fused(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, void* out,
+                     int ldc, int M, int N, int K, int act_gelu, int out_dtype, const float* ln_stats, int ln_parts,
+                     const float* ln_colsum, float ln_eps, float* stats_out, int use_simt, void* stream);
+int lmv_linear_stats_parts(int N, int use_simt);
+/* same contract as lmv_linear on the SIMT cross-check kernel */
 int lmv_linear_simt(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
                     void* out, int ldc, int M, int N, int K, int act_gelu, int out_dtype, void* stream);
 /* x + dwconv3x3(x) followed by LayerNorm without affine (models/lemevit.py:546,589,619 + :513).
  * tokens: [B, T, C] bf16, the first N = H*W rows of each image are the H x W map, rows N..T-1 (meta
- * tokens) get LayerNorm only.  resid_out (nullable) receives x + dw(x); norm_out the normalised rows. */
+ * tokens) get LayerNorm only.  resid_out (nullable) receives x + dw(x); norm_out (nullable) the normalised rows;
+ * stats_out (nullable, [B*T][2] fp32, needs C % 8 == 0) the (sum, sum of squares) of every stored resid_out row —
+ * the input (ln_parts = 1) of the LayerNorm fold of lmv_linear_fused. */
 int lmv_posembed_layernorm(const void* tokens, const float* dw_weight /*[9][C], centre tap +1*/,
-                           const float* dw_bias, void* resid_out, void* norm_out, int B, int H, int W, int T, int C,
-                           float eps, void* stream);
+                           const float* dw_bias, void* resid_out, void* norm_out, float* stats_out, int B, int H, int W,
+                           int T, int C, float eps, void* stream);
 /* LayerNorm over rows [R, C] bf16; gamma/beta nullable (no affine); optional GELU afterwards;
  * out row r -> (r / grp_rows) * grp_stride + grp_off + r % grp_rows when grp_rows > 0. */
 int lmv_layernorm(const void* in, void* out, const float* gamma, const float* beta, int R, int C, float eps,
@@ -125,6 +140,14 @@ int lmv_layernorm(const void* in, void* out, const float* gamma, const float* be
 int lmv_attention(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
                   long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
                   float scale, int impl, void* stream);
+/* The meta-token side of CrossAttention / DualCrossAttention (models/lemevit.py:484, :300-302): Lq = M (16) queries
+ * per head over Lk = N image tokens, heads * Lq <= 128, heads * 32 <= 256.  Split-N tcgen05 kernel (one CTA per image
+ * and 128-token tile, block-diagonal Q so that all heads share one accumulation) + deterministic merge of the
+ * per-tile softmax partials.  workspace: lmv_attention_meta_workspace(...) bytes of device scratch, 16-byte aligned. */
+size_t lmv_attention_meta_workspace(int B, int heads, int Lq, int Lk);
+int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
+                       long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
+                       float scale, void* workspace, size_t workspace_bytes, void* stream);
 /* patch gather for the first stem conv 3x3/s2/p1 (models/lemevit.py:699): x NCHW (f32|bf16) ->
  * out[B*Ho*Wo, Kp] bf16 with k = ci*9 + ky*3 + kx, zero padded to Kp = round_up(9*Cin, 8); the conv
  * itself (+ folded BN + GELU, :700-701) is then lmv_linear on the tcgen05 GEMM. */

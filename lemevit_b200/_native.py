@@ -60,10 +60,14 @@ SIGNATURES = {
     "lmv_forward_cls": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _i, _vp]),
     "lmv_forward_features": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, C.POINTER(_vp), _i, _i, _vp]),
     "lmv_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lmv_linear_fused": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _f, _vp, _i, _vp]),
+    "lmv_linear_stats_parts": (_i, [_i, _i]),
     "lmv_linear_simt": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "lmv_posembed_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "lmv_posembed_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "lmv_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),
     "lmv_attention": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "lmv_attention_meta_workspace": (_sz, [_i, _i, _i, _i]),
+    "lmv_attention_meta": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "lmv_stem_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "lmv_im2col_3x3s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lmv_tail": (_i, [_vp, _ll, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _i, _vp]),

@@ -90,6 +90,7 @@ struct BlockW {
   const float *ba, *bb, *bp1, *bp2;
   const bf16 *w1, *w2;
   const float *b1, *b2;
+  const float *csa, *csb, *cs1;   // column sums of the LayerNorm-folded weights wa, wb, w1 (gemm.cu LN fold)
 };
 struct StageW {
   const bf16* ds_w = nullptr;
@@ -101,8 +102,8 @@ struct StageW {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
-enum OpClass { OP_GEMM = 0, OP_ATTN_TC, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
-static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "attention_tcgen05", "attention_simt",
+enum OpClass { OP_GEMM = 0, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
+static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
                                                           "posembed_layernorm", "layernorm", "im2col", "misc"};
 struct OpRec {
   Launch fn;
@@ -236,21 +237,21 @@ static void walk(const lmv_config& c, PackWalker& w, lmv_plan* plan) {
       b.dw_b = w.f(C, "dw_b");
       switch (c.attn_type[i]) {
         case 'C':
-          b.wa = w.h((int64_t)C * C, "q_w"); b.ba = w.f(C, "q_b");
-          b.wb = w.h((int64_t)2 * C * C, "kv_w"); b.bb = w.f(2 * C, "kv_b");
+          b.wa = w.h((int64_t)C * C, "q_w"); b.ba = w.f(C, "q_b"); b.csa = w.f(C, "q_colsum");
+          b.wb = w.h((int64_t)2 * C * C, "kv_w"); b.bb = w.f(2 * C, "kv_b"); b.csb = w.f(2 * C, "kv_colsum");
           b.wp1 = w.h((int64_t)C * C, "proj_w"); b.bp1 = w.f(C, "proj_b");
           break;
         case 'D':
-          b.wa = w.h((int64_t)3 * C * C, "qkv1_w"); b.ba = w.f(3 * C, "qkv1_b");
-          b.wb = w.h((int64_t)3 * C * C, "qkv2_w"); b.bb = w.f(3 * C, "qkv2_b");
+          b.wa = w.h((int64_t)3 * C * C, "qkv1_w"); b.ba = w.f(3 * C, "qkv1_b"); b.csa = w.f(3 * C, "qkv1_colsum");
+          b.wb = w.h((int64_t)3 * C * C, "qkv2_w"); b.bb = w.f(3 * C, "qkv2_b"); b.csb = w.f(3 * C, "qkv2_colsum");
           b.wp1 = w.h((int64_t)C * C, "proj_x_w"); b.bp1 = w.f(C, "proj_x_b");
           b.wp2 = w.h((int64_t)C * C, "proj_c_w"); b.bp2 = w.f(C, "proj_c_b");
           break;
         default:
-          b.wa = w.h((int64_t)3 * C * C, "qkv_w"); b.ba = w.f(3 * C, "qkv_b");
+          b.wa = w.h((int64_t)3 * C * C, "qkv_w"); b.ba = w.f(3 * C, "qkv_b"); b.csa = w.f(3 * C, "qkv_colsum");
           b.wp1 = w.h((int64_t)C * C, "proj_w"); b.bp1 = w.f(C, "proj_b");
       }
-      b.w1 = w.h((int64_t)Hd * C, "mlp0_w"); b.b1 = w.f(Hd, "mlp0_b");
+      b.w1 = w.h((int64_t)Hd * C, "mlp0_w"); b.b1 = w.f(Hd, "mlp0_b"); b.cs1 = w.f(Hd, "mlp0_colsum");
       b.w2 = w.h((int64_t)C * Hd, "mlp3_w"); b.b2 = w.f(C, "mlp3_b");
     }
   }
@@ -299,7 +300,7 @@ static int geometry(const lmv_config& c, int H, int W, Geo* g) {
 }
 
 struct WsLayout {
-  size_t patches, stem1, x0, x1, xn, qkv, hid, ca, cb, cn, cqkv, chid, ctmp, feat, total;
+  size_t patches, stem1, x0, x1, xn, qkv, hid, ca, cb, cn, cqkv, chid, ctmp, feat, stats1, stats2, cpart, cpart_bytes, total;
 };
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
@@ -331,6 +332,17 @@ static void ws_layout(const lmv_config& c, const Geo& g, int B, WsLayout* L) {
   L->ca = take(crow * cmax); L->cb = take(crow * cmax); L->cn = take(crow * cmax); L->ctmp = take(crow * cmax);
   L->cqkv = take(crow * 3 * cmax); L->chid = take(crow * chid);
   L->feat = take((size_t)B * cmax);
+  size_t rows_max = 0;
+  for (int i = 0; i < c.num_stages; ++i) rows_max = std::max(rows_max, (size_t)B * g.T[i]);
+  L->stats1 = take(rows_max * 4);    // [rows][1][2] fp32 (take() counts 2-byte elements)
+  L->stats2 = take(rows_max * 16);   // [rows][parts <= 4][2] fp32
+  // split-softmax partials of the meta-token attention (attention_meta.cu): per C/D stage B x ceil(N/128) x heads*M rows
+  size_t cpart = 0;
+  for (int i = 0; i < c.num_stages; ++i)
+    if (c.attn_type[i] != 'S')
+      cpart = std::max(cpart, (size_t)B * ((g.N[i] + 127) / 128) * (c.embed_dim[i] / c.head_dim) * M * (32 * 4 + 8));
+  L->cpart_bytes = cpart;
+  L->cpart = take((cpart + 1) / 2);
   L->total = off;
 }
 
@@ -342,6 +354,8 @@ struct Builder {
   Schedule* sc;
   int rc = LMV_OK;
   bool simt;
+  void* cpart = nullptr;      // split-softmax partials of the meta-token attention
+  size_t cpart_bytes = 0;
 
   void gemm(GemmArgs a) {
     if (rc) return;
@@ -355,7 +369,8 @@ struct Builder {
     rc = gemm_prepare(a, &op);
     if (rc) return;
     char d[160];
-    snprintf(d, sizeof(d), "gemm M=%d N=%d K=%d BN=%d%s%s", a.M, a.N, a.K, op.p.BN, a.act ? " gelu" : "", a.residual ? " res" : "");
+    snprintf(d, sizeof(d), "gemm M=%d N=%d K=%d BN=%d%s%s%s%s", a.M, a.N, a.K, op.p.BN, a.ln_stats ? " ln" : "", a.act ? " gelu" : "",
+             a.residual ? " res" : "", a.stats_out ? " stats" : "");
     sc->push([op](cudaStream_t s) { return gemm_run(op, s); }, OP_GEMM, fl, by, d);
   }
   void linear(const bf16* A, int lda, const bf16* Wt, const float* bias, int M, int N, int K, bf16* out, int ldc,
@@ -366,15 +381,50 @@ struct Builder {
     a.grp_rows = grp_rows; a.grp_stride = grp_stride;
     gemm(a);
   }
-  void posln(const bf16* tok, const float* dw_w, const float* dw_b, bf16* resid, bf16* norm, int B, int H, int W, int T,
-             int C) {
+  // LayerNorm(eps 1e-6, affine folded into Wt/bias at pack time) -> Linear, the norm folded into the epilogue:
+  // A holds the raw rows, ln_stats their (sum, sum^2), colsum the column sums of Wt.
+  void ln_linear(const bf16* A, const float* ln_stats, int ln_parts, const bf16* Wt, const float* bias, const float* colsum,
+                 int M, int N, int K, bf16* out, int gelu = 0) {
+    GemmArgs a;
+    a.A = A; a.lda = K; a.W = Wt; a.ldw = K; a.M = M; a.N = N; a.K = K;
+    a.bias = bias; a.act = gelu; a.out = out; a.ldc = N;
+    a.ln_stats = ln_stats; a.ln_parts = ln_parts; a.ln_colsum = colsum; a.ln_eps = 1e-6f;
+    gemm(a);
+  }
+  // Linear + residual (in place on x) that also emits the LayerNorm statistics of the new x rows as
+  // `*parts` partial (sum, sum^2) pairs per row (deterministic plain stores; the consumer adds them up)
+  void linear_res_stats(const bf16* A, const bf16* Wt, const float* bias, int M, int N, int K, bf16* x, float* stats, int* parts) {
     if (rc) return;
-    PosLnArgs a{tok, dw_w, dw_b, resid, norm, B, H, W, T, C, 1e-6f};
+    GemmArgs a;
+    a.A = A; a.lda = K; a.W = Wt; a.ldw = K; a.M = M; a.N = N; a.K = K;
+    a.bias = bias; a.residual = x; a.out = x; a.ldc = N;
+    if (simt) {
+      gemm(a);
+      sc->push([x, stats, M, N](cudaStream_t s) { return row_stats_run(x, stats, M, N, s); }, OP_MISC, 0.0, 2.0 * M * N, "row_stats");
+      *parts = 1;
+      return;
+    }
+    *parts = gemm_stats_parts(N);
+    if (*parts > 4) { rc = fail(LMV_ERR_UNSUPPORTED, "linear_res_stats: more than 4 statistics partials per row"); return; }
+    a.stats_out = stats;
+    gemm(a);
+  }
+  void posln(const bf16* tok, const float* dw_w, const float* dw_b, bf16* resid, bf16* norm, int B, int H, int W, int T,
+             int C, float* stats = nullptr) {
+    if (rc) return;
+    PosLnArgs a{tok, dw_w, dw_b, resid, norm, B, H, W, T, C, 1e-6f, stats};
     const double rows = (double)B * T;
     char d[160];
-    snprintf(d, sizeof(d), "posln rows=%d C=%d conv=%d resid=%d", B * T, C, dw_w ? 1 : 0, resid ? 1 : 0);
-    sc->push([a](cudaStream_t s) { return posembed_ln_run(a, s); }, OP_POSLN, dw_w ? 18.0 * B * H * W * C : 0.0,
-             2.0 * rows * C * (1 + (resid ? 1 : 0) + (norm ? 1 : 0)), d);
+    snprintf(d, sizeof(d), "posln rows=%d C=%d conv=%d resid=%d norm=%d", B * T, C, dw_w ? 1 : 0, resid ? 1 : 0, norm ? 1 : 0);
+    const double fl = dw_w ? 18.0 * B * H * W * C : 0.0, by = 2.0 * rows * C * (1 + (resid ? 1 : 0) + (norm ? 1 : 0));
+    if (posembed_tile_supported(a)) {
+      PosEmbedOp op;
+      rc = posembed_tile_prepare(a, &op);
+      if (rc) return;
+      sc->push([op](cudaStream_t s) { return posembed_tile_run(op, s); }, OP_POSLN, fl, by, d);
+      return;
+    }
+    sc->push([a](cudaStream_t s) { return posembed_ln_run(a, s); }, OP_POSLN, fl, by, d);
   }
   void ln(const bf16* in, bf16* out, const float* g, const float* b, int R, int C, float eps, int gelu = 0,
           int grp_rows = 0, int grp_stride = 0, int grp_off = 0) {
@@ -390,9 +440,16 @@ struct Builder {
     a.q_bs = q_bs; a.k_bs = kv_bs; a.v_bs = kv_bs; a.o_bs = o_bs;
     a.q_rs = q_rs; a.k_rs = kv_rs; a.v_rs = kv_rs; a.o_rs = o_rs;
     a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
-    const bool tc = !simt && attention_tc_supported(a);
     const double fl = 4.0 * B * heads * (double)Lq * Lk * 32;
     const double by = 2.0 * B * heads * 32.0 * (2.0 * Lq + 2.0 * Lk);
+    if (!simt && Lk >= 8 * Lq && Lk > 224 && attention_meta_supported(a) && cpart && attention_meta_workspace(a) <= cpart_bytes) {
+      void* wsp = cpart;
+      const size_t wsb = cpart_bytes;
+      sc->push([a, wsp, wsb](cudaStream_t s) { return attention_meta_run(a, wsp, wsb, s); }, OP_ATTN_META, fl, by,
+               "attn_meta B=" + std::to_string(B) + " h=" + std::to_string(heads) + " Lq=" + std::to_string(Lq) + " Lk=" + std::to_string(Lk));
+      return;
+    }
+    const bool tc = !simt && attention_tc_supported(a);
     sc->push([a, tc](cudaStream_t s) { return tc ? attention_tc_run(a, s) : attention_simt_run(a, s); },
              tc ? OP_ATTN_TC : OP_ATTN_SIMT, fl, by,
              std::string(tc ? "attn_tc" : "attn_simt") + " B=" + std::to_string(B) + " h=" + std::to_string(heads) + " Lq=" +
@@ -412,8 +469,11 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
   bf16* xbuf[2] = {P(L.x0), P(L.x1)};
   bf16* cbuf[2] = {P(L.ca), P(L.cb)};
   bf16 *cn = P(L.cn), *ctmp = P(L.ctmp), *cqkv = P(L.cqkv), *chid = P(L.chid), *feat = P(L.feat);
+  float *stats1 = reinterpret_cast<float*>(ws + L.stats1), *stats2 = reinterpret_cast<float*>(ws + L.stats2);
   IoSlots* io = sc->io.get();
   Builder b{plan, sc, LMV_OK, plan->debug_simt != 0};
+  b.cpart = ws + L.cpart;
+  b.cpart_bytes = L.cpart_bytes;
   const int M = c.queries_len, C0 = c.embed_dim[0], S = c.num_stages;
 
   // ---- stem (models/lemevit.py:698-704): conv3x3/s2 + BN + GELU + conv3x3/s2 + BN, both on the GEMM
@@ -482,10 +542,11 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
       const BlockW& bw = sw.blocks[j];
       if (kind == 'C') {
         // forward_with_c (models/lemevit.py:584-613) + CrossAttention (:477-486); x is returned unchanged
-        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, nullptr, xn, B, g.H[i], g.W[i], T, C);
+        // xn <- x + dw(x) (raw; norm1 is folded into the kv GEMM through stats1)
+        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xn, nullptr, B, g.H[i], g.W[i], T, C, stats1);
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.wa, bw.ba, B * M, C, C, cqkv, C);
-        b.linear(xn, C, bw.wb, bw.bb, B * N, 2 * C, C, qkv, 2 * C);
+        b.ln_linear(xn, stats1, 1, bw.wb, bw.bb, bw.csb, B * N, 2 * C, C, qkv);
         b.attn(cqkv, (long long)M * C, C, qkv, qkv + C, (long long)N * 2 * C, 2 * C, cn, (long long)M * C, C, B, heads, M, N,
                1.0f / sqrtf((float)c.head_dim));
         b.linear(cn, C, bw.wp1, bw.bp1, B * M, C, C, cc, C, 0, cc);
@@ -494,11 +555,11 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         b.linear(chid, Hd, bw.w2, bw.b2, B * M, C, Hd, cc, C, 0, cc);
       } else if (kind == 'D') {
         // forward_with_xc (models/lemevit.py:542-582) + DualCrossAttention (:252-256,288-302)
-        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], xn, B, g.H[i], g.W[i], T, C);
+        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
         cur ^= 1;
         bf16* x = xbuf[cur];
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
-        b.linear(xn, C, bw.wa, bw.ba, B * N, 3 * C, C, qkv, 3 * C);
+        b.ln_linear(x, stats1, 1, bw.wa, bw.ba, bw.csa, B * N, 3 * C, C, qkv);
         b.linear(cn, C, bw.wb, bw.bb, B * M, 3 * C, C, cqkv, 3 * C);
         const double scale = 1.0 / std::sqrt((double)C);                       // :235 full channel dim
         const double scale_x = std::log((double)M) / std::log((double)N) * scale;  // :255 math.log(M, N)
@@ -506,10 +567,10 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
                B, heads, N, M, (float)scale_x);
         b.attn(cqkv, (long long)M * 3 * C, 3 * C, qkv + C, qkv + 2 * C, (long long)N * 3 * C, 3 * C, cn, (long long)M * C, C,
                B, heads, M, N, (float)scale);
-        b.linear(xn, C, bw.wp1, bw.bp1, B * N, C, C, x, C, 0, x);
+        int parts2 = 1;
+        b.linear_res_stats(xn, bw.wp1, bw.bp1, B * N, C, C, x, stats2, &parts2);     // x += proj_x(attn), stats2 = LN2 statistics
         b.linear(cn, C, bw.wp2, bw.bp2, B * M, C, C, cc, C, 0, cc);
-        b.posln(x, nullptr, nullptr, nullptr, xn, B, g.H[i], g.W[i], T, C);
-        b.linear(xn, C, bw.w1, bw.b1, B * N, Hd, C, hid, Hd, 1);
+        b.ln_linear(x, stats2, parts2, bw.w1, bw.b1, bw.cs1, B * N, Hd, C, hid, 1);  // norm2 folded, bias + GELU fused
         b.linear(hid, Hd, bw.w2, bw.b2, B * N, C, Hd, x, C, 0, x);
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.w1, bw.b1, B * M, Hd, C, chid, Hd, 1);
@@ -517,10 +578,10 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
       } else {
         // forward_with_x (models/lemevit.py:615-650) + StandardAttention (:199-205); image and meta tokens
         // share norm1/attn/norm2/mlp, so they travel in one [B, N+M, C] buffer (classification model only)
-        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], xn, B, g.H[i], g.W[i], T, C);
+        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
         cur ^= 1;
         bf16* x = xbuf[cur];
-        b.linear(xn, C, bw.wa, bw.ba, B * T, 3 * C, C, qkv, 3 * C);
+        b.ln_linear(x, stats1, 1, bw.wa, bw.ba, bw.csa, B * T, 3 * C, C, qkv);
         const float sc_ = 1.0f / sqrtf((float)c.head_dim);
         b.attn(qkv, (long long)T * 3 * C, 3 * C, qkv + C, qkv + 2 * C, (long long)T * 3 * C, 3 * C, xn, (long long)T * C, C, B,
                heads, N, N, sc_);
@@ -529,9 +590,9 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
           b.attn(qkv + ro, (long long)T * 3 * C, 3 * C, qkv + ro + C, qkv + ro + 2 * C, (long long)T * 3 * C, 3 * C,
                  xn + (size_t)N * C, (long long)T * C, C, B, heads, M, M, sc_);
         }
-        b.linear(xn, C, bw.wp1, bw.bp1, B * T, C, C, x, C, 0, x);
-        b.posln(x, nullptr, nullptr, nullptr, xn, B, g.H[i], g.W[i], T, C);
-        b.linear(xn, C, bw.w1, bw.b1, B * T, Hd, C, hid, Hd, 1);
+        int parts2 = 1;
+        b.linear_res_stats(xn, bw.wp1, bw.bp1, B * T, C, C, x, stats2, &parts2);
+        b.ln_linear(x, stats2, parts2, bw.w1, bw.b1, bw.cs1, B * T, Hd, C, hid, 1);
         b.linear(hid, Hd, bw.w2, bw.b2, B * T, C, Hd, x, C, 0, x);
       }
     }
@@ -830,6 +891,27 @@ int lmv_linear(const void* A, int lda, const void* W, int ldw, const float* bias
   return gemm_run(op, static_cast<cudaStream_t>(stream));
 }
 
+int lmv_linear_fused(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual, void* out,
+                     int ldc, int M, int N, int K, int act_gelu, int out_dtype, const float* ln_stats, int ln_parts,
+                     const float* ln_colsum, float ln_eps, float* stats_out, int use_simt, void* stream) {
+  GemmArgs a = make_gemm_args(A, lda, W, ldw, bias, residual, out, ldc, M, N, K, act_gelu, out_dtype);
+  a.ln_stats = ln_stats; a.ln_parts = ln_parts; a.ln_colsum = ln_colsum; a.ln_eps = ln_eps; a.stats_out = stats_out;
+  if (use_simt) {
+    if (!a.A || !a.W || !a.out || M <= 0 || N <= 0 || K <= 0) return fail(LMV_ERR_INVALID, "linear_fused: bad argument");
+    if ((ln_stats == nullptr) != (ln_colsum == nullptr)) return fail(LMV_ERR_INVALID, "linear_fused: ln_stats and ln_colsum go together");
+    int rc = gemm_simt_run(a, static_cast<cudaStream_t>(stream));
+    if (rc || !stats_out) return rc;
+    if (out_dtype != LMV_DTYPE_BF16 || ldc != N) return fail(LMV_ERR_INVALID, "linear_fused(simt): stats_out needs a dense bf16 output");
+    return row_stats_run(static_cast<const bf16*>(out), stats_out, M, N, static_cast<cudaStream_t>(stream));
+  }
+  GemmOp op;
+  int rc = gemm_prepare(a, &op);
+  if (rc) return rc;
+  return gemm_run(op, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_linear_stats_parts(int N, int use_simt) { return use_simt ? 1 : gemm_stats_parts(N); }
+
 int lmv_linear_simt(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
                     void* out, int ldc, int M, int N, int K, int act_gelu, int out_dtype, void* stream) {
   GemmArgs a = make_gemm_args(A, lda, W, ldw, bias, residual, out, ldc, M, N, K, act_gelu, out_dtype);
@@ -838,10 +920,10 @@ int lmv_linear_simt(const void* A, int lda, const void* W, int ldw, const float*
 }
 
 int lmv_posembed_layernorm(const void* tokens, const float* dw_weight, const float* dw_bias, void* resid_out,
-                           void* norm_out, int B, int H, int W, int T, int C, float eps, void* stream) {
-  if (!tokens || (!resid_out && !norm_out)) return fail(LMV_ERR_INVALID, "posembed_layernorm: null pointer");
+                           void* norm_out, float* stats_out, int B, int H, int W, int T, int C, float eps, void* stream) {
+  if (!tokens || (!resid_out && !norm_out && !stats_out)) return fail(LMV_ERR_INVALID, "posembed_layernorm: null pointer");
   PosLnArgs a{static_cast<const bf16*>(tokens), dw_weight, dw_bias, static_cast<bf16*>(resid_out),
-              static_cast<bf16*>(norm_out), B, H, W, T, C, eps};
+              static_cast<bf16*>(norm_out), B, H, W, T, C, eps, stats_out};
   return posembed_ln_run(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -866,6 +948,32 @@ int lmv_attention(const void* q, long long q_bs, int q_rs, const void* k, long l
   if (impl == 2) return attention_tc_supported(a) ? attention_tc_run(a, static_cast<cudaStream_t>(stream))
                                                   : fail(LMV_ERR_UNSUPPORTED, "attention: shape not supported by the tcgen05 kernel");
   return attention_simt_run(a, static_cast<cudaStream_t>(stream));
+}
+
+static AttnArgs make_attn_args(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
+                               long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
+                               float scale) {
+  AttnArgs a;
+  a.q = static_cast<const bf16*>(q); a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v);
+  a.out = static_cast<bf16*>(out);
+  a.q_bs = q_bs; a.k_bs = k_bs; a.v_bs = v_bs; a.o_bs = o_bs;
+  a.q_rs = q_rs; a.k_rs = k_rs; a.v_rs = v_rs; a.o_rs = o_rs;
+  a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
+  return a;
+}
+
+size_t lmv_attention_meta_workspace(int B, int heads, int Lq, int Lk) {
+  AttnArgs a{};
+  a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk;
+  return attention_meta_workspace(a);
+}
+
+int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
+                       long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
+                       float scale, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q || !k || !v || !out) return fail(LMV_ERR_INVALID, "attention_meta: null pointer");
+  AttnArgs a = make_attn_args(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, out, o_bs, o_rs, B, heads, Lq, Lk, scale);
+  return attention_meta_run(a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int lmv_stem_im2col(const void* x, int x_dtype, void* out, int B, int Cin, int H, int W, void* stream) {

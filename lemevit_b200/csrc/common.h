@@ -58,6 +58,15 @@ struct GemmArgs {
   // optional row remap of the OUTPUT (and residual): row r -> (r / grp_rows) * grp_stride + r % grp_rows
   int grp_rows = 0, grp_stride = 0;
   int force_bn = 0;                  // test hook: override the tile-N heuristic
+  // LayerNorm folded into the GEMM (LN(y) W'^T = r (y W'^T - mu colsum(W'))): A holds the RAW rows y,
+  // ln_stats[row] = (sum_k y, sum_k y^2) of A row `row`, ln_colsum[n] = sum_k W'[n,k] (of the bf16 weights).
+  const float* ln_stats = nullptr;   // [M][2] or null
+  const float* ln_colsum = nullptr;  // [N]
+  float ln_eps = 0.f;
+  int ln_parts = 1;                  // ln_stats holds [M][ln_parts][2]: partial sums, added up by the consumer
+  // per OUTPUT row, partial (sum, sum of squares) of the stored bf16 values: stats_out[orow][part] with
+  // part = 2 * n_tile + warp_half, gemm_stats_parts(N) parts per row — plain stores, deterministic, no zeroing needed
+  float* stats_out = nullptr;        // [rows][gemm_stats_parts(N)][2] or null
 };
 
 struct GemmParams {
@@ -68,15 +77,22 @@ struct GemmParams {
   void* out;
   int ldc, out_fp32, act;
   int grp_rows, grp_stride;
+  const float* ln_stats;
+  const float* ln_colsum;
+  float ln_eps, ln_inv_k;
+  int ln_parts;
+  float* stats_out;
+  int prefetch_res;
 };
 
 struct GemmOp {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmR;   // tmR: residual tile, only used for L2 prefetch
   GemmParams p;
   int grid = 0;
   int smem_bytes = 0;
 };
 
+int gemm_stats_parts(int N, int force_bn = 0);   // partial-sum slots per row that stats_out receives
 int gemm_prepare(const GemmArgs& a, GemmOp* op);
 int gemm_run(const GemmOp& op, cudaStream_t stream);
 int gemm_simt_run(const GemmArgs& a, cudaStream_t stream);  // bring-up cross-check kernel (tests only)

@@ -5,9 +5,16 @@
 // sm_100a design: persistent CTAs (one per SM), warp-specialised:
 //   warp 0      TMA producer   — cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BNx64) tiles
 //   warp 1      MMA issuer     — one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
-//   warps 2..5  epilogue       — tcgen05.ld accumulators, + bias, GELU, + residual, bf16/fp32 store
+//   warps 2..9  epilogue       — two warps per TMEM lane quarter (they split the 32-column chunks):
+//                                tcgen05.ld -> [LayerNorm fold] + bias -> [GELU] -> per-warp smem transpose ->
+//                                coalesced (+ residual) bf16 stores, optional per-row (sum, sum^2) output
 // smem ring of `num_stages` (A,W) tiles with full/empty mbarriers; TMEM holds two 256-column
 // accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Fusions carried by the epilogue (north star: "LN fused into the following projection, bias+GELU fused into the
+// MLP GEMM"): LayerNorm (norm1 -> q/kv/qkv*, norm2 -> mlp.0; models/lemevit.py:560-564,600-601,632-635) is folded
+// algebraically: LN(y) W'^T = r (y W'^T - mu colsum(W')), with the row statistics (sum y, sum y^2) produced by the
+// kernel that wrote y (posembed kernel, or the proj GEMM's own epilogue through `stats_out`).
 #include <algorithm>
 #include <mutex>
 
@@ -21,7 +28,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kStageF32 = 32 * 32 * 4;   // per-warp transpose buffer: 32 rows x 32 fp32
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -33,14 +42,20 @@ struct SmemCtrl {
   uint32_t tmem_base;
 };
 
+// Generic (slow-path) chunk epilogue: one thread owns one output row; handles ragged N, fp32 output, odd ldc.
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int row, long long orow,
-                                               int col0, bool vec_ok) {
+                                               int col0, bool vec_ok, float ln_r, float ln_nrm) {
   const int ncols = min(32, p.N - col0);
   if (row >= p.M || ncols <= 0) return;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   const bool full = (ncols == 32) && vec_ok;
+  if (p.ln_stats) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < ncols) v[j] = fmaf(ln_r, v[j], ln_nrm * __ldg(p.ln_colsum + col0 + j));
+  }
   if (p.bias) {
     if (full) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
@@ -57,7 +72,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
   if (p.act == 1) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
   }
   const long long off = orow * (long long)p.ldc + col0;
   if (p.residual) {
@@ -109,12 +124,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   SmemCtrl* ctrl = reinterpret_cast<SmemCtrl*>(smem);
-  uint8_t* tiles = smem + 1024;
+  uint8_t* tiles = smem + 1024 + kEpiWarps * kStageF32;   // [ctrl 1 KB][8 x 4 KB transpose buffers][stage ring]
   const int a_bytes = BM * BK * 2;
   const int stage_bytes = a_bytes + p.BN * BK * 2;
   const int warp = threadIdx.x >> 5;
@@ -127,7 +142,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->acc_full[i], 1);
-      mbar_init(&ctrl->acc_empty[i], 4);  // one elected lane per epilogue warp
+      mbar_init(&ctrl->acc_empty[i], kEpiWarps);  // one elected lane per epilogue warp
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -150,6 +165,8 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
+        // pull the residual tile into L2 while the mainloop of this tile runs: the epilogue reads it ~2 tiles later
+        if (p.prefetch_res) tma_prefetch_l2_2d(&tmR, n_blk * p.BN, m_blk * BM);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&ctrl->empty[stage], phase ^ 1u, 1);
           uint8_t* sa = tiles + (size_t)stage * stage_bytes;
@@ -190,29 +207,153 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else {
-    // ---------------- epilogue (warps 2..5) ----------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ---------------- epilogue (warps 2..9) ----------------
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // the two warps of a quarter take alternate 32-column chunks
     const bool vec_ok = (p.ldc % 8 == 0);
+    const bool fast_ok = vec_ok && !p.out_fp32;
+    float* stg = reinterpret_cast<float*>(smem + 1024 + (size_t)(warp - 2) * kStageF32);
+    const int lr = lane >> 2, lc = (lane & 3) * 8;   // transposed domain: this lane owns rows it*8 + lr, columns lc .. lc+7
     int as = 0;
     uint32_t aphase = 0;
+    // LayerNorm statistics of row (q*32 + lane) of the NEXT tile are loaded one tile ahead (coalesced, <= 4 partial
+    // pairs per row) so their latency never sits on the epilogue's critical path
+    float2 nst[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
+    auto load_stats = [&](int tile) {
+      const int row = (tile / p.tiles_n) * BM + q * 32 + lane;
+      if (row < p.M) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (long long)row * p.ln_parts;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < p.ln_parts) nst[k] = __ldg(st + k);
+      }
+    };
+    if (p.ln_stats && (int)blockIdx.x < num_tiles) load_stats(blockIdx.x);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
-      mbar_wait(&ctrl->acc_full[as], aphase, 4);
-      tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      long long orow = row;
-      if (p.grp_rows > 0) orow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows);
+      long long orow_t[4];
+      bool rok_t[4];
+      float lnr[4], lnn[4];   // LayerNorm fold: v = r * acc + (-r * mu) * colsum[n] + bias[n]
+      float own_r = 1.f, own_n = 0.f;
+      if (p.ln_stats) {
+        const float s1 = (nst[0].x + nst[1].x) + (nst[2].x + nst[3].x), s2 = (nst[0].y + nst[1].y) + (nst[2].y + nst[3].y);
+        const float mu = s1 * p.ln_inv_k;
+        const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mu * mu), 0.f);
+        own_r = rsqrtf(var + p.ln_eps);
+        own_n = -own_r * mu;
+        if (t + (int)gridDim.x < num_tiles) load_stats(t + gridDim.x);
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int rr = m_blk * BM + q * 32 + it * 8 + lr;
+        rok_t[it] = rr < p.M;
+        orow_t[it] = (p.grp_rows > 0) ? (long long)(rr / p.grp_rows) * p.grp_stride + (rr % p.grp_rows) : (long long)rr;
+        lnr[it] = __shfl_sync(0xffffffffu, own_r, it * 8 + lr);
+        lnn[it] = __shfl_sync(0xffffffffu, own_n, it * 8 + lr);
+      }
+      float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
+      bool waited = false;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride);
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        if (n_blk * p.BN + c0 >= p.N) break;  // uniform
+      for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
+        const int col0 = n_blk * p.BN + c0;
+        if (col0 >= p.N) break;  // uniform
+        const bool fast = fast_ok && col0 + 32 <= p.N;
+        // ---- issue everything that does not depend on the accumulator first (latency hidden behind TMEM/smem) ----
+        float bs[8], cs[8];
+        uint4 res[4];
+        if (fast) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { bs[j] = 0.f; cs[j] = 0.f; }
+          if (p.bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + lc));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + lc) + 1);
+            bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+          }
+          if (p.ln_stats) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + lc));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + lc) + 1);
+            cs[0] = s0.x; cs[1] = s0.y; cs[2] = s0.z; cs[3] = s0.w; cs[4] = s1.x; cs[5] = s1.y; cs[6] = s1.z; cs[7] = s1.w;
+          }
+          if (p.residual) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              res[it] = rok_t[it] ? *reinterpret_cast<const uint4*>(p.residual + orow_t[it] * (long long)p.ldc + col0 + lc)
+                                  : make_uint4(0u, 0u, 0u, 0u);   // plain load: residual may alias out
+          }
+        }
+        if (!waited) {
+          mbar_wait(&ctrl->acc_full[as], aphase, 4);
+          tc_fence_after();
+          waited = true;
+        }
         uint32_t r[32];
         tmem_ld_x32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
-        epilogue_chunk(p, r, row, orow, n_blk * p.BN + c0, vec_ok);
+        if (!fast) {
+          const int row = m_blk * BM + q * 32 + lane;
+          long long orow = row;
+          if (p.grp_rows > 0) orow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows);
+          epilogue_chunk(p, r, row, orow, col0, vec_ok, own_r, own_n);
+          continue;
+        }
+        // ---- transpose the raw fp32 accumulators through the per-warp staging buffer ----
+        // lane = row writes 8 x 16 B with the chunk index XOR (row & 7) (conflict-free both ways)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rl = it * 8 + lr;
+          const int cj = (lane & 3) * 2;
+          const float4 a = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj) ^ (rl & 7)) << 2));
+          const float4 b = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj + 1) ^ (rl & 7)) << 2));
+          float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(lnr[it], o[j], fmaf(lnn[it], cs[j], bs[j]));
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = gelu_fast(o[j]);
+          }
+          if (p.residual) {
+            const float2 r0 = unpack_bf16x2(res[it].x), r1 = unpack_bf16x2(res[it].y), r2 = unpack_bf16x2(res[it].z),
+                         r3 = unpack_bf16x2(res[it].w);
+            o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y; o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
+          }
+          uint4 w;
+          w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+          w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+          if (p.stats_out) {   // statistics of the STORED (bf16-rounded) values
+            const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z), f3 = unpack_bf16x2(w.w);
+            st1[it] += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+            st2[it] = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, st2[it]))));
+            st2[it] = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, fmaf(f3.y, f3.y, st2[it]))));
+          }
+          if (rok_t[it]) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow_t[it] * (long long)p.ldc + col0 + lc) = w;
+        }
+      }
+      if (!waited) {   // this warp had no chunk in this tile (BN == 32): still consume the phase
+        mbar_wait(&ctrl->acc_full[as], aphase, 4);
+        tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
+      if (p.stats_out) {
+        // deterministic partials (no atomics): slot (n_blk, half) of every row this warp covers
+        const int parts = 2 * p.tiles_n, part = 2 * n_blk + half;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float a = st1[it], b = st2[it];
+          a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+          if ((lane & 3) == 0 && rok_t[it])
+            *reinterpret_cast<float2*>(p.stats_out + (orow_t[it] * parts + part) * 2) = make_float2(a, b);
+        }
+      }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -231,6 +372,17 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16
   float acc = 0.f;
   for (int k = 0; k < p.K; ++k)
     acc += __bfloat162float(A[(long long)row * lda + k]) * __bfloat162float(W[(long long)col * ldw + k]);
+  if (p.ln_stats) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < p.ln_parts; ++k) {
+      s1 += p.ln_stats[((long long)row * p.ln_parts + k) * 2];
+      s2 += p.ln_stats[((long long)row * p.ln_parts + k) * 2 + 1];
+    }
+    const float mu = s1 * p.ln_inv_k;
+    const float var = fmaxf(s2 * p.ln_inv_k - mu * mu, 0.f);
+    const float r = rsqrtf(var + p.ln_eps);
+    acc = r * (acc - mu * p.ln_colsum[col]);
+  }
   if (p.bias) acc += p.bias[col];
   if (p.act == 1) acc = gelu_erf(acc);
   long long orow = row;
@@ -254,6 +406,11 @@ cudaError_t g_attr_err = cudaSuccess;
 
 }  // namespace
 
+int gemm_stats_parts(int N, int force_bn) {
+  const int bn = force_bn > 0 ? force_bn : pick_bn(N);
+  return 2 * ((N + bn - 1) / bn);
+}
+
 int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   LMV_REQUIRE(a.A && a.W && a.out, "gemm: null pointer");
   LMV_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
@@ -269,11 +426,19 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   p.tiles_n = (a.N + p.BN - 1) / p.BN;
   p.k_blocks = (a.K + BK - 1) / BK;
   const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
-  p.num_stages = std::min(kMaxStages, (kSmemLimit - 2048) / stage_bytes);
+  p.num_stages = std::min(kMaxStages, (kSmemLimit - 2048 - kEpiWarps * kStageF32) / stage_bytes);
   p.bias = a.bias; p.residual = a.residual; p.out = a.out;
   p.ldc = a.ldc; p.out_fp32 = a.out_fp32; p.act = a.act;
   p.grp_rows = a.grp_rows; p.grp_stride = a.grp_stride;
-  op->smem_bytes = 2048 + p.num_stages * stage_bytes;
+  LMV_REQUIRE((a.ln_stats == nullptr) == (a.ln_colsum == nullptr), "gemm: ln_stats and ln_colsum go together");
+  LMV_REQUIRE(a.ln_colsum == nullptr || (reinterpret_cast<uintptr_t>(a.ln_colsum) & 15) == 0, "gemm: ln_colsum must be 16-byte aligned");
+  p.ln_stats = a.ln_stats; p.ln_colsum = a.ln_colsum; p.ln_eps = a.ln_eps; p.ln_inv_k = 1.0f / (float)a.K;
+  p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1;
+  LMV_REQUIRE(p.ln_parts <= 4, "gemm: at most 4 LayerNorm statistics partials per row");
+  p.stats_out = a.stats_out;
+  LMV_REQUIRE(a.stats_out == nullptr || (a.N % 32 == 0 && a.ldc % 8 == 0 && !a.out_fp32),
+              "gemm: stats_out needs N % 32 == 0, ldc % 8 == 0 and a bf16 output");
+  op->smem_bytes = 2048 + kEpiWarps * kStageF32 + p.num_stages * stage_bytes;
   op->grid = std::min(p.tiles_m * p.tiles_n, device_sm_count());
   {
     uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
@@ -289,6 +454,15 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
     int rc = encode_tmap_bf16(&op->tmB, a.W, 2, dims, strides, box, 128);
     if (rc) return rc;
   }
+  op->tmR = op->tmA;
+  p.prefetch_res = 0;
+  if (a.residual && a.grp_rows == 0 && a.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t strides[1] = {(uint64_t)a.ldc * 2};
+    uint32_t box[2] = {(uint32_t)std::min(p.BN, ((a.N + 7) / 8) * 8), BM};
+    if (encode_tmap_bf16(&op->tmR, a.residual, 2, dims, strides, box, 0) == LMV_OK) p.prefetch_res = 1;
+    else op->tmR = op->tmA;
+  }
   return LMV_OK;
 }
 
@@ -297,7 +471,7 @@ int gemm_run(const GemmOp& op, cudaStream_t stream) {
     g_attr_err = cudaFuncSetAttribute(gemm_bf16_tn_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   });
   LMV_CUDA_OK(g_attr_err);
-  gemm_bf16_tn_tcgen05<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tmA, op.tmB, op.p);
+  gemm_bf16_tn_tcgen05<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tmA, op.tmB, op.tmR, op.p);
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -307,6 +481,9 @@ int gemm_simt_run(const GemmArgs& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.bias = a.bias; p.residual = a.residual; p.out = a.out; p.ldc = a.ldc; p.out_fp32 = a.out_fp32; p.act = a.act;
   p.grp_rows = a.grp_rows; p.grp_stride = a.grp_stride;
+  p.ln_stats = a.ln_stats; p.ln_colsum = a.ln_colsum; p.ln_eps = a.ln_eps; p.ln_inv_k = 1.0f / (float)a.K;
+  p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1;
+  p.stats_out = nullptr;   // the SIMT path gets its row statistics from row_stats_run (kernels.h)
   const long long total = (long long)a.M * a.N;
   gemm_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a.A, a.lda, a.W, a.ldw, p);
   LMV_CUDA_OK(cudaGetLastError());

@@ -12,8 +12,19 @@ struct PosLnArgs {
   bf16* norm_out;       // nullable, [B, T, C]
   int B, H, W, T, C;
   float eps;
+  float* stats_out = nullptr;   // nullable, [B*T][2]: (sum_c v, sum_c v^2) of the bf16-rounded resid_out row (LayerNorm fold input)
 };
 int posembed_ln_run(const PosLnArgs& a, cudaStream_t s);
+
+// TMA-tiled x' = x + dwconv(x) (+ statistics) — posembed.cu; used whenever resid_out is wanted without norm_out
+struct PosEmbedOp {
+  CUtensorMap tm;
+  PosLnArgs a;
+  int TW, TH, tiles_x, tiles_y, cbox, ncb, smem, sub_bytes, threads;
+};
+bool posembed_tile_supported(const PosLnArgs& a);
+int posembed_tile_prepare(const PosLnArgs& a, PosEmbedOp* op);
+int posembed_tile_run(const PosEmbedOp& op, cudaStream_t s);
 
 struct LnArgs {
   const bf16* in;       // [R, C]
@@ -27,6 +38,9 @@ struct LnArgs {
 };
 int layernorm_run(const LnArgs& a, cudaStream_t s);
 
+// stats[r] = (sum_c x[r,c], sum_c x[r,c]^2) of dense bf16 rows — statistics producer of the SIMT cross-check path
+int row_stats_run(const bf16* x, float* stats, int R, int C, cudaStream_t s);
+
 struct AttnArgs {
   const bf16 *q, *k, *v;
   bf16* out;
@@ -38,6 +52,10 @@ struct AttnArgs {
 int attention_simt_run(const AttnArgs& a, cudaStream_t s);
 int attention_tc_run(const AttnArgs& a, cudaStream_t s);      // tcgen05 self/cross attention (attention.cu)
 bool attention_tc_supported(const AttnArgs& a);
+// few queries (meta tokens) x many keys (image tokens): split-N tcgen05 kernel + partial merge (attention_meta.cu)
+bool attention_meta_supported(const AttnArgs& a);
+size_t attention_meta_workspace(const AttnArgs& a);
+int attention_meta_run(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 struct StemArgs {
   const void* x;  // NCHW, f32 or bf16

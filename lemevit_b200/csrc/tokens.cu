@@ -2,6 +2,8 @@
 // im2col for the strided 3x3 convolutions (which then run on the tcgen05 GEMM), the classification
 // tail and the NCHW export of the backbone feature maps.  All activations are token-major
 // [B, T, C] bf16 (NHWC); the reference's NCHW<->token rearranges (models/lemevit.py:548,579) vanish.
+#include <algorithm>
+
 #include "kernels.h"
 #include "umma.cuh"
 
@@ -91,6 +93,157 @@ posembed_ln_kernel(PosLnArgs a) {
       if (a.norm_out)
         reinterpret_cast<__nv_bfloat162*>(a.norm_out + off)[p] =
             __floats2bfloat162_rn((val[i].x - mean) * rstd, (val[i].y - mean) * rstd);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2 of the same op for C % 8 == 0: G lanes per token, each lane owns 8 consecutive channels (one 16-byte vector)
+// per ITER; consecutive lanes -> consecutive 16-byte chunks (fully coalesced), the 9 taps x 8 channels of depthwise
+// weights live in registers (ITERS == 1) and are reused over `iters` tokens; a block covers a compact run of
+// ~4 image rows so the vertical taps hit L1.  Emits the LayerNorm statistics of the stored (bf16-rounded) row
+// so that the consuming GEMM can fold norm1 into its epilogue (gemm.cu).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+template <int G, int ITERS>
+__global__ void __launch_bounds__(256)
+posembed_ln_v2_kernel(PosLnArgs a, int iters) {
+  constexpr int SLOTS = 256 / G;
+  const int slot = threadIdx.x / G, gl = threadIdx.x % G;
+  const int C = a.C, V = C >> 3, HW = a.H * a.W;
+  const long long rows = (long long)a.B * a.T;
+  const long long base = (long long)blockIdx.x * (SLOTS * iters);
+  const bool has_conv = a.dw_w != nullptr;
+  float w[ITERS == 1 ? 9 : 1][8], bias[8];
+  if (ITERS == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias[j] = 0.f;
+    if (has_conv && gl < V) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.dw_w + tap * C + gl * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.dw_w + tap * C + gl * 8) + 1);
+        w[tap][0] = w0.x; w[tap][1] = w0.y; w[tap][2] = w0.z; w[tap][3] = w0.w;
+        w[tap][4] = w1.x; w[tap][5] = w1.y; w[tap][6] = w1.z; w[tap][7] = w1.w;
+      }
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.dw_b + gl * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.dw_b + gl * 8) + 1);
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    }
+  }
+  for (int k = 0; k < iters; ++k) {
+    const long long row = base + (long long)k * SLOTS + slot;
+    const bool active = row < rows;
+    const int b = active ? (int)(row / a.T) : 0, t = active ? (int)(row % a.T) : 0;
+    const bf16* img = a.tokens + (long long)b * a.T * C;
+    const bool conv = has_conv && t < HW;
+    const int y = t / a.W, x = t - y * a.W;
+    uint4 packed[ITERS];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int v = gl + G * it;
+      float val[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) val[j] = 0.f;
+      if (active && v < V) {
+        if (conv) {
+          if (ITERS == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) val[j] = bias[j];
+          } else {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.dw_b + v * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.dw_b + v * 8) + 1);
+            val[0] = b0.x; val[1] = b0.y; val[2] = b0.z; val[3] = b0.w; val[4] = b1.x; val[5] = b1.y; val[6] = b1.z; val[7] = b1.w;
+          }
+          // issue all 9 tap loads before any arithmetic (memory-level parallelism); out-of-image taps read the
+          // clamped address and are replaced by zeros
+          uint4 tapv[9];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int yy = y + ky - 1, xx = x + kx - 1;
+              const bool ok = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+              const int yc = min(max(yy, 0), a.H - 1), xc = min(max(xx, 0), a.W - 1);
+              const uint4 ld = __ldg(reinterpret_cast<const uint4*>(img + (long long)(yc * a.W + xc) * C) + v);
+              tapv[ky * 3 + kx] = ok ? ld : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            float f[8];
+            unpack8(tapv[tap], f);
+            if (ITERS == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) val[j] = fmaf(f[j], w[tap][j], val[j]);
+            } else {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.dw_w + tap * C + v * 8));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.dw_w + tap * C + v * 8) + 1);
+              val[0] = fmaf(f[0], w0.x, val[0]); val[1] = fmaf(f[1], w0.y, val[1]);
+              val[2] = fmaf(f[2], w0.z, val[2]); val[3] = fmaf(f[3], w0.w, val[3]);
+              val[4] = fmaf(f[4], w1.x, val[4]); val[5] = fmaf(f[5], w1.y, val[5]);
+              val[6] = fmaf(f[6], w1.z, val[6]); val[7] = fmaf(f[7], w1.w, val[7]);
+            }
+          }
+        } else {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(img + (long long)t * C) + v);
+          unpack8(u, val);
+        }
+      }
+      // round to the stored precision first: the statistics must describe exactly what the consumer reads
+      uint4 pk;
+      pk.x = pack_bf16x2(val[0], val[1]); pk.y = pack_bf16x2(val[2], val[3]);
+      pk.z = pack_bf16x2(val[4], val[5]); pk.w = pack_bf16x2(val[6], val[7]);
+      packed[it] = pk;
+      unpack8(pk, val);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1 += val[j]; s2 = fmaf(val[j], val[j], s2); }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (!active) continue;
+    if (a.stats_out && gl == 0) *reinterpret_cast<float2*>(a.stats_out + 2 * row) = make_float2(s1, s2);
+    float mean = 0.f, rstd = 0.f;
+    if (a.norm_out) {
+      mean = s1 / (float)C;
+      // centred second pass over the registers (exactly the reference's biased variance of the rounded row)
+      float ss = 0.f;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        if (gl + G * it < V) {
+          float f[8];
+          unpack8(packed[it], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float d = f[j] - mean; ss = fmaf(d, d, ss); }
+        }
+      }
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      rstd = rsqrtf(ss / (float)C + a.eps);
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int v = gl + G * it;
+      if (v >= V) continue;
+      if (a.resid_out) reinterpret_cast<uint4*>(a.resid_out + row * C)[v] = packed[it];
+      if (a.norm_out) {
+        float f[8];
+        unpack8(packed[it], f);
+        uint4 pk;
+        pk.x = pack_bf16x2((f[0] - mean) * rstd, (f[1] - mean) * rstd); pk.y = pack_bf16x2((f[2] - mean) * rstd, (f[3] - mean) * rstd);
+        pk.z = pack_bf16x2((f[4] - mean) * rstd, (f[5] - mean) * rstd); pk.w = pack_bf16x2((f[6] - mean) * rstd, (f[7] - mean) * rstd);
+        reinterpret_cast<uint4*>(a.norm_out + row * C)[v] = pk;
+      }
     }
   }
 }
@@ -279,16 +432,65 @@ gather_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int row
   reinterpret_cast<uint4*>(dst + (long long)r * C)[v] = __ldg(reinterpret_cast<const uint4*>(src + srow * C) + v);
 }
 
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int R, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= R) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = __bfloat162float(x[row * C + c]);
+    s1 += v; s2 = fmaf(v, v, s2);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if (lane == 0) { stats[2 * row] = s1; stats[2 * row + 1] = s2; }
+}
+
 inline unsigned blocks_for(long long total, int per_block) { return (unsigned)((total + per_block - 1) / per_block); }
 
 }  // namespace
+
+template <int G, int ITERS>
+static void launch_posln_v2(const PosLnArgs& a, cudaStream_t s) {
+  constexpr int SLOTS = 256 / G;
+  const long long rows = (long long)a.B * a.T;
+  int iters = (4 * a.W + SLOTS - 1) / SLOTS;                       // ~4 image rows per block
+  iters = std::max(1, std::min(iters, 16));
+  const long long want_blocks = 2LL * device_sm_count();            // keep at least two waves of blocks
+  while (iters > 1 && (rows + (long long)SLOTS * iters - 1) / (SLOTS * iters) < want_blocks) --iters;
+  const long long per_block = (long long)SLOTS * iters;
+  posembed_ln_v2_kernel<G, ITERS><<<(unsigned)((rows + per_block - 1) / per_block), 256, 0, s>>>(a, iters);
+}
 
 int posembed_ln_run(const PosLnArgs& a, cudaStream_t s) {
   LMV_REQUIRE(a.C % 2 == 0 && a.C <= 64 * kMaxPairs, "posembed_layernorm: C must be even and <= 512");
   LMV_REQUIRE(a.T >= (a.dw_w ? a.H * a.W : 0), "posembed_layernorm: T < H*W");
   const long long rows = (long long)a.B * a.T;
   if (rows == 0) return LMV_OK;
-  posembed_ln_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(a);
+  if (posembed_tile_supported(a)) {
+    PosEmbedOp op;
+    int rc = posembed_tile_prepare(a, &op);
+    if (rc) return rc;
+    return posembed_tile_run(op, s);
+  }
+  if (a.C % 8 == 0) {
+    const int V = a.C / 8;
+    if (V <= 4) launch_posln_v2<4, 1>(a, s);
+    else if (V <= 8) launch_posln_v2<8, 1>(a, s);
+    else if (V <= 16) launch_posln_v2<16, 1>(a, s);
+    else if (V <= 32) launch_posln_v2<32, 1>(a, s);
+    else launch_posln_v2<32, 2>(a, s);
+  } else {
+    LMV_REQUIRE(a.stats_out == nullptr, "posembed_layernorm: statistics output needs C % 8 == 0");
+    posembed_ln_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(a);
+  }
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+int row_stats_run(const bf16* x, float* stats, int R, int C, cudaStream_t s) {
+  if (R == 0) return LMV_OK;
+  row_stats_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, stats, R, C);
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

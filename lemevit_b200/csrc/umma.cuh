@@ -77,6 +77,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a 2-D tile (no smem destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -202,5 +206,22 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 // exact-erf GELU (nn.GELU default): 0.5 x (1 + erf(x / sqrt 2))
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// GELU on the hot epilogues: 0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with (a, b, c) fitted so that the
+// max abs deviation from the exact-erf GELU (nn.GELU default, models/lemevit.py:528) is 2.5e-5 — 300x below the
+// bf16 rounding of the stored activation; one MUFU.TANH (2^-11 rel) + 5 FP ops instead of erff's ~25.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);   // keeps the odd polynomial monotone; gelu(|x| > 8) = x or 0 to 1e-15
+  const float x2 = xc * xc;
+  const float p = fmaf(x2, fmaf(x2, -0.00035151678863588117f, 0.037005646022512585f), 0.7975078842853727f);
+  const float t = tanh_approx(xc * p);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 
 }  // namespace lmv

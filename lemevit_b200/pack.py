@@ -17,8 +17,10 @@ ORDER of the packed list (checked entry by entry by ``lmv_plan_create`` in csrc/
       if i > 0:  [ds_w bf16[Ci, 9*Cp], ds_b f32[Ci]]   (absent when stage i-1 is 'C': nn.Identity, :711-712)
                  md_w0 bf16[4Cp,Cp] md_b0 f32 md_g1 f32 md_be1 f32 md_w3 bf16[Ci,4Cp] md_b3 f32 md_g4 f32 md_be4 f32
       for each block:  dw_w f32[9,C] dw_b f32[C]
-          'C': q_w q_b kv_w kv_b proj_w proj_b          'D': qkv1_w qkv1_b qkv2_w qkv2_b proj_x_w proj_x_b proj_c_w proj_c_b
-          'S': qkv_w qkv_b proj_w proj_b                 then: mlp0_w mlp0_b mlp3_w mlp3_b      (weights bf16 [out,in], biases f32)
+          'C': q_w q_b q_cs kv_w kv_b kv_cs proj_w proj_b
+          'D': qkv1_w qkv1_b qkv1_cs qkv2_w qkv2_b qkv2_cs proj_x_w proj_x_b proj_c_w proj_c_b
+          'S': qkv_w qkv_b qkv_cs proj_w proj_b          then: mlp0_w mlp0_b mlp0_cs mlp3_w mlp3_b
+          (weights bf16 [out,in], biases f32, *_cs = f32[out] column sums of the bf16 LayerNorm-folded weight)
   classification only:  bn_scale bn_shift norm_c_g norm_c_b (f32[CL])  [head_w bf16[ncls, CL], head_b f32[ncls]]
 
 conv weights are stored [Cout, K] with K = (ky*3 + kx)*Cin + ci (matches the im2col kernels), except stem1
@@ -119,9 +121,12 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], *, depth: Sequence[int], embed_
             for lin, ln in names:
                 if ln is None:
                     w, b = _d(sd[p + lin + ".weight"]), _d(sd[p + lin + ".bias"])
+                    h(w); f(b)
                 else:
                     w, b = _fold_ln_linear(sd, ln, p + lin)
-                h(w); f(b)
+                    h(w); f(b)
+                    # column sums of the weights AS STORED (bf16): LN(y) W^T = r (y W^T - mu colsum), csrc/gemm.cu
+                    f(w.to(torch.bfloat16).to(torch.float64).sum(dim=1))
     # ---- tail
     if not backbone:
         s = _d(sd["norm.weight"]) / torch.sqrt(_d(sd["norm.running_var"]) + BN_EPS)

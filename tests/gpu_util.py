@@ -70,6 +70,23 @@ def linear(A, W, bias=None, residual=None, gelu=False, out_dtype=torch.bfloat16,
     return out
 
 
+def stats_parts(N, simt=False):
+    return int(lib().lmv_linear_stats_parts(N, int(simt)))
+
+
+def linear_fused(A, W, bias=None, residual=None, gelu=False, ln_stats=None, ln_colsum=None, ln_eps=0.0, stats_out=None,
+                 simt=False, out=None):
+    """ln_stats: [M, parts, 2] partial sums (or [M, 2]); stats_out: [M, stats_parts(N, simt), 2]."""
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=A.device)
+    ok(lib().lmv_linear_fused(ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(residual), ptr(out), out.stride(0), M, N, K,
+                              int(gelu), BF16, ptr(ln_stats), (ln_stats.numel() // (2 * M)) if ln_stats is not None else 1,
+                              ptr(ln_colsum), float(ln_eps), ptr(stats_out), int(simt), stream()))
+    return out
+
+
 def ref_linear(A, W, bias=None, residual=None, gelu=False):
     y = A.float() @ W.float().t()
     if bias is not None:
@@ -90,6 +107,18 @@ def attention(q, k, v, scale, impl=0):
         assert t.stride(3) == 1 and t.stride(2) == d
     ok(lib().lmv_attention(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v), v.stride(0), v.stride(1),
                            ptr(out), out.stride(0), out.stride(1), B, h, Lq, Lk, float(scale), impl, stream()))
+    return out
+
+
+def attention_meta(q, k, v, scale):
+    """Few queries x many keys (meta-token side of the cross attentions): split-N tcgen05 kernel + merge."""
+    B, Lq, h, d = q.shape
+    Lk = k.shape[1]
+    out = torch.empty((B, Lq, h * d), dtype=torch.bfloat16, device=q.device)
+    need = int(lib().lmv_attention_meta_workspace(B, h, Lq, Lk))
+    ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+    ok(lib().lmv_attention_meta(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v), v.stride(0), v.stride(1),
+                                ptr(out), out.stride(0), out.stride(1), B, h, Lq, Lk, float(scale), ptr(ws), ws.numel(), stream()))
     return out
 
 

@@ -17,6 +17,17 @@ def _norm(t, eps):
     return (t - mu) / torch.sqrt(var + eps)
 
 
+def _ln_linear(t, w, b, cs, eps=1e-6):
+    """LayerNorm folded into the linear exactly as csrc/gemm.cu does it: r (t W^T - mu colsum) + b, with colsum the
+    column sums of the STORED (bf16) weight."""
+    K = t.shape[-1]
+    assert torch.allclose(cs, w.sum(-1), rtol=1e-5, atol=1e-5), "colsum does not describe the packed weight"
+    mu = t.sum(-1, keepdim=True) / K
+    var = (t * t).sum(-1, keepdim=True) / K - mu * mu
+    r = 1.0 / torch.sqrt(var + eps)
+    return r * (t @ w.t() - mu * cs) + b
+
+
 def _attn(q, k, v, heads, scale):
     B, Lq, C = q.shape
     d = C // heads
@@ -72,23 +83,23 @@ def forward(packed, x, *, depth, embed_dim, attn_type, head_dim, queries_len, nu
         for j in range(depth[i]):
             dw_w, dw_b = nx(), nx()
             if kind == "C":
-                wq, bq, wkv, bkv, wp, bp = [nx() for _ in range(6)]
+                wq, bq, csq, wkv, bkv, cskv, wp, bp = [nx() for _ in range(8)]
             elif kind == "D":
-                wa, ba, wb, bb, wpx, bpx, wpc, bpc = [nx() for _ in range(8)]
+                wa, ba, csa, wb, bb, csb, wpx, bpx, wpc, bpc = [nx() for _ in range(10)]
             else:
-                wqkv, bqkv, wp, bp = [nx() for _ in range(4)]
-            w1, b1, w2, b2 = [nx() for _ in range(4)]
-            mlp = lambda t: _gelu(_norm(t, 1e-6) @ w1.t() + b1) @ w2.t() + b2
+                wqkv, bqkv, csqkv, wp, bp = [nx() for _ in range(5)]
+            w1, b1, cs1, w2, b2 = [nx() for _ in range(5)]
+            mlp = lambda t: _gelu(_ln_linear(t, w1, b1, cs1)) @ w2.t() + b2
             xp = _posembed(xt, H, W, dw_w, dw_b)
             if kind == "C":
                 q = _norm(c, 1e-6) @ wq.t() + bq
-                kv = _norm(xp, 1e-6) @ wkv.t() + bkv
+                kv = _ln_linear(xp, wkv, bkv, cskv)
                 a = _attn(q, kv[..., :C], kv[..., C:], heads, head_dim ** -0.5)
                 c = c + a @ wp.t() + bp
                 c = c + mlp(c)
             elif kind == "D":
                 xt = xp
-                qkv1 = _norm(xt, 1e-6) @ wa.t() + ba
+                qkv1 = _ln_linear(xt, wa, ba, csa)
                 qkv2 = _norm(c, 1e-6) @ wb.t() + bb
                 s = C ** -0.5
                 sx = math.log(M) / math.log(N) * s
@@ -103,7 +114,7 @@ def forward(packed, x, *, depth, embed_dim, attn_type, head_dim, queries_len, nu
                 toks = [xt] if backbone else [xt, c]
                 res = []
                 for t in toks:
-                    qkv = _norm(t, 1e-6) @ wqkv.t() + bqkv
+                    qkv = _ln_linear(t, wqkv, bqkv, csqkv)
                     t = t + _attn(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, head_dim ** -0.5) @ wp.t() + bp
                     res.append(t + mlp(t))
                 xt = res[0]

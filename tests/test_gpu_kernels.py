@@ -70,6 +70,57 @@ def test_linear_epilogue_gelu_residual_inplace():
     assert G.rel_err(out_g, ref_g) < TOL and G.cosine(out_g, ref_g) > 0.9999
 
 
+@pytest.mark.parametrize("M,N,K,gelu", [(1000, 288, 96, False), (777, 384, 96, True), (424, 1152, 384, False), (424, 1536, 384, True),
+                                        (300, 768, 192, True), (130, 960, 320, False), (98, 2048, 512, True), (64, 51, 64, False)])
+@pytest.mark.parametrize("simt", [False, True])
+def test_linear_layernorm_fold(M, N, K, gelu, simt):
+    """LayerNorm (no affine) -> Linear (+GELU), the norm folded into the GEMM epilogue from per-row (sum, sum^2)."""
+    y = G.bf(torch.randn(M, K, device="cuda") * 1.5 + torch.randn(M, 1, device="cuda") * 2.0)   # rows with large means
+    W = _rand(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    stats = torch.stack([y.float().sum(-1), (y.float() ** 2).sum(-1)], dim=1).contiguous()
+    if M % 2 == 0:   # the same statistics split into 3 partials per row (what a multi-tile producer GEMM emits)
+        stats = torch.stack([stats * 0.5, stats * 0.25, stats * 0.25], dim=1).contiguous()
+    colsum = W.float().sum(-1).contiguous()
+    ref = G.ref_linear(torch.nn.functional.layer_norm(y.float(), (K,), eps=1e-6), W, bias, gelu=gelu)
+    out = G.linear_fused(y, W, bias, gelu=gelu, ln_stats=stats, ln_colsum=colsum, ln_eps=1e-6, simt=simt)
+    assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999, G.describe_mismatch(out.float(), ref, TOL)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 96, 96), (777, 192, 192), (424, 384, 384), (130, 320, 320), (98, 512, 512), (50, 32, 64)])
+@pytest.mark.parametrize("simt", [False, True])
+def test_linear_residual_row_statistics(M, N, K, simt):
+    """x += A W^T + b in place, and stats_out += (sum_n x, sum_n x^2) per row (input of the next LayerNorm fold)."""
+    A, W = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    x = _rand(M, N)
+    ref = G.ref_linear(A, W, bias, residual=x)
+    parts = torch.full((M, G.stats_parts(N, simt), 2), float("nan"), device="cuda")
+    out = G.linear_fused(A, W, bias, residual=x, out=x, stats_out=parts, simt=simt)
+    assert out.data_ptr() == x.data_ptr() and G.rel_err(out, ref) < TOL
+    stats = parts.sum(1)     # the statistics describe the STORED bf16 rows exactly (up to fp32 summation order)
+    o = out.float()
+    assert torch.allclose(stats[:, 0], o.sum(-1), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[:, 1], (o * o).sum(-1), rtol=1e-4, atol=1e-3)
+    # and the run is deterministic
+    x2 = x.clone()
+    parts2 = torch.empty_like(parts)
+    G.linear_fused(A, W, bias, residual=None, out=x2, stats_out=parts2, simt=simt)
+    G.linear_fused(A, W, bias, residual=None, out=x, stats_out=parts, simt=simt)
+    assert torch.equal(x, x2) and torch.equal(parts, parts2)
+
+
+def test_gelu_epilogue_close_to_exact_erf():
+    """The tcgen05 epilogue uses a tanh-form GELU fitted to the exact-erf GELU (max abs deviation 2.5e-5 + MUFU.TANH
+    2^-11); the SIMT cross-check kernel uses erff.  fp32 outputs isolate the activation error."""
+    M, N, K = 256, 256, 64
+    A = G.bf(torch.linspace(-6, 6, M * K, device="cuda").reshape(M, K))
+    W = G.bf(torch.eye(N, K, device="cuda"))
+    out = G.linear(A, W, gelu=True, out_dtype=torch.float32)
+    ref = G.ref_linear(A, W, gelu=True)
+    assert float((out - ref).abs().max()) < 2e-3
+
+
 def test_linear_many_tiles_persistent_loop():
     # > 148 * 2 tiles: exercises the smem-ring and TMEM double-buffer phase wrap-around
     M, N, K = 128 * 40, 1024, 320
@@ -96,7 +147,8 @@ def test_linear_rejects_bad_arguments():
 
 
 # ---- positional conv + LayerNorm / LayerNorm --------------------------------------------------------
-@pytest.mark.parametrize("B,H,W,C,M", [(2, 14, 14, 384, 16), (3, 7, 5, 64, 0), (2, 28, 28, 192, 0), (1, 9, 11, 512, 16)])
+@pytest.mark.parametrize("B,H,W,C,M", [(2, 14, 14, 384, 16), (3, 7, 5, 64, 0), (2, 28, 28, 192, 0), (1, 9, 11, 512, 16),
+                                       (3, 56, 56, 96, 0), (2, 13, 9, 320, 16), (2, 8, 8, 32, 0), (5, 28, 28, 128, 0), (2, 6, 6, 34, 0)])
 def test_posembed_layernorm(B, H, W, C, M):
     T = H * W + M
     tok = _rand(B, T, C)
@@ -107,16 +159,30 @@ def test_posembed_layernorm(B, H, W, C, M):
     resid = torch.empty_like(tok)
     norm = torch.empty_like(tok)
     L = G.lib()
-    G.ok(L.lmv_posembed_layernorm(G.ptr(tok), G.ptr(dw_packed), G.ptr(db), G.ptr(resid), G.ptr(norm), B, H, W, T, C, 1e-6, G.stream()))
+    stats = torch.full((B * T, 2), -1.0, device="cuda") if C % 8 == 0 else None
+    G.ok(L.lmv_posembed_layernorm(G.ptr(tok), G.ptr(dw_packed), G.ptr(db), G.ptr(resid), G.ptr(norm), G.ptr(stats), B, H, W, T, C, 1e-6, G.stream()))
     x = tok[:, :H * W].float().transpose(1, 2).reshape(B, C, H, W)
     xt = (x + torch.nn.functional.conv2d(x, dw, db, padding=1, groups=C)).flatten(2).transpose(1, 2)
     full = torch.cat([xt, tok[:, H * W:].float()], dim=1)
     ref_n = torch.nn.functional.layer_norm(full, (C,), eps=1e-6)
     assert G.rel_err(resid, full) < TOL
     assert G.rel_err(norm, ref_n) < TOL and G.cosine(norm, ref_n) > 0.9999
+    if stats is not None:   # statistics describe the STORED (bf16) rows exactly
+        r = resid.float().reshape(B * T, C)
+        assert torch.allclose(stats[:, 0], r.sum(-1), rtol=1e-4, atol=1e-3)
+        assert torch.allclose(stats[:, 1], (r * r).sum(-1), rtol=1e-4, atol=1e-3)
+    if stats is not None:   # resid + stats only: the TMA-tiled kernel the block schedule uses
+        resid2 = torch.empty_like(tok)
+        stats2 = torch.full((B * T, 2), -1.0, device="cuda")
+        G.ok(L.lmv_posembed_layernorm(G.ptr(tok), G.ptr(dw_packed), G.ptr(db), G.ptr(resid2), None, G.ptr(stats2), B, H, W, T, C, 1e-6, G.stream()))
+        assert G.rel_err(resid2, full) < TOL
+        r2 = resid2.float().reshape(B * T, C)
+        assert torch.allclose(stats2[:, 0], r2.sum(-1), rtol=1e-4, atol=1e-3)
+        assert torch.allclose(stats2[:, 1], (r2 * r2).sum(-1), rtol=1e-4, atol=1e-3)
+        assert torch.equal(resid2, resid), "tiled and per-token kernels must round identically"
     # LayerNorm-only mode (no conv), norm output only
     norm2 = torch.empty_like(tok)
-    G.ok(L.lmv_posembed_layernorm(G.ptr(tok), None, None, None, G.ptr(norm2), B, H, W, T, C, 1e-6, G.stream()))
+    G.ok(L.lmv_posembed_layernorm(G.ptr(tok), None, None, None, G.ptr(norm2), None, B, H, W, T, C, 1e-6, G.stream()))
     assert G.rel_err(norm2, torch.nn.functional.layer_norm(tok.float(), (C,), eps=1e-6)) < TOL
 
 
@@ -199,6 +265,25 @@ def test_attention(B, h, Lq, Lk, impl):
     out = G.attention(q, k, v, scale, impl=impl)
     ref = G.ref_attention(q, k, v, scale)
     assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999
+
+
+@pytest.mark.parametrize("B,h,Lq,Lk", [(2, 3, 16, 3136), (2, 6, 16, 784), (1, 2, 16, 500), (3, 4, 16, 300), (1, 3, 16, 128),
+                                       (2, 8, 16, 1000), (1, 1, 8, 129), (2, 3, 16, 16384)])
+def test_attention_meta_queries_over_image_tokens(B, h, Lq, Lk):
+    """CrossAttention / DualCrossAttention meta-token branch: 16 queries per head, softmax over all N image tokens."""
+    C = h * 32
+    qc = _rand(B, Lq, 3 * C)
+    kvx = _rand(B, Lk, 3 * C)
+    q = qc[:, :, :C].unflatten(2, (h, 32))
+    k = kvx[:, :, C:2 * C].unflatten(2, (h, 32))
+    v = kvx[:, :, 2 * C:].unflatten(2, (h, 32))
+    scale = C ** -0.5 * 3.0        # peaky enough that the per-tile maxima differ
+    out = G.attention_meta(q, k, v, scale)
+    ref = G.ref_attention(q, k, v, scale)
+    assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999, G.describe_mismatch(out.float().flatten(0, 1), ref.flatten(0, 1), TOL)
+    assert torch.equal(out, G.attention_meta(q, k, v, scale)), "split-softmax merge must be deterministic"
+    simt = G.attention(q, k, v, scale, impl=1)
+    assert G.rel_err(out, simt.float()) < TOL
 
 
 # ---- tail / export ------------------------------------------------------------------------------------
