@@ -20,6 +20,6 @@ run bench 600 python bench.py --steps 20 --warmup 5
 TAILN=80 run ops_base256 300 python tools/quick_bench.py lemevit_base 256 --ops
 if [ -z "$SKIP_NCU" ]; then
   run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv python tools/ncu_target.py lemevit_base 256 2
-  run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-gemm_bf16} -s ${NCU_SKIP:-700} -c 3 -f -o gpurun_out/prof_$TAG python tools/ncu_target.py lemevit_base 256 2
+  run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-gemm_bf16} -s ${NCU_SKIP:-120} -c 3 -f -o gpurun_out/prof_$TAG python tools/ncu_target.py lemevit_base 256 2
 fi
 for extra in "$@"; do :; done
