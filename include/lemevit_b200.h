@@ -72,6 +72,9 @@ void lmv_plan_destroy(lmv_plan* plan);
 /* images processed per pass through the network (0 = whole batch at once); smaller chunks keep the
  * producer->consumer activations L2-resident. */
 int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
+/* schedule options (A/B switches; every schedule is rebuilt afterwards).  Known names:
+ *   "fused_mlp" (default 1): run `x + mlp(norm2(x))` as ONE kernel (lmv_mlp_fused) where the shape allows it. */
+int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
 /* bring-up switch: 1 routes every GEMM / attention through the plain SIMT cross-check kernels. */
 int lmv_plan_set_debug_simt(lmv_plan* plan, int enable);
 size_t lmv_workspace_bytes(const lmv_plan* plan, int batch, int H, int W);
@@ -119,6 +122,14 @@ int lmv_linear_fused(const void* A, int lda, const void* W, int ldw, const float
                      int ldc, int M, int N, int K, int act_gelu, int out_dtype, const float* ln_stats, int ln_parts,
                      const float* ln_colsum, float ln_eps, float* stats_out, int use_simt, void* stream);
 int lmv_linear_stats_parts(int N, int use_simt);
+/* Fused MLP branch of a LeMeBlock — `x + mlp(norm2(x))`, models/lemevit.py:526-530 with :562,564,601,633,635 — in one
+ * kernel: out[R,C] = resid + W2 gelu(W1 LN(x) + b1) + b2; the [R,Hd] hidden activation never leaves the SM.
+ * x: [R,C] bf16 dense raw rows; ln_stats [R][ln_parts][2] + colsum1 [Hd] fold the LayerNorm exactly as in
+ * lmv_linear_fused (both null: x is used as is); resid nullable (= x); out may alias x.
+ * Requires C % 32 == 0, 32 <= C <= 384, Hd % 128 == 0 (LMV_ERR_UNSUPPORTED otherwise). */
+int lmv_mlp_fused(const void* x, const void* resid, void* out, const void* W1, const float* b1, const float* colsum1,
+                  const void* W2, const float* b2, const float* ln_stats, int ln_parts, float ln_eps, int R, int C, int Hd,
+                  void* stream);
 /* same contract as lmv_linear on the SIMT cross-check kernel */
 int lmv_linear_simt(const void* A, int lda, const void* W, int ldw, const float* bias, const void* residual,
                     void* out, int ldc, int M, int N, int K, int act_gelu, int out_dtype, void* stream);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "lmv_plan_destroy": (None, [_vp]),
     "lmv_plan_set_chunk": (_i, [_vp, _i]),
     "lmv_plan_set_debug_simt": (_i, [_vp, _i]),
+    "lmv_plan_set_option": (_i, [_vp, C.c_char_p, _i]),
     "lmv_plan_set_profile": (_i, [_vp, _i]),
     "lmv_plan_get_profile": (_i, [_vp, _vp, _i]),
     "lmv_plan_profile_report": (_i, [_vp, C.c_char_p, _i]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "lmv_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lmv_linear_fused": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _f, _vp, _i, _vp]),
     "lmv_linear_stats_parts": (_i, [_i, _i]),
+    "lmv_mlp_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _i, _i, _vp]),
     "lmv_linear_simt": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "lmv_posembed_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "lmv_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),

@@ -102,8 +102,8 @@ struct StageW {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
-enum OpClass { OP_GEMM = 0, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
-static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
+enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
+static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "mlp_fused_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
                                                           "posembed_layernorm", "layernorm", "im2col", "misc"};
 struct OpRec {
   Launch fn;
@@ -144,6 +144,7 @@ struct lmv_plan {
   std::vector<lmv::StageW> stages;
   int chunk = 0;
   int debug_simt = 0;
+  int fused_mlp = 1;
   int profile = 0;
   std::vector<cudaEvent_t> events;          // profile mode: one event between consecutive launches
   std::vector<const lmv::OpRec*> pending;   // ops whose events have not been harvested yet
@@ -409,6 +410,25 @@ struct Builder {
     a.stats_out = stats;
     gemm(a);
   }
+  // x <- x + mlp(norm2(x)) (models/lemevit.py:562,564,601,633,635): one fused kernel when the shape allows it,
+  // otherwise fc1 (+LN fold, bias, GELU) and fc2 (+bias, residual) on the GEMM with the hidden activation in `hid`
+  void mlp(bf16* x, const float* stats, int parts, const BlockW& bw, int R, int C, int Hd, bf16* hid) {
+    if (rc) return;
+    if (!simt && plan->fused_mlp && mlp_fused_supported(C, Hd)) {
+      MlpArgs a;
+      a.x = x; a.out = x; a.W1 = bw.w1; a.b1 = bw.b1; a.cs1 = bw.cs1; a.W2 = bw.w2; a.b2 = bw.b2;
+      a.ln_stats = stats; a.ln_parts = parts; a.ln_eps = 1e-6f; a.R = R; a.C = C; a.Hd = Hd;
+      MlpOp op;
+      rc = mlp_fused_prepare(a, &op);
+      if (rc) return;
+      char d[120];
+      snprintf(d, sizeof(d), "mlp_fused R=%d C=%d Hd=%d", R, C, Hd);
+      sc->push([op](cudaStream_t s) { return mlp_fused_run(op, s); }, OP_MLP, 4.0 * R * C * (double)Hd, 4.0 * R * C, d);
+      return;
+    }
+    ln_linear(x, stats, parts, bw.w1, bw.b1, bw.cs1, R, Hd, C, hid, 1);
+    linear(hid, Hd, bw.w2, bw.b2, R, C, Hd, x, C, 0, x);
+  }
   void posln(const bf16* tok, const float* dw_w, const float* dw_b, bf16* resid, bf16* norm, int B, int H, int W, int T,
              int C, float* stats = nullptr) {
     if (rc) return;
@@ -570,8 +590,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         int parts2 = 1;
         b.linear_res_stats(xn, bw.wp1, bw.bp1, B * N, C, C, x, stats2, &parts2);     // x += proj_x(attn), stats2 = LN2 statistics
         b.linear(cn, C, bw.wp2, bw.bp2, B * M, C, C, cc, C, 0, cc);
-        b.ln_linear(x, stats2, parts2, bw.w1, bw.b1, bw.cs1, B * N, Hd, C, hid, 1);  // norm2 folded, bias + GELU fused
-        b.linear(hid, Hd, bw.w2, bw.b2, B * N, C, Hd, x, C, 0, x);
+        b.mlp(x, stats2, parts2, bw, B * N, C, Hd, hid);                             // norm2 folded, hidden stays on chip
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.w1, bw.b1, B * M, Hd, C, chid, Hd, 1);
         b.linear(chid, Hd, bw.w2, bw.b2, B * M, C, Hd, cc, C, 0, cc);
@@ -592,8 +611,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         }
         int parts2 = 1;
         b.linear_res_stats(xn, bw.wp1, bw.bp1, B * T, C, C, x, stats2, &parts2);
-        b.ln_linear(x, stats2, parts2, bw.w1, bw.b1, bw.cs1, B * T, Hd, C, hid, 1);
-        b.linear(hid, Hd, bw.w2, bw.b2, B * T, C, Hd, x, C, 0, x);
+        b.mlp(x, stats2, parts2, bw, B * T, C, Hd, hid);
       }
     }
     // ---- backbone outputs: x after stages 1..S-1 as NCHW (semantic_segmentation/.../lemevit.py:800-820)
@@ -820,6 +838,16 @@ int lmv_plan_set_chunk(lmv_plan* plan, int n) {
   plan->chunk = n;
   return LMV_OK;
 }
+int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
+  if (!plan || !name) return fail(LMV_ERR_INVALID, "set_option: null argument");
+  int rc = harvest_profile(plan);
+  if (rc) return rc;
+  const std::string n(name);
+  if (n == "fused_mlp") plan->fused_mlp = value ? 1 : 0;
+  else return fail(LMV_ERR_INVALID, "set_option: unknown option " + n);
+  plan->cache.clear();   // schedules are rebuilt with the new setting
+  return LMV_OK;
+}
 int lmv_plan_set_debug_simt(lmv_plan* plan, int enable) {
   if (!plan) return fail(LMV_ERR_INVALID, "null plan");
   plan->debug_simt = enable ? 1 : 0;
@@ -908,6 +936,19 @@ int lmv_linear_fused(const void* A, int lda, const void* W, int ldw, const float
   int rc = gemm_prepare(a, &op);
   if (rc) return rc;
   return gemm_run(op, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_mlp_fused(const void* x, const void* resid, void* out, const void* W1, const float* b1, const float* colsum1,
+                  const void* W2, const float* b2, const float* ln_stats, int ln_parts, float ln_eps, int R, int C, int Hd,
+                  void* stream) {
+  MlpArgs a;
+  a.x = static_cast<const bf16*>(x); a.resid = static_cast<const bf16*>(resid); a.out = static_cast<bf16*>(out);
+  a.W1 = static_cast<const bf16*>(W1); a.b1 = b1; a.cs1 = colsum1; a.W2 = static_cast<const bf16*>(W2); a.b2 = b2;
+  a.ln_stats = ln_stats; a.ln_parts = ln_parts; a.ln_eps = ln_eps; a.R = R; a.C = C; a.Hd = Hd;
+  MlpOp op;
+  int rc = mlp_fused_prepare(a, &op);
+  if (rc) return rc;
+  return mlp_fused_run(op, static_cast<cudaStream_t>(stream));
 }
 
 int lmv_linear_stats_parts(int N, int use_simt) { return use_simt ? 1 : gemm_stats_parts(N); }

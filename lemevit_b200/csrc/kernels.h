@@ -98,4 +98,38 @@ int broadcast_rows_run(const bf16* src, bf16* dst, int rows, int C, int B, long 
 int gather_rows_run(const bf16* src, bf16* dst, int rows, int C, int grp_rows, int grp_stride, int grp_off,
                     cudaStream_t s);
 
+// ------------------------------------------------------------------------------------------------
+// fused MLP branch (mlp_fused.cu): out = resid + W2 gelu(W1' LN(x) + b1') + b2, hidden activation kept on chip
+// ------------------------------------------------------------------------------------------------
+struct MlpArgs {
+  const bf16* x = nullptr;       // [R, C] raw rows (LayerNorm folded through ln_stats / cs1), dense
+  const bf16* resid = nullptr;   // [R, C] residual (null: x)
+  bf16* out = nullptr;           // [R, C] (may alias x / resid)
+  const bf16* W1 = nullptr;      // [Hd, C]  (LayerNorm affine folded in)
+  const float* b1 = nullptr;     // [Hd]
+  const float* cs1 = nullptr;    // [Hd] column sums of W1 (with ln_stats) or null
+  const bf16* W2 = nullptr;      // [C, Hd]
+  const float* b2 = nullptr;     // [C]
+  const float* ln_stats = nullptr;   // [R][ln_parts][2] partial (sum, sum^2) of the x rows, or null (input already normalised)
+  int ln_parts = 1;
+  float ln_eps = 1e-6f;
+  int R = 0, C = 0, Hd = 0;
+};
+struct MlpParams {
+  int R, C, Hd, tiles, kb1, chunks, nparts2, n2, nx, nh, n1slots, n2slots, slot2_bytes, const_bytes;
+  const float *b1, *cs1, *b2, *ln_stats;
+  int ln_parts;
+  float ln_eps, ln_inv_k;
+  const bf16* resid;
+  bf16* out;
+};
+struct MlpOp {
+  CUtensorMap tmX, tmW1, tmW2;
+  MlpParams p;
+  int grid = 0, smem_bytes = 0;
+};
+bool mlp_fused_supported(int C, int Hd);
+int mlp_fused_prepare(const MlpArgs& a, MlpOp* op);
+int mlp_fused_run(const MlpOp& op, cudaStream_t s);
+
 }  // namespace lmv

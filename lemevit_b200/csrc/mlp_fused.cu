@@ -1,0 +1,447 @@
+// out = x + W2 · gelu(W1' · LN(x) + b1') + b2      — the whole MLP branch of a LeMeBlock in ONE kernel.
+// Reference: `self.mlp = nn.Sequential(Linear, Identity, GELU, Linear)` (models/lemevit.py:526-530) applied as
+// `x = x + self.drop_path(self.mlp(self.norm2(x)))` (:562,564 D blocks; :601 C blocks; :633,635 S blocks).
+// MLP is 2/3 of the linear FLOPs of the network; unfused, the [rows, 4C] hidden activation is written to and read
+// back from HBM (8C bytes/token against 4C for x in + x out).  Here it only ever exists as TMEM accumulators and
+// bf16 shared-memory tiles.
+//
+// sm_100a design — persistent CTA (one per SM) over 128-row tiles, hidden dimension in chunks of 128, warp-specialised:
+//   warp 0      TMA producer A: the X tile (128 x C as K-blocks of 64, 128B swizzle) + ring 1 of W1' boxes [128 hidden x 64 k]
+//   warp 1      TMA producer B: ring 2 of W2 boxes [n2 out x 64 hidden]   (its own ring: W1' prefetch never queues behind
+//               W2 boxes that wait for the epilogue)
+//   warp 2      one thread issues tcgen05.mma:  fc1(g): acc1[g&1][128 x 128] = X · W1'[g]^T      (K = C)
+//                                               fc2(g): acc2[128 x C]      += H_g · W2[:, g]^T    (K = 128)
+//               issue order fc1(g+1), fc2(g): the tensor pipe works on the next hidden chunk while the epilogue warps turn
+//               chunk g into bf16
+//   warps 4..19 epilogue (4 warps per TMEM lane quarter, each owning 32 of the chunk's 128 columns): tcgen05.ld acc1 -> LayerNorm fold
+//               (r·acc + (−r·mu)·colsum + b1, constants in smem) -> GELU (packed fp32 math + MUFU.TANH) -> bf16 ->
+//               128B-swizzled K-major smem tiles H_g (the A operand of fc2).  After the last chunk of a tile they run the
+//               output epilogue: acc2 + b2 + residual -> bf16 -> global.
+// TMEM: acc2 in columns [0, C <= 256), the two acc1 buffers in columns [256, 512).
+// LayerNorm (norm2) is folded exactly as in gemm.cu: the producer of x emitted per-row (sum, sum^2) partials.
+#include <algorithm>
+#include <mutex>
+
+#include "common.h"
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace lmv {
+
+namespace {
+
+constexpr int BM = 128;          // rows per tile
+constexpr int BK = 64;           // K-block (one 128B swizzle span of bf16)
+constexpr int HC = 128;          // hidden columns per chunk
+constexpr int kEpiWarps = 16;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+constexpr int kMaxSlots = 8;
+constexpr int kXBlockBytes = BM * BK * 2;      // 16 KB
+constexpr int kHidBytes = BM * HC * 2;         // 32 KB per hidden buffer (2 K-blocks)
+constexpr int kW1BoxBytes = HC * BK * 2;       // 16 KB
+constexpr int kAcc1Col = 256;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct Ctrl {
+  uint64_t x_full[2], x_empty[2];
+  uint64_t w1_full[kMaxSlots], w1_empty[kMaxSlots];
+  uint64_t w2_full[kMaxSlots], w2_empty[kMaxSlots];
+  uint64_t acc1_full[2], acc1_empty[2];
+  uint64_t hid_full[2], hid_empty[2];
+  uint64_t acc2_full, acc2_empty;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Ctrl) <= 1024, "control block");
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+// gelu_fast (umma.cuh) on two values with the packed fp32 pipe (FFMA2 / FMUL2): same polynomial, same MUFU.TANH
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  float2 t = fmul2(x, x);
+  t.x = fminf(t.x, 64.f);   // |x| > 8: the argument stays > 13.8 -> tanh = +-1 exactly
+  t.y = fminf(t.y, 64.f);
+  float2 p = ffma2(t, make_float2(-0.00035151678863588117f, -0.00035151678863588117f),
+                   make_float2(0.037005646022512585f, 0.037005646022512585f));
+  p = ffma2(p, t, make_float2(0.7975078842853727f, 0.7975078842853727f));
+  const float2 u = fmul2(x, p);
+  const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(hx, th, hx);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
+  const int x_bytes = p.kb1 * kXBlockBytes;
+  float4* sCB = reinterpret_cast<float4*>(smem + 1024);               // [Hd/2] (cs0, cs1, b0, b1) of two hidden columns
+  float* sB2 = reinterpret_cast<float*>(smem + 1024 + (size_t)p.Hd * 8);   // [C]
+  uint8_t* sX = smem + 1024 + p.const_bytes;                          // nx buffers of kb1 K-blocks
+  uint8_t* sH = sX + (size_t)p.nx * x_bytes;                          // nh hidden buffers
+  uint8_t* sW1 = sH + (size_t)p.nh * kHidBytes;                       // ring 1
+  uint8_t* sW2 = sW1 + (size_t)p.n1slots * kW1BoxBytes;               // ring 2
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int J = p.chunks;
+  const int my_tiles = ((int)blockIdx.x < p.tiles) ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->x_full[i], 1);
+      mbar_init(&ctrl->x_empty[i], 1);
+      mbar_init(&ctrl->acc1_full[i], 1);
+      mbar_init(&ctrl->acc1_empty[i], kEpiWarps);
+      mbar_init(&ctrl->hid_full[i], kEpiWarps);
+      mbar_init(&ctrl->hid_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(&ctrl->w1_full[i], 1);
+      mbar_init(&ctrl->w1_empty[i], 1);
+      mbar_init(&ctrl->w2_full[i], 1);
+      mbar_init(&ctrl->w2_empty[i], 1);
+    }
+    mbar_init(&ctrl->acc2_full, 1);
+    mbar_init(&ctrl->acc2_empty, kEpiWarps);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctrl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  // epilogue constants -> shared memory (read on every chunk by every epilogue warp)
+  for (int i = threadIdx.x; i < p.Hd / 2; i += kThreads) {
+    const float2 b = __ldg(reinterpret_cast<const float2*>(p.b1) + i);
+    const float2 c = p.cs1 ? __ldg(reinterpret_cast<const float2*>(p.cs1) + i) : make_float2(0.f, 0.f);
+    sCB[i] = make_float4(c.x, c.y, b.x, b.y);
+  }
+  for (int i = threadIdx.x; i < p.C; i += kThreads) sB2[i] = __ldg(p.b2 + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0) {
+    // ---------------- TMA producer A: X tiles + W1' ring ----------------
+    if (lane == 0) {
+      int slot = 0, xb = 0;
+      uint32_t wphase = 0, xphase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int t = blockIdx.x + it * gridDim.x;
+        mbar_wait(&ctrl->x_empty[xb], xphase ^ 1u, 40);
+        mbar_expect_tx(&ctrl->x_full[xb], (uint32_t)x_bytes);
+        for (int kb = 0; kb < p.kb1; ++kb)
+          tma_load_2d(sX + (size_t)xb * x_bytes + (size_t)kb * kXBlockBytes, &tmX, &ctrl->x_full[xb], kb * BK, t * BM);
+        if (++xb == p.nx) { xb = 0; xphase ^= 1u; }
+        for (int j = 0; j < J; ++j)
+          for (int kb = 0; kb < p.kb1; ++kb) {
+            mbar_wait(&ctrl->w1_empty[slot], wphase ^ 1u, 41);
+            mbar_expect_tx(&ctrl->w1_full[slot], (uint32_t)kW1BoxBytes);
+            tma_load_2d(sW1 + (size_t)slot * kW1BoxBytes, &tmW1, &ctrl->w1_full[slot], kb * BK, j * HC);
+            if (++slot == p.n1slots) { slot = 0; wphase ^= 1u; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- TMA producer B: W2 ring ----------------
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t wphase = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int j = 0; j < J; ++j)
+          for (int kb = 0; kb < HC / BK; ++kb)
+            for (int q = 0; q < p.nparts2; ++q) {
+              mbar_wait(&ctrl->w2_empty[slot], wphase ^ 1u, 42);
+              mbar_expect_tx(&ctrl->w2_full[slot], (uint32_t)(p.n2 * BK * 2));
+              tma_load_2d(sW2 + (size_t)slot * p.slot2_bytes, &tmW2, &ctrl->w2_full[slot], j * HC + kb * BK, q * p.n2);
+              if (++slot == p.n2slots) { slot = 0; wphase ^= 1u; }
+            }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_bf16(BM, HC);
+      const uint32_t idesc2 = make_idesc_bf16(BM, p.n2);
+      const int G = my_tiles * J;
+      int s1 = 0, s2 = 0, xb = 0;
+      uint32_t ph1 = 0, ph2 = 0, xphase = 0;
+      uint32_t xaddr = 0;
+      int i1 = 0, i2 = 0;     // next fc1 / fc2 chunk (global over this CTA's tiles)
+      auto fc1 = [&](int g) {
+        const int j = g % J;
+        if (j == 0) {   // first chunk of a tile: its X must have landed
+          mbar_wait(&ctrl->x_full[xb], xphase, 50);
+          xaddr = smem_u32(sX + (size_t)xb * x_bytes);
+        }
+        const uint32_t buf = (uint32_t)g & 1u, use = (uint32_t)g >> 1;
+        mbar_wait(&ctrl->acc1_empty[buf], (use & 1u) ^ 1u, 51);
+        tc_fence_after();
+        const uint32_t d = tmem_base + kAcc1Col + buf * HC;
+        for (int kb = 0; kb < p.kb1; ++kb) {
+          mbar_wait(&ctrl->w1_full[s1], ph1, 52);
+          tc_fence_after();
+          const uint64_t da = make_kmajor_desc<128>(xaddr + (uint32_t)kb * kXBlockBytes);
+          const uint64_t db = make_kmajor_desc<128>(smem_u32(sW1 + (size_t)s1 * kW1BoxBytes));
+          const int ks = min(BK / 16, (p.C - kb * BK) / 16);
+          for (int k = 0; k < ks; ++k) umma_bf16_ss(d, da + 2ull * k, db + 2ull * k, idesc1, (uint32_t)((kb | k) != 0));
+          umma_commit(&ctrl->w1_empty[s1]);
+          if (++s1 == p.n1slots) { s1 = 0; ph1 ^= 1u; }
+        }
+        umma_commit(&ctrl->acc1_full[buf]);
+        if (j == J - 1) {   // X tile no longer needed once the last fc1 of the tile retires
+          umma_commit(&ctrl->x_empty[xb]);
+          if (++xb == p.nx) { xb = 0; xphase ^= 1u; }
+        }
+      };
+      auto fc2 = [&](int g) {
+        const int j = g % J;
+        const uint32_t tile_it = (uint32_t)(g / J);
+        const uint32_t hb = (uint32_t)g & 1u, use = (uint32_t)g >> 1;
+        mbar_wait(&ctrl->hid_full[hb], use & 1u, 53);
+        if (j == 0) mbar_wait(&ctrl->acc2_empty, (tile_it & 1u) ^ 1u, 54);
+        tc_fence_after();
+        for (int kb = 0; kb < HC / BK; ++kb) {
+          const uint64_t da = make_kmajor_desc<128>(smem_u32(sH + (size_t)hb * kHidBytes + (size_t)kb * kXBlockBytes));
+          for (int q = 0; q < p.nparts2; ++q) {
+            mbar_wait(&ctrl->w2_full[s2], ph2, 55);
+            tc_fence_after();
+            const uint64_t db = make_kmajor_desc<128>(smem_u32(sW2 + (size_t)s2 * p.slot2_bytes));
+            const uint32_t d = tmem_base + (uint32_t)(q * p.n2);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | kb | k) != 0));
+            umma_commit(&ctrl->w2_empty[s2]);
+            if (++s2 == p.n2slots) { s2 = 0; ph2 ^= 1u; }
+          }
+        }
+        umma_commit(&ctrl->hid_empty[hb]);
+        if (j == J - 1) umma_commit(&ctrl->acc2_full);
+      };
+      while (i2 < G) {
+        // fc1 runs one chunk ahead of fc2 (two accumulators); with a single X buffer never run ahead into the next tile
+        while (i1 < G && i1 < i2 + 2 && (p.nx == 2 || i1 / J == i2 / J)) fc1(i1++);
+        fc2(i2++);
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ---------------- epilogue warps ----------------
+    const int q = warp & 3;                        // TMEM lane quarter
+    const int e = (warp - kFirstEpiWarp) >> 2;     // 0..3
+    // this warp's 32 of the chunk's 128 hidden columns: K-block (e >> 1) of the hidden tile, 16-byte chunks (e & 1) * 4 ..
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int rloc = q * 32 + lane;                // row inside the tile == TMEM lane
+    // LayerNorm statistics of this thread's row are fetched one tile ahead (<= 4 partial pairs)
+    float2 nst[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
+    auto load_stats = [&](int tile) {
+      const int r = tile * BM + rloc;
+      if (r < p.R) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (long long)r * p.ln_parts;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < p.ln_parts) nst[k] = __ldg(st + k);
+      }
+    };
+    if (p.ln_stats && my_tiles > 0) load_stats(blockIdx.x);
+    // ---- output epilogue of tile iteration `oit` (all 16 warps): acc2 + b2 + residual -> out.  It runs AFTER the first hidden
+    // chunk of the next tile, so the wait for the last fc2 of the tile is hidden behind useful work.
+    auto output_epilogue = [&](int oit) {
+      const int row = (blockIdx.x + oit * gridDim.x) * BM + rloc;
+      const bool rok = row < p.R;
+        bool waited = false;
+        for (int c0 = e * 32; c0 < p.C; c0 += 128) {
+          uint4 res[4];
+          if (rok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (long long)row * p.C + c0);
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) res[i] = rp[i];   // plain loads: resid may alias out
+          }
+          if (!waited) {
+            mbar_wait(&ctrl->acc2_full, (uint32_t)oit & 1u, 62);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t v[32];
+          tmem_ld_x32(lane_addr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (rok) {
+            uint4 o[4];
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sB2 + c0 + 8 * i);
+              const float4 b1 = *reinterpret_cast<const float4*>(sB2 + c0 + 8 * i + 4);
+              const float2 r0 = unpack_bf16x2(res[i].x), r1 = unpack_bf16x2(res[i].y), r2_ = unpack_bf16x2(res[i].z),
+                           r3 = unpack_bf16x2(res[i].w);
+              o[i].x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + b0.x + r0.x, __uint_as_float(v[8 * i + 1]) + b0.y + r0.y);
+              o[i].y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + b0.z + r1.x, __uint_as_float(v[8 * i + 3]) + b0.w + r1.y);
+              o[i].z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + b1.x + r2_.x, __uint_as_float(v[8 * i + 5]) + b1.y + r2_.y);
+              o[i].w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + b1.z + r3.x, __uint_as_float(v[8 * i + 7]) + b1.w + r3.y);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + (long long)row * p.C + c0);
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = o[i];
+          }
+        }
+        if (!waited) {   // this warp owns no output columns (C < 128): still consume the phase
+          mbar_wait(&ctrl->acc2_full, (uint32_t)oit & 1u, 62);
+          tc_fence_after();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->acc2_empty);
+    };
+    for (int it = 0; it < my_tiles; ++it) {
+      const int t = blockIdx.x + it * gridDim.x;
+      const int row = t * BM + rloc;
+      const bool rok = row < p.R;
+      float own_r = 1.f, own_n = 0.f;
+      if (p.ln_stats) {
+        const float s1 = (nst[0].x + nst[1].x) + (nst[2].x + nst[3].x), s2 = (nst[0].y + nst[1].y) + (nst[2].y + nst[3].y);
+        const float mu = s1 * p.ln_inv_k;
+        const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mu * mu), 0.f);
+        own_r = rsqrtf(var + p.ln_eps);
+        own_n = -own_r * mu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
+        if (it + 1 < my_tiles) load_stats(t + gridDim.x);
+      }
+      const float2 r2 = make_float2(own_r, own_r), n2v = make_float2(own_n, own_n);
+      for (int j = 0; j < J; ++j) {
+        const uint32_t g = (uint32_t)(it * J + j);
+        const uint32_t buf = g & 1u, use1 = g >> 1;
+        const uint32_t hb = g & 1u, useh = g >> 1;
+        mbar_wait(&ctrl->acc1_full[buf], use1 & 1u, 60);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_x32(lane_addr + kAcc1Col + buf * HC + (uint32_t)(e * 32), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->acc1_empty[buf]);   // accumulator drained: the next fc1 may overwrite it
+        const float4* cb = sCB + ((j * HC + e * 32) >> 1);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 c = cb[i];   // (cs, cs, b1, b1) of hidden columns 2i, 2i+1 of this warp's 32 — broadcast read
+          float2 a = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          a = ffma2(r2, a, ffma2(n2v, make_float2(c.x, c.y), make_float2(c.z, c.w)));
+          a = gelu_fast2(a);
+          pk[i] = pack_bf16x2(a.x, a.y);
+        }
+        mbar_wait(&ctrl->hid_empty[hb], (useh & 1u) ^ 1u, 61);   // the fc2 that last read this buffer has retired
+        uint8_t* hrow = sH + (size_t)hb * kHidBytes + (size_t)(e >> 1) * kXBlockBytes + (size_t)rloc * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = (e & 1) * 4 + i;
+          *reinterpret_cast<uint4*>(hrow + ((ch ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->hid_full[hb]);
+        if (p.nx == 2 && j == 0 && it > 0) output_epilogue(it - 1);   // deferred output epilogue of the previous tile
+      }
+      if (p.nx != 2) output_epilogue(it);
+    }
+    if (p.nx == 2 && my_tiles > 0) output_epilogue(my_tiles - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+std::once_flag g_once;
+cudaError_t g_attr = cudaSuccess;
+
+}  // namespace
+
+bool mlp_fused_supported(int C, int Hd) {
+  // acc2 [128 x C] + two acc1 buffers must fit the 512 TMEM columns; the X tile, two hidden buffers and both weight rings
+  // must fit 227 KB of shared memory
+  return C >= 32 && C <= 192 && C % 32 == 0 && Hd % HC == 0 && Hd >= HC && Hd <= 4096;
+}
+
+int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
+  LMV_REQUIRE(a.x && a.W1 && a.W2 && a.b1 && a.b2 && a.out, "mlp_fused: null pointer");
+  LMV_REQUIRE(a.R > 0, "mlp_fused: empty problem");
+  if (!mlp_fused_supported(a.C, a.Hd))
+    return fail(LMV_ERR_UNSUPPORTED, "mlp_fused: needs C % 32 == 0, 32 <= C <= 192, hidden % 128 == 0, hidden <= 4096");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  LMV_REQUIRE(al16(a.x) && al16(a.W1) && al16(a.W2) && al16(a.b1) && al16(a.b2) && al16(a.out) && al16(a.resid ? a.resid : a.x),
+              "mlp_fused: pointers must be 16-byte aligned");
+  LMV_REQUIRE((a.ln_stats == nullptr) == (a.cs1 == nullptr), "mlp_fused: ln_stats and colsum go together");
+  LMV_REQUIRE(a.cs1 == nullptr || al16(a.cs1), "mlp_fused: colsum must be 16-byte aligned");
+  LMV_REQUIRE(a.ln_parts <= 4, "mlp_fused: at most 4 LayerNorm statistics partials per row");
+  MlpParams& p = op->p;
+  p.R = a.R; p.C = a.C; p.Hd = a.Hd;
+  p.tiles = (a.R + BM - 1) / BM;
+  p.kb1 = (a.C + BK - 1) / BK;
+  p.chunks = a.Hd / HC;
+  p.nparts2 = 1;
+  p.n2 = a.C;
+  p.slot2_bytes = p.n2 * BK * 2;
+  p.const_bytes = ((a.Hd * 8 + a.C * 4 + 1023) / 1024) * 1024;
+  const int x_bytes = p.kb1 * kXBlockBytes;
+  const int budget = kSmemLimit - 2048 - p.const_bytes;     // ctrl + alignment slack
+  // X double-buffered when that still leaves one chunk of lookahead in each ring (kb1 W1' boxes, 2 W2 boxes)
+  const int min_rings = (p.kb1 + 1) * kW1BoxBytes + 3 * p.slot2_bytes;
+  p.nx = 2; p.nh = 2;
+  if (budget - p.nx * x_bytes - p.nh * kHidBytes < min_rings) p.nx = 1;
+  const int rest = budget - p.nx * x_bytes - p.nh * kHidBytes;
+  p.n2slots = std::min(4, std::max(2, (rest - (p.kb1 + 1) * kW1BoxBytes) / p.slot2_bytes));
+  p.n1slots = std::min(kMaxSlots, (rest - p.n2slots * p.slot2_bytes) / kW1BoxBytes);
+  LMV_REQUIRE(p.n1slots >= 2 && p.n2slots >= 2, "mlp_fused: shared memory budget (weight rings)");
+  op->smem_bytes = 2048 + p.const_bytes + p.nx * x_bytes + p.nh * kHidBytes + p.n1slots * kW1BoxBytes + p.n2slots * p.slot2_bytes;
+  LMV_REQUIRE(op->smem_bytes <= kSmemLimit, "mlp_fused: shared memory budget");
+  p.b1 = a.b1; p.cs1 = a.cs1; p.b2 = a.b2;
+  p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1; p.ln_eps = a.ln_eps; p.ln_inv_k = 1.0f / (float)a.C;
+  p.resid = a.resid ? a.resid : a.x;
+  p.out = a.out;
+  op->grid = std::min(p.tiles, device_sm_count());
+  int rc;
+  {
+    uint64_t dims[2] = {(uint64_t)a.C, (uint64_t)a.R};
+    uint64_t strides[1] = {(uint64_t)a.C * 2};
+    uint32_t box[2] = {BK, BM};
+    if ((rc = encode_tmap_bf16(&op->tmX, a.x, 2, dims, strides, box, 128))) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.C, (uint64_t)a.Hd};
+    uint64_t strides[1] = {(uint64_t)a.C * 2};
+    uint32_t box[2] = {BK, HC};
+    if ((rc = encode_tmap_bf16(&op->tmW1, a.W1, 2, dims, strides, box, 128))) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a.Hd, (uint64_t)a.C};
+    uint64_t strides[1] = {(uint64_t)a.Hd * 2};
+    uint32_t box[2] = {BK, (uint32_t)p.n2};
+    if ((rc = encode_tmap_bf16(&op->tmW2, a.W2, 2, dims, strides, box, 128))) return rc;
+  }
+  return LMV_OK;
+}
+
+int mlp_fused_run(const MlpOp& op, cudaStream_t stream) {
+  std::call_once(g_once, [] {
+    g_attr = cudaFuncSetAttribute(mlp_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+  });
+  LMV_CUDA_OK(g_attr);
+  mlp_fused_tcgen05<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tmX, op.tmW1, op.tmW2, op.p);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+}  // namespace lmv

@@ -74,6 +74,11 @@ class Engine:
         _native.check(self.lib.lmv_plan_set_debug_simt(self._plan, int(bool(enable))))
         self._graphs.clear()
 
+    def set_option(self, name: str, value: int):
+        """Schedule A/B switches of the native plan (lmv_plan_set_option), e.g. ``fused_mlp``."""
+        _native.check(self.lib.lmv_plan_set_option(self._plan, name.encode(), int(value)))
+        self._graphs.clear()
+
     def set_profile(self, enable: bool):
         """Per-kernel-class CUDA-event timing of every following forward (see lmv_plan_set_profile)."""
         _native.check(self.lib.lmv_plan_set_profile(self._plan, int(bool(enable))))

@@ -87,6 +87,18 @@ def linear_fused(A, W, bias=None, residual=None, gelu=False, ln_stats=None, ln_c
     return out
 
 
+def mlp_fused(x, W1, b1, W2, b2, ln_stats=None, colsum1=None, ln_eps=1e-6, resid=None, out=None):
+    """out = resid + W2 gelu(W1 LN(x) + b1) + b2 in one kernel (lmv_mlp_fused); ln_stats [R, parts, 2] or None."""
+    R, Cc = x.shape
+    Hd = W1.shape[0]
+    if out is None:
+        out = torch.empty_like(x)
+    parts = (ln_stats.numel() // (2 * R)) if ln_stats is not None else 1
+    ok(lib().lmv_mlp_fused(ptr(x), ptr(resid), ptr(out), ptr(W1), ptr(b1), ptr(colsum1), ptr(W2), ptr(b2), ptr(ln_stats), parts,
+                           float(ln_eps), R, Cc, Hd, stream()))
+    return out
+
+
 def ref_linear(A, W, bias=None, residual=None, gelu=False):
     y = A.float() @ W.float().t()
     if bias is not None:

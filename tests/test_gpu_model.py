@@ -107,6 +107,21 @@ def test_simt_crosscheck_path_agrees_with_tensor_core_path():
     assert G.rel_err(y, y_simt) < 1e-2
 
 
+def test_fused_mlp_schedule_agrees_with_unfused_gemm_schedule():
+    cfg, sd, m = _build("lemevit_tiny", 2)
+    x = Wt.make_input(3, 224, 224, 2).cuda().to(torch.bfloat16)
+    eng = m.native_engine(x.device)
+    y = m(x).float()
+    n_fused = eng.launch_count(3, 224, 224)
+    eng.set_option("fused_mlp", 0)
+    y_unfused = m(x).float()
+    n_unfused = eng.launch_count(3, 224, 224)
+    eng.set_option("fused_mlp", 1)
+    assert n_fused < n_unfused            # one launch instead of two for every fusable MLP
+    assert G.rel_err(y, y_unfused) < 1e-2
+    assert torch.equal(m(x).float(), y)
+
+
 def test_chunked_batch_and_cuda_graph_are_bit_identical():
     cfg, sd, m = _build("lemevit_tiny", 3)
     x = Wt.make_input(6, 224, 224, 3).cuda().to(torch.bfloat16)

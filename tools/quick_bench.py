@@ -17,6 +17,10 @@ m = getattr(L, name)(native_chunk=chunk).to("cuda", torch.bfloat16)
 m.train(False)
 x = torch.randn(B, 3, res, res, device="cuda").to(torch.bfloat16)
 with torch.no_grad():
+    for a in sys.argv:
+        if a.startswith("--opt="):          # e.g. --opt=fused_mlp=0
+            k, v = a[6:].split("=")
+            m.native_engine(x.device).set_option(k, int(v))
     for _ in range(3):
         y = m(x)
     torch.cuda.synchronize()
