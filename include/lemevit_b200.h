@@ -73,7 +73,8 @@ void lmv_plan_destroy(lmv_plan* plan);
  * producer->consumer activations L2-resident. */
 int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
 /* schedule options (A/B switches; every schedule is rebuilt afterwards).  Known names:
- *   "fused_mlp" (default 1): run `x + mlp(norm2(x))` as ONE kernel (lmv_mlp_fused) where the shape allows it. */
+ *   "fused_mlp" (default 1): run `x + mlp(norm2(x))` as ONE kernel (lmv_mlp_fused) where the shape allows it;
+ *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self). */
 int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
 /* bring-up switch: 1 routes every GEMM / attention through the plain SIMT cross-check kernels. */
 int lmv_plan_set_debug_simt(lmv_plan* plan, int enable);
@@ -151,6 +152,13 @@ int lmv_layernorm(const void* in, void* out, const float* gamma, const float* be
 int lmv_attention(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
                   long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
                   float scale, int impl, void* stream);
+/* Self-attention of an 'S' block (StandardAttention, models/lemevit.py:199-205) over T <= 224 rows per image, head_dim 32, in ONE
+ * persistent tcgen05 kernel: rows [0, N) (image tokens) attend keys [0, N); rows [N, T) (the meta tokens of a unified
+ * [B, N+M, 3C] qkv buffer, forward_with_x :634) attend keys [N, T).  N == T: plain self-attention.  Same pointer / stride
+ * conventions as lmv_attention. */
+int lmv_attention_self(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
+                       long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int T, int N, float scale,
+                       void* stream);
 /* The meta-token side of CrossAttention / DualCrossAttention (models/lemevit.py:484, :300-302): Lq = M (16) queries
  * per head over Lk = N image tokens, heads * Lq <= 128, heads * 32 <= 256.  Split-N tcgen05 kernel (one CTA per image
  * and 128-token tile, block-diagonal Q so that all heads share one accumulation) + deterministic merge of the

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblemevit_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "mlp_fused.cu", "tokens.cu", "posembed.cu", "attention_simt.cu", "attention_tc.cu", "attention_meta.cu"]
+SOURCES = ["api.cu", "gemm.cu", "mlp_fused.cu", "tokens.cu", "posembed.cu", "attention_simt.cu", "attention_tc.cu", "attention_self.cu", "attention_meta.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

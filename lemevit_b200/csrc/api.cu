@@ -102,8 +102,8 @@ struct StageW {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
-enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
-static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "mlp_fused_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
+enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_SELF, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
+static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "mlp_fused_tcgen05", "attention_self_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
                                                           "posembed_layernorm", "layernorm", "im2col", "misc"};
 struct OpRec {
   Launch fn;
@@ -145,6 +145,7 @@ struct lmv_plan {
   int chunk = 0;
   int debug_simt = 0;
   int fused_mlp = 1;
+  int fused_self_attn = 1;
   int profile = 0;
   std::vector<cudaEvent_t> events;          // profile mode: one event between consecutive launches
   std::vector<const lmv::OpRec*> pending;   // ops whose events have not been harvested yet
@@ -429,6 +430,29 @@ struct Builder {
     ln_linear(x, stats, parts, bw.w1, bw.b1, bw.cs1, R, Hd, C, hid, 1);
     linear(hid, Hd, bw.w2, bw.b2, R, C, Hd, x, C, 0, x);
   }
+  // StandardAttention of an 'S' block on a [B, T, 3C] qkv buffer: image tokens (rows < N) and meta tokens (rows >= N) attend
+  // within their own segment (models/lemevit.py:632-635 run the same attention module on x and on c)
+  void self_attn(const bf16* qkv, bf16* out, int B, int heads, int T, int N, int C, float scale) {
+    if (rc) return;
+    AttnArgs a;
+    a.q = qkv; a.k = qkv + C; a.v = qkv + 2 * C; a.out = out;
+    a.q_bs = a.k_bs = a.v_bs = (long long)T * 3 * C; a.o_bs = (long long)T * C;
+    a.q_rs = a.k_rs = a.v_rs = 3 * C; a.o_rs = C;
+    a.B = B; a.heads = heads; a.Lq = T; a.Lk = T; a.scale = scale;
+    if (!simt && plan->fused_self_attn && attention_self_supported(a, T, N)) {
+      const double fl = 4.0 * B * heads * 32.0 * ((double)N * N + (double)(T - N) * (T - N));
+      const double by = 2.0 * B * T * 4.0 * C;
+      sc->push([a, T, N](cudaStream_t s) { return attention_self_run(a, T, N, s); }, OP_ATTN_SELF, fl, by,
+               "attn_self B=" + std::to_string(B) + " h=" + std::to_string(heads) + " T=" + std::to_string(T) + " N=" + std::to_string(N));
+      return;
+    }
+    attn(qkv, (long long)T * 3 * C, 3 * C, qkv + C, qkv + 2 * C, (long long)T * 3 * C, 3 * C, out, (long long)T * C, C, B, heads, N, N, scale);
+    if (T > N) {
+      const size_t ro = (size_t)N * 3 * C;
+      attn(qkv + ro, (long long)T * 3 * C, 3 * C, qkv + ro + C, qkv + ro + 2 * C, (long long)T * 3 * C, 3 * C, out + (size_t)N * C,
+           (long long)T * C, C, B, heads, T - N, T - N, scale);
+    }
+  }
   void posln(const bf16* tok, const float* dw_w, const float* dw_b, bf16* resid, bf16* norm, int B, int H, int W, int T,
              int C, float* stats = nullptr) {
     if (rc) return;
@@ -601,14 +625,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         cur ^= 1;
         bf16* x = xbuf[cur];
         b.ln_linear(x, stats1, 1, bw.wa, bw.ba, bw.csa, B * T, 3 * C, C, qkv);
-        const float sc_ = 1.0f / sqrtf((float)c.head_dim);
-        b.attn(qkv, (long long)T * 3 * C, 3 * C, qkv + C, qkv + 2 * C, (long long)T * 3 * C, 3 * C, xn, (long long)T * C, C, B,
-               heads, N, N, sc_);
-        if (uni) {
-          const size_t ro = (size_t)N * 3 * C;
-          b.attn(qkv + ro, (long long)T * 3 * C, 3 * C, qkv + ro + C, qkv + ro + 2 * C, (long long)T * 3 * C, 3 * C,
-                 xn + (size_t)N * C, (long long)T * C, C, B, heads, M, M, sc_);
-        }
+        b.self_attn(qkv, xn, B, heads, T, N, C, 1.0f / sqrtf((float)c.head_dim));
         int parts2 = 1;
         b.linear_res_stats(xn, bw.wp1, bw.bp1, B * T, C, C, x, stats2, &parts2);
         b.mlp(x, stats2, parts2, bw, B * T, C, Hd, hid);
@@ -844,6 +861,7 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   if (rc) return rc;
   const std::string n(name);
   if (n == "fused_mlp") plan->fused_mlp = value ? 1 : 0;
+  else if (n == "fused_self_attn") plan->fused_self_attn = value ? 1 : 0;
   else return fail(LMV_ERR_INVALID, "set_option: unknown option " + n);
   plan->cache.clear();   // schedules are rebuilt with the new setting
   return LMV_OK;
@@ -1001,6 +1019,14 @@ static AttnArgs make_attn_args(const void* q, long long q_bs, int q_rs, const vo
   a.q_rs = q_rs; a.k_rs = k_rs; a.v_rs = v_rs; a.o_rs = o_rs;
   a.B = B; a.heads = heads; a.Lq = Lq; a.Lk = Lk; a.scale = scale;
   return a;
+}
+
+int lmv_attention_self(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
+                       long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int T, int N, float scale,
+                       void* stream) {
+  if (!q || !k || !v || !out) return fail(LMV_ERR_INVALID, "attention_self: null pointer");
+  AttnArgs a = make_attn_args(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, out, o_bs, o_rs, B, heads, T, T, scale);
+  return attention_self_run(a, T, N, static_cast<cudaStream_t>(stream));
 }
 
 size_t lmv_attention_meta_workspace(int B, int heads, int Lq, int Lk) {

@@ -1,0 +1,421 @@
+// Self-attention of the late LeMeViT stages on tensor cores, persistent and warp-specialised:
+//   StandardAttention (models/lemevit.py:199-205; F.scaled_dot_product_attention :203) on the N image tokens of every image
+//   AND, in the same launch, on the M = 16 meta tokens that share the block's weights (forward_with_x :632-635): the
+//   [B, N+M, 3C] qkv buffer holds both, rows [0, N) attend keys [0, N), rows [N, N+M) attend keys [N, N+M).
+//
+// sm_100a design — one CTA per SM, looping over work items (image, head, pair of 128-row query tiles):
+//   warp 0        TMA producer: K, V [Lkp x 32] and the two Q tiles [128 x 32] of the item (64B swizzle) into a 2-stage ring —
+//                 K and V are fetched ONCE for both query tiles
+//   warp 1        one thread issues tcgen05.mma:  S_g = Q_g K^T  (M=128, N=Lkp<=224, K=32)   -> TMEM columns [224 g, 224 g + Lkp)
+//                                                 O_g = P_g V    (M=128, N=32,  K=Lkp)       -> TMEM columns [448 + 32 g, +32)
+//                 S_g of item i+1 is issued BEFORE P_g V of item i, so a softmax group always finds its next scores ready
+//   warps 4..11   softmax group 0 (query tile 0): two warps per TMEM lane quarter, each owning half of the key columns of its 32
+//   warps 12..19  softmax group 1 (query tile 1)   rows: partial row max -> exchange through smem -> exp2 with the scale folded
+//                 in, P as bf16 into 128B-swizzled K-major smem tiles (A operand of P V), partial row sums exchanged; the output
+//                 epilogue of item i (O / rowsum -> bf16 -> global) runs after the softmax of item i+1 was started, so nobody
+//                 ever waits for the P V MMA
+// The two groups drift apart naturally: while one is in its MUFU-bound exp phase the other loads TMEM or stores results.
+#include <mutex>
+
+#include "kernels.h"
+#include "umma.cuh"
+
+namespace lmv {
+
+namespace {
+
+constexpr int kD = 32;
+constexpr int kQTile = 128;
+constexpr int kMaxKeys = 224;
+constexpr int kSCols = 224;              // TMEM columns reserved per S accumulator
+constexpr int kOCol = 2 * kSCols;        // 448
+constexpr int kFirstSoftmaxWarp = 4;
+constexpr int kGroupWarps = 8;               // two warps per TMEM lane quarter
+constexpr int kThreads = 32 * (kFirstSoftmaxWarp + 2 * kGroupWarps);
+constexpr int kQBytes = kQTile * kD * 2;           // 8 KB
+constexpr int kKVBytes = kMaxKeys * kD * 2;        // 14 KB
+constexpr int kStageBytes = 2 * kQBytes + 2 * kKVBytes;   // 44 KB
+constexpr int kPTileBytes = kQTile * 128;          // [128 x 64] bf16
+constexpr int kPBytes = 4 * kPTileBytes;           // 64 KB per group (Lkp <= 256)
+constexpr int kXchgBytes = 2 * 2 * kQTile * 4 * 3;   // per group and column half: row max + two parities of row sums
+constexpr int kSmemBytes = 2048 + ((kXchgBytes + 1023) / 1024) * 1024 + 2 * kStageBytes + 2 * kPBytes;
+
+struct SelfParams {
+  bf16* out;
+  long long o_bs;
+  int o_rs;
+  int B, heads, T, N, Lkp, pairs, qtiles;
+  long long items;
+  float scale_log2e;
+};
+
+struct Ctrl {
+  uint64_t ld_full[2], ld_empty[2];
+  uint64_t s_full[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= 1ull << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;   // SWIZZLE_64B
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const SelfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
+  float* sXchg = reinterpret_cast<float*>(smem + 1024);   // [group][half][max | sum parity 0 | sum parity 1][128 rows]
+  uint8_t* sStage = smem + 1024 + ((kXchgBytes + 1023) / 1024) * 1024;   // 2 x {Q0, Q1, K, V}
+  uint8_t* sP = sStage + 2 * kStageBytes;              // 2 groups x 4 tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n_my = ((long long)blockIdx.x < p.items) ? (p.items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->ld_full[i], 1);
+      mbar_init(&ctrl->ld_empty[i], 1);
+      mbar_init(&ctrl->s_full[i], 1);
+      mbar_init(&ctrl->p_full[i], kGroupWarps);
+      mbar_init(&ctrl->p_empty[i], 1);
+      mbar_init(&ctrl->o_full[i], 1);
+      mbar_init(&ctrl->o_empty[i], kGroupWarps);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 2) {
+    tmem_alloc(&ctrl->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctrl->tmem_base;
+  const bool two = p.qtiles > 1;                 // does query tile 1 of a pair ever exist
+  const uint32_t kv_bytes = (uint32_t)(p.Lkp * kD * 2);
+
+  // item -> (b, h, pair)
+  auto decode = [&](long long it, int& b, int& h, int& pr) {
+    const long long item = blockIdx.x + it * gridDim.x;
+    pr = (int)(item % p.pairs);
+    const long long bh = item / p.pairs;
+    h = (int)(bh % p.heads);
+    b = (int)(bh / p.heads);
+  };
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      for (long long it = 0; it < n_my; ++it) {
+        const int s = (int)(it & 1);
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        int b, h, pr;
+        decode(it, b, h, pr);
+        const bool has1 = (2 * pr + 1) < p.qtiles;
+        mbar_wait_lean(&ctrl->ld_empty[s], ph ^ 1u);
+        uint8_t* st = sStage + (size_t)s * kStageBytes;
+        mbar_expect_tx(&ctrl->ld_full[s], (uint32_t)(kQBytes * (has1 ? 2 : 1)) + 2u * kv_bytes);
+        tma_load_3d(st, &tmQ, &ctrl->ld_full[s], h * kD, (2 * pr) * kQTile, b);
+        if (has1) tma_load_3d(st + kQBytes, &tmQ, &ctrl->ld_full[s], h * kD, (2 * pr + 1) * kQTile, b);
+        tma_load_3d(st + 2 * kQBytes, &tmK, &ctrl->ld_full[s], h * kD, 0, b);
+        tma_load_3d(st + 2 * kQBytes + kKVBytes, &tmV, &ctrl->ld_full[s], h * kD, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(kQTile, p.Lkp);
+      const uint32_t idesc_o = make_idesc_bf16(kQTile, kD) | (1u << 16);   // b_major = MN (V as loaded)
+      const int ksteps = p.Lkp >> 4;
+      auto issue_s = [&](long long it, int g) {   // S_g(it) = Q_g K^T
+        const uint8_t* st = sStage + (size_t)(it & 1) * kStageBytes;
+        const uint64_t dq = make_kmajor_desc<64>(smem_u32(st + (size_t)g * kQBytes));
+        const uint64_t dk = make_kmajor_desc<64>(smem_u32(st + 2 * kQBytes));
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tmem + (uint32_t)(g * kSCols), dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)(k != 0));
+        umma_commit(&ctrl->s_full[g]);
+      };
+      // Event loop: per group the next S and the next P V to issue; whichever dependency completes first is served first, so
+      // the two softmax groups never wait for each other's hand-shakes.
+      //   S_g(i)   needs the K/Q stage of item i and P_g(i-1) written (which implies S_g(i-1) fully consumed)
+      //   PV_g(i)  needs P_g(i) written and the output epilogue of item i-1 done with O_g
+      const int ng = two ? 2 : 1;
+      long long s_next[2] = {0, 0}, pv_next[2] = {0, 0}, released = 0;
+      const long long t_start = clock64();
+      while (pv_next[0] < n_my || (ng == 2 && pv_next[1] < n_my)) {
+        bool progress = false;
+        for (int g = 0; g < ng; ++g) {
+          long long i = s_next[g];
+          if (i < n_my && i <= pv_next[g] + 1 && (i == 0 || mbar_test_wait(&ctrl->p_full[g], (uint32_t)(i - 1) & 1u)) &&
+              mbar_test_wait(&ctrl->ld_full[i & 1], (uint32_t)(i >> 1) & 1u)) {
+            tc_fence_after();
+            issue_s(i, g);
+            ++s_next[g];
+            progress = true;
+          }
+          i = pv_next[g];
+          if (i < n_my && i < s_next[g] && mbar_test_wait(&ctrl->p_full[g], (uint32_t)i & 1u) &&
+              (i == 0 || mbar_test_wait(&ctrl->o_empty[g], (uint32_t)(i - 1) & 1u))) {
+            tc_fence_after();
+            const uint8_t* st = sStage + (size_t)(i & 1) * kStageBytes;
+            const uint32_t pbase = smem_u32(sP + (size_t)g * kPBytes), vbase = smem_u32(st + 2 * kQBytes + kKVBytes);
+            for (int s = 0; s < ksteps; ++s) {
+              const uint64_t da = make_kmajor_desc<128>(pbase + (uint32_t)(s >> 2) * kPTileBytes) + 2ull * (s & 3);
+              const uint64_t db = make_mnmajor_sw64_desc(vbase + (uint32_t)s * (16 * kD * 2));
+              umma_bf16_ss(tmem + kOCol + (uint32_t)(g * kD), da, db, idesc_o, (uint32_t)(s != 0));
+            }
+            umma_commit(&ctrl->o_full[g]);
+            umma_commit(&ctrl->p_empty[g]);
+            ++pv_next[g];
+            progress = true;
+            // a K/V/Q stage is free once BOTH groups' P V of that item (and hence every MMA reading it) have been issued
+            const long long both = ng == 2 ? (pv_next[0] < pv_next[1] ? pv_next[0] : pv_next[1]) : pv_next[0];
+            while (released < both) { umma_commit(&ctrl->ld_empty[released & 1]); ++released; }
+          }
+        }
+        if (!progress) __nanosleep(40);
+        if (!progress && clock64() - t_start > (1ll << 33)) {
+          printf("[lemevit_b200] attention_self MMA loop stuck: block %d s_next %lld %lld pv_next %lld %lld of %lld\n", (int)blockIdx.x, s_next[0],
+                 s_next[1], pv_next[0], pv_next[1], n_my);
+          __trap();
+        }
+      }
+    }
+  } else if (warp >= kFirstSoftmaxWarp) {
+    // ---------------- softmax groups ----------------
+    const int g = (warp - kFirstSoftmaxWarp) / kGroupWarps;     // group == query tile of the pair
+    const int hcol = ((warp - kFirstSoftmaxWarp) >> 2) & 1;      // which half of the key columns (and of the 32 output columns)
+    const int q = warp & 3;                            // TMEM lane quarter
+    const int r = q * 32 + lane;                       // row inside the tile == TMEM lane
+    const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_s = t_row + (uint32_t)(g * kSCols), t_o = t_row + kOCol + (uint32_t)(g * kD);
+    uint8_t* pg = sP + (size_t)g * kPBytes + (size_t)r * 128;
+    const int nchunk = (p.Lkp + 31) >> 5;
+    const int nsplit = (nchunk + 1) >> 1;
+    const int cbeg = hcol ? nsplit : 0, cend = hcol ? nchunk : nsplit;   // this warp's 32-column chunks
+    float* x_max = sXchg + ((g * 2 + hcol) * 3 + 0) * kQTile;       // own slots; the partner's are at (hcol ^ 1)
+    float* x_sum = sXchg + ((g * 2 + hcol) * 3 + 1) * kQTile;
+    const float* y_max = sXchg + ((g * 2 + (hcol ^ 1)) * 3 + 0) * kQTile;
+    const float* y_sum = sXchg + ((g * 2 + (hcol ^ 1)) * 3 + 1) * kQTile;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kGroupWarps * 32) : "memory"); };
+    // deferred output epilogue state of the previous item
+    float prev_ps = 0.f;          // this warp's partial row sum
+    uint32_t prev_par = 0;        // which x_sum / y_sum slot holds the previous item's partial sums
+    bf16* prev_out = nullptr;
+    bool prev_any = false;
+    uint32_t n_done = 0;          // items this group has processed (phase counter of its barriers)
+    auto output_epilogue = [&]() {
+      mbar_wait_lean(&ctrl->o_full[g], (n_done - 1) & 1u);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld_x16(t_o + (uint32_t)(hcol * 16), v);     // this warp's 16 of the 32 output columns
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->o_empty[g]);
+      if (prev_out) {
+        const float inv = 1.f / (prev_ps + y_sum[prev_par * kQTile + r]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+          reinterpret_cast<uint4*>(prev_out + hcol * 16)[j] = u;
+        }
+      }
+    };
+    // The key range of a row depends only on (tile, row) — identical for every item: classify the 32-column chunks once.
+    // bit c of full_mask: every lane of this warp sees all 32 keys of chunk c (no masking code needed).
+    const int tile = g;                                // T <= 224: one pair per (image, head), query tile == group
+    const int row = tile * kQTile + r;
+    const bool rok = row < p.T;
+    // image tokens attend image tokens, meta tokens attend meta tokens (rows that do not exist behave like image rows)
+    const int kbeg = (rok && row >= p.N) ? p.N : 0;
+    const int kend = (rok && row >= p.N) ? p.T : p.N;
+    const bool warp_active = tile * kQTile + q * 32 < p.T;   // warp-uniform: any valid row in this warp
+    uint32_t full_mask = 0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int c0 = c * 32;
+      if (__all_sync(0xffffffffu, kbeg <= c0 && c0 + 32 <= kend)) full_mask |= 1u << c;
+    }
+
+    const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
+
+    for (long long it = 0; it < n_my; ++it) {
+      if (tile >= p.qtiles) break;                     // no second query tile: nothing for group 1
+      int b, h, pr;
+      decode(it, b, h, pr);
+      mbar_wait_lean(&ctrl->s_full[g], n_done & 1u);
+      tc_fence_after();
+      float psum = 0.f;
+      float pm = -INFINITY;
+      auto mask_chunk = [&](uint32_t (&v)[32], int c0) {
+        // keys outside this row's segment get a score of -inf (exp2 -> exactly 0); applied to the loaded registers of the few
+        // chunks that are not fully visible, so that each pass has ONE math body (instruction-cache footprint matters here)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < kbeg || c0 + j >= kend) v[j] = 0xff800000u;
+      };
+      if (warp_active) {
+        // ---- pass 1: partial row max over this warp's chunks (four independent chains) ----
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+        for (int c = cbeg; c < cend; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_s + (uint32_t)(c * 32), v);
+          tmem_ld_wait();
+          if (!((full_mask >> c) & 1u)) mask_chunk(v, c * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[j]));
+            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+            m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+          }
+        }
+        pm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      x_max[r] = pm;
+      group_sync();                                     // partial maxima (and the previous item's partial sums) are visible
+      // the P V MMA of the previous item must have finished reading this group's P tiles
+      mbar_wait_lean(&ctrl->p_empty[g], (n_done & 1u) ^ 1u);
+      if (warp_active) {
+        const float mxs = fmaxf(pm, y_max[r]) * p.scale_log2e;
+        const float2 nm2 = make_float2(-mxs, -mxs);
+        // ---- pass 2: p = exp2(s * scale - max), partial row sum (two packed chains), bf16 P tile ----
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int c = cbeg; c < cend; ++c) {
+          const int c0 = c * 32;
+          uint32_t v[32];
+          tmem_ld_x32(t_s + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (!((full_mask >> c) & 1u)) mask_chunk(v, c0);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float2 a0 = ffma2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2);
+            float2 a1 = ffma2(make_float2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), sc2, nm2);
+            a0.x = ex2_approx(a0.x); a0.y = ex2_approx(a0.y);
+            a1.x = ex2_approx(a1.x); a1.y = ex2_approx(a1.y);
+            s0 = fadd2(s0, a0);
+            s1 = fadd2(s1, a1);
+            pk[j] = pack_bf16x2(a0.x, a0.y);
+            pk[j + 1] = pack_bf16x2(a1.x, a1.y);
+          }
+          // P[r, c0 .. c0+31] -> tile (c0 / 64), 16-byte chunks ((c0 % 64) / 8) .. +3, XOR-swizzled with (r % 8)
+          uint8_t* tile_p = pg + (size_t)(c0 >> 6) * kPTileBytes;
+          const int ch = (c0 & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(tile_p + (((ch + j) ^ (r & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        psum = (s0.x + s0.y) + (s1.x + s1.y);
+      } else {
+        // rows of this warp do not exist: P = 0 keeps the (unused) accumulator rows finite
+        for (int c = cbeg; c < cend; ++c) {
+          uint8_t* tile_p = pg + (size_t)((c * 32) >> 6) * kPTileBytes;
+          const int ch = ((c * 32) & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(tile_p + (((ch + j) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      const uint32_t par = n_done & 1u;
+      x_sum[par * kQTile + r] = psum;                  // read by the partner warp in its deferred output epilogue
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->p_full[g]);
+      // ---- deferred output epilogue of the previous item, while the tensor pipe works on this one ----
+      if (prev_any) output_epilogue();
+      ++n_done;
+      prev_any = true;
+      prev_ps = psum;
+      prev_par = par;
+      prev_out = (rok && warp_active) ? p.out + (long long)b * p.o_bs + (long long)row * p.o_rs + h * kD : nullptr;
+    }
+    if (prev_any) {
+      group_sync();                                     // the partner's partial sums of the last item
+      output_epilogue();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+std::once_flag g_once;
+cudaError_t g_attr = cudaSuccess;
+
+}  // namespace
+
+bool attention_self_supported(const AttnArgs& a, int T, int N) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return T >= 1 && T <= kMaxKeys && N >= 1 && N <= T && a.B >= 1 && a.heads >= 1 && al16(a.q) && al16(a.k) && al16(a.v) && al16(a.out) &&
+         a.q_rs % 8 == 0 && a.k_rs % 8 == 0 && a.v_rs % 8 == 0 && a.o_rs % 8 == 0 && a.q_bs % 8 == 0 && a.k_bs % 8 == 0 &&
+         a.v_bs % 8 == 0 && a.o_bs % 8 == 0 && a.q_rs >= a.heads * kD && a.k_rs >= a.heads * kD && a.v_rs >= a.heads * kD;
+}
+
+// a.Lq / a.Lk are ignored: T rows per image, the first N attend among themselves, the remaining T - N among themselves
+int attention_self_run(const AttnArgs& a, int T, int N, cudaStream_t s) {
+  if (!attention_self_supported(a, T, N)) return fail(LMV_ERR_UNSUPPORTED, "attention_self: unsupported shape / alignment");
+  std::call_once(g_once, [] {
+    g_attr = cudaFuncSetAttribute(attention_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  });
+  LMV_CUDA_OK(g_attr);
+  SelfParams p;
+  p.out = a.out; p.o_bs = a.o_bs; p.o_rs = a.o_rs;
+  p.B = a.B; p.heads = a.heads; p.T = T; p.N = N;
+  p.Lkp = (T + 15) & ~15;
+  p.qtiles = (T + kQTile - 1) / kQTile;
+  p.pairs = (p.qtiles + 1) / 2;
+  p.items = (long long)a.B * a.heads * p.pairs;
+  p.scale_log2e = a.scale * 1.4426950408889634f;
+  CUtensorMap tq, tk, tv;
+  auto enc = [&](CUtensorMap* m, const bf16* base, long long bs, int rs, int box_rows) {
+    uint64_t dims[3] = {(uint64_t)a.heads * kD, (uint64_t)T, (uint64_t)a.B};
+    uint64_t strides[2] = {(uint64_t)rs * 2, (uint64_t)bs * 2};
+    uint32_t box[3] = {kD, (uint32_t)box_rows, 1};
+    return encode_tmap_bf16(m, base, 3, dims, strides, box, 64);
+  };
+  int rc;
+  if ((rc = enc(&tq, a.q, a.q_bs, a.q_rs, kQTile))) return rc;
+  if ((rc = enc(&tk, a.k, a.k_bs, a.k_rs, p.Lkp))) return rc;
+  if ((rc = enc(&tv, a.v, a.v_bs, a.v_rs, p.Lkp))) return rc;
+  const int grid = (int)std::min<long long>(p.items, device_sm_count());
+  attention_self_kernel<<<grid, kThreads, kSmemBytes, s>>>(tq, tk, tv, p);
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+}  // namespace lmv

@@ -42,6 +42,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test of a phase (no hardware suspend): for event loops that watch several barriers
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as
 // a hung GPU.  ~2^31 cycles is > 1 s at any clock; legitimate waits are microseconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
@@ -53,6 +65,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
              (int)threadIdx.x, tag, parity);
       __trap();
     }
+  }
+}
+
+// Same bounded wait without the diagnostic printf (about 35 instructions per call site): for kernels whose instruction
+// footprint matters (many warp roles sharing the instruction cache).
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 31)) __trap();
   }
 }
 

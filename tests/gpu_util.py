@@ -14,7 +14,7 @@ def lib():
 
 
 def ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)   # data_ptr() of a view includes its storage offset
 
 
 def stream():
@@ -119,6 +119,17 @@ def attention(q, k, v, scale, impl=0):
         assert t.stride(3) == 1 and t.stride(2) == d
     ok(lib().lmv_attention(ptr(q), q.stride(0), q.stride(1), ptr(k), k.stride(0), k.stride(1), ptr(v), v.stride(0), v.stride(1),
                            ptr(out), out.stride(0), out.stride(1), B, h, Lq, Lk, float(scale), impl, stream()))
+    return out
+
+
+def attention_self(qkv, heads, N, scale):
+    """qkv [B, T, 3C] packed (q | k | v, heads x 32 each): rows < N and rows >= N attend within their own segment."""
+    B, T, C3 = qkv.shape
+    Cc = C3 // 3
+    out = torch.empty((B, T, Cc), dtype=torch.bfloat16, device=qkv.device)
+    q, k, v = qkv[:, :, :Cc], qkv[:, :, Cc:2 * Cc], qkv[:, :, 2 * Cc:]
+    ok(lib().lmv_attention_self(ptr(q), qkv.stride(0), qkv.stride(1), ptr(k), qkv.stride(0), qkv.stride(1), ptr(v), qkv.stride(0), qkv.stride(1),
+                                ptr(out), out.stride(0), out.stride(1), B, heads, T, N, float(scale), stream()))
     return out
 
 

@@ -324,6 +324,23 @@ def test_attention_meta_queries_over_image_tokens(B, h, Lq, Lk):
 
 
 # ---- tail / export ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,h,T,N", [(3, 12, 212, 196), (2, 16, 65, 49), (2, 6, 196, 196), (1, 3, 224, 208), (5, 2, 130, 128), (2, 4, 16, 16),
+                                     (300, 12, 212, 196)])
+def test_attention_self_two_segments(B, h, T, N):
+    """Image tokens (rows < N) and meta tokens (rows >= N) of a packed qkv buffer attend within their own segment."""
+    Cc = h * 32
+    qkv = _rand(B, T, 3 * Cc)
+    scale = 32 ** -0.5
+    out = G.attention_self(qkv, h, N, scale)
+    q, k, v = (qkv[:, :, i * Cc:(i + 1) * Cc].reshape(B, T, h, 32) for i in range(3))
+    ref = torch.empty(B, T, Cc, device="cuda")
+    ref[:, :N] = G.ref_attention(q[:, :N], k[:, :N], v[:, :N], scale)
+    if T > N:
+        ref[:, N:] = G.ref_attention(q[:, N:], k[:, N:], v[:, N:], scale)
+    assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999, G.describe_mismatch(out.float().reshape(B * T, Cc), ref.reshape(B * T, Cc), TOL)
+    assert torch.equal(out, G.attention_self(qkv, h, N, scale))     # deterministic
+
+
 def test_tail_and_nchw_export():
     B, N, M, C = 3, 49, 16, 320
     T = N + M

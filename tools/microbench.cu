@@ -389,6 +389,43 @@ __global__ void __launch_bounds__(384, 1) mma2_bench(const __grid_constant__ CUt
   if (threadIdx.x < 32) tmem_dealloc(tbase, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tma6: boxes of `rows` rows x `cols` bf16 columns cut out of a wide row-major matrix (row pitch `pitch` bytes), i.e. many short
+// row segments per request — what an attention kernel does when it fetches one head's [keys x 32] slice of a packed qkv tensor.
+__global__ void __launch_bounds__(64, 1) tma6_bench(const __grid_constant__ CUtensorMap tm, int box_bytes, int slots, int boxes, int ncol_tiles,
+                                                     int nrow_tiles, int rows, int cols, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  __shared__ uint64_t full[16], empty[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0; uint32_t ph = 0;
+    for (int i = 0; i < boxes; ++i) {
+      mbar_wait(&empty[s], ph ^ 1u, 1);
+      mbar_expect_tx(&full[s], (uint32_t)box_bytes);
+      const int ct = (i + blockIdx.x) % ncol_tiles, rt = (i * 3 + blockIdx.x * 7) % nrow_tiles;
+      tma_load_2d(smem + (size_t)s * 32768, &tm, &full[s], ct * cols, rt * rows);
+      if (++s == slots) { s = 0; ph ^= 1u; }
+    }
+  } else if (threadIdx.x == 32) {
+    int s = 0; uint32_t ph = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < boxes; ++i) {
+      mbar_wait(&full[s], ph, 2);
+      mbar_arrive(&empty[s]);
+      if (++s == slots) { s = 0; ph ^= 1u; }
+    }
+    out[blockIdx.x] = clock64() - t0;
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -500,6 +537,40 @@ int main() {
         printf("tma3 box %3d rows x %d kb (%3d KB) slots %d cluster %d %s: %7.1f cyc/box -> %6.1f B/cyc/SM delivered\n", c.rows, c.kbs,
                c.rows * c.kbs * 128 / 1024, c.slots, c.cluster, mode ? "distinct" : "same    ", avg / boxes, c.rows * c.kbs * 128.0 * boxes / avg);
       }
+  }
+  // ---- tma6: short row segments out of a wide matrix
+  {
+    void* fnp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q));
+    EncodeFn enc = (EncodeFn)fnp;
+    const int width = 1152, total_rows = 16384;          // [16384 x 1152] bf16 = 37.7 MB (L2 resident)
+    void* buf;
+    CK(cudaMalloc(&buf, (size_t)total_rows * width * 2));
+    CK(cudaMemset(buf, 0, (size_t)total_rows * width * 2));
+    CK(cudaFuncSetAttribute(tma6_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    struct Cfg { int rows, cols, swz; };
+    const Cfg cfgs[] = {{224, 32, 64}, {128, 32, 64}, {224, 64, 128}, {128, 64, 128}, {64, 64, 128}, {256, 16, 32}};
+    for (const Cfg& c : cfgs) {
+      CUtensorMap tm;
+      cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)total_rows};
+      cuuint64_t strides[1] = {(cuuint64_t)width * 2};
+      cuuint32_t box[2] = {(cuuint32_t)c.cols, (cuuint32_t)c.rows}, estr[2] = {1, 1};
+      CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       c.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : c.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { printf("encode7 failed %d\n", (int)r); return 1; }
+      const int boxes = 512, slots = 4, box_bytes = c.rows * c.cols * 2;
+      for (int rep = 0; rep < 2; ++rep) {
+        tma6_bench<<<sms, 64, 4 * 32768 + 1024>>>(tm, box_bytes, slots, boxes, width / c.cols, total_rows / c.rows, c.rows, c.cols, out);
+        CK(cudaDeviceSynchronize());
+      }
+      double avg = 0;
+      for (int b = 0; b < sms; ++b) avg += out[b];
+      avg /= sms;
+      printf("tma6 box %3d rows x %2d cols (%3d B segments, pitch 2304 B): %7.1f cyc/box = %5.2f cyc/row -> %5.1f B/cyc/SM\n", c.rows, c.cols, c.cols * 2,
+             avg / boxes, avg / boxes / c.rows, box_bytes * (double)boxes / avg);
+    }
   }
   // ---- mma2: MMA rate under concurrent TMA / LDS traffic
   {

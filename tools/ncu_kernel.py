@@ -23,3 +23,10 @@ elif kind == "gemm":
         G.linear(A, W, bias, gelu="gelu" in sys.argv)
 torch.cuda.synchronize()
 print("done")
+if kind == "attn_self":
+    B, h, T, N = (int(v) for v in sys.argv[2:6])
+    qkv = G.bf(torch.randn(B, T, 3 * h * 32, device="cuda"))
+    for _ in range(3):
+        G.attention_self(qkv, h, N, 32 ** -0.5)
+    torch.cuda.synchronize()
+    print("done attn_self")
