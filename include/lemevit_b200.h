@@ -74,6 +74,7 @@ void lmv_plan_destroy(lmv_plan* plan);
 int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
 /* schedule options (A/B switches; every schedule is rebuilt afterwards).  Known names:
  *   "fused_mlp" (default 1): run `x + mlp(norm2(x))` as ONE kernel (lmv_mlp_fused) where the shape allows it;
+ *   "direct_stem" (default 1): first stem convolution as a direct kernel (lmv_stem_conv1) instead of im2col + GEMM;
  *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self). */
 int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
 /* bring-up switch: 1 routes every GEMM / attention through the plain SIMT cross-check kernels. */
@@ -171,6 +172,11 @@ int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, l
  * out[B*Ho*Wo, Kp] bf16 with k = ci*9 + ky*3 + kx, zero padded to Kp = round_up(9*Cin, 8); the conv
  * itself (+ folded BN + GELU, :700-701) is then lmv_linear on the tcgen05 GEMM. */
 int lmv_stem_im2col(const void* x, int x_dtype, void* out, int B, int Cin, int H, int W, void* stream);
+/* First stem convolution without the im2col detour: x NCHW [B, 3, H, W] (f32 | bf16) -> conv3x3 / stride 2 / pad 1 with the
+ * BatchNorm-folded weights w bf16 [C1][Kp = 32] (k = ci*9 + ky*3 + kx, lemevit_b200/pack.py) + bias -> GELU -> out token-major
+ * [B, ceil(H/2)*ceil(W/2), C1] bf16 (models/lemevit.py:699-701).  Cin must be 3, C1 32 or 48. */
+int lmv_stem_conv1(const void* x, int x_dtype, const void* w, const float* bias, void* out, int B, int Cin, int C1, int H, int W,
+                   void* stream);
 /* im2col for conv 3x3/s2/p1 on NHWC bf16 tokens [B, T, C] (first H*W rows): out[B*Ho*Wo, 9*C] */
 int lmv_im2col_3x3s2(const void* in, void* out, int B, int H, int W, int T, int C, void* stream);
 /* classification tail (models/lemevit.py:815-827): feat[b] = bn_scale*mean_n(x[b]) + bn_shift + mean_m(LN(c[b])) */

@@ -72,6 +72,7 @@ SIGNATURES = {
     "lmv_attention_meta_workspace": (_sz, [_i, _i, _i, _i]),
     "lmv_attention_meta": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "lmv_stem_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "lmv_stem_conv1": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lmv_im2col_3x3s2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lmv_tail": (_i, [_vp, _ll, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _i, _vp]),
     "lmv_tokens_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

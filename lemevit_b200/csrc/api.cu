@@ -71,6 +71,11 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return LMV_OK;
 }
 
+bool pdl_enabled() {
+  static bool v = [] { const char* e = getenv("LMV_PDL"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 int device_sm_count() {
   static int n = [] {
     int dev = 0, v = 148;
@@ -102,9 +107,9 @@ struct StageW {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
-enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_SELF, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
+enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_SELF, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_STEM, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
 static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "mlp_fused_tcgen05", "attention_self_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
-                                                          "posembed_layernorm", "layernorm", "im2col", "misc"};
+                                                          "posembed_layernorm", "layernorm", "stem_conv_direct", "im2col", "misc"};
 struct OpRec {
   Launch fn;
   std::string desc;
@@ -146,6 +151,7 @@ struct lmv_plan {
   int debug_simt = 0;
   int fused_mlp = 1;
   int fused_self_attn = 1;
+  int direct_stem = 1;
   int profile = 0;
   std::vector<cudaEvent_t> events;          // profile mode: one event between consecutive launches
   std::vector<const lmv::OpRec*> pending;   // ops whose events have not been harvested yet
@@ -522,10 +528,20 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
 
   // ---- stem (models/lemevit.py:698-704): conv3x3/s2 + BN + GELU + conv3x3/s2 + BN, both on the GEMM
   {
-    StemArgs sa{nullptr, x_dtype, patches, B, c.in_chans, H, W};
-    sc->push([sa, io](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_im2col_run(a, s); }, OP_IM2COL, 0.0,
-             (double)B * c.in_chans * H * W * (x_dtype == LMV_DTYPE_F32 ? 4 : 2) + 2.0 * B * g.H1 * g.W1 * kp0(c));
-    b.linear(patches, kp0(c), plan->stem1_w, plan->stem1_b, B * g.H1 * g.W1, C0 / 2, kp0(c), stem1, C0 / 2, /*gelu=*/1);
+    if (!b.simt && plan->direct_stem && stem_conv1_supported(c.in_chans, C0 / 2)) {
+      StemArgs sa{nullptr, x_dtype, stem1, B, c.in_chans, H, W};
+      const bf16* w1 = plan->stem1_w;
+      const float* b1 = plan->stem1_b;
+      const int C1 = C0 / 2;
+      sc->push([sa, io, w1, b1, C1](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_conv1_run(a, w1, b1, C1, s); }, OP_STEM,
+               2.0 * B * g.H1 * g.W1 * C1 * 27.0,
+               (double)B * c.in_chans * H * W * (x_dtype == LMV_DTYPE_F32 ? 4 : 2) + 2.0 * B * g.H1 * g.W1 * C1, "stem_conv1_direct");
+    } else {
+      StemArgs sa{nullptr, x_dtype, patches, B, c.in_chans, H, W};
+      sc->push([sa, io](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_im2col_run(a, s); }, OP_IM2COL, 0.0,
+               (double)B * c.in_chans * H * W * (x_dtype == LMV_DTYPE_F32 ? 4 : 2) + 2.0 * B * g.H1 * g.W1 * kp0(c));
+      b.linear(patches, kp0(c), plan->stem1_w, plan->stem1_b, B * g.H1 * g.W1, C0 / 2, kp0(c), stem1, C0 / 2, /*gelu=*/1);
+    }
     Im2colArgs ia{stem1, patches, B, g.H1, g.W1, g.H1 * g.W1, C0 / 2};
     sc->push([ia](cudaStream_t s) { return im2col_run(ia, s); }, OP_IM2COL, 0.0,
              2.0 * B * (C0 / 2) * ((double)g.H1 * g.W1 + 9.0 * g.N[0]));
@@ -862,6 +878,7 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   const std::string n(name);
   if (n == "fused_mlp") plan->fused_mlp = value ? 1 : 0;
   else if (n == "fused_self_attn") plan->fused_self_attn = value ? 1 : 0;
+  else if (n == "direct_stem") plan->direct_stem = value ? 1 : 0;
   else return fail(LMV_ERR_INVALID, "set_option: unknown option " + n);
   plan->cache.clear();   // schedules are rebuilt with the new setting
   return LMV_OK;
@@ -1047,6 +1064,13 @@ int lmv_stem_im2col(const void* x, int x_dtype, void* out, int B, int Cin, int H
   if (!x || !out) return fail(LMV_ERR_INVALID, "stem_im2col: null pointer");
   StemArgs a{x, x_dtype, static_cast<bf16*>(out), B, Cin, H, W};
   return stem_im2col_run(a, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_stem_conv1(const void* x, int x_dtype, const void* w, const float* bias, void* out, int B, int Cin, int C1, int H, int W,
+                   void* stream) {
+  if (!x || !w || !bias || !out) return fail(LMV_ERR_INVALID, "stem_conv1: null pointer");
+  StemArgs a{x, x_dtype, static_cast<bf16*>(out), B, Cin, H, W};
+  return stem_conv1_run(a, static_cast<const bf16*>(w), bias, C1, static_cast<cudaStream_t>(stream));
 }
 
 int lmv_im2col_3x3s2(const void* in, void* out, int B, int H, int W, int T, int C, void* stream) {

@@ -72,6 +72,8 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   const int n0 = tile * kTile;
   const int valid = min(kTile, p.Lk - n0);
 
+  pdl_launch_dependents();
+  pdl_wait();   // the TMA loads below are issued right away
   if (threadIdx.x == 0) {
     mbar_init(&ctrl->bar_load, 1);
     mbar_init(&ctrl->bar_s, 1);
@@ -210,6 +212,8 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
 __global__ void __launch_bounds__(256)
 attention_meta_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, bf16* __restrict__ out,
                             long long o_bs, int o_rs, int B, int tiles, int R, int Lq) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (idx >= (long long)B * R) return;
@@ -278,10 +282,10 @@ int attention_meta_run(const AttnArgs& a, void* workspace, size_t workspace_byte
   if ((rc = enc(&tk, a.k, a.k_bs, a.k_rs))) return rc;
   if ((rc = enc(&tv, a.v, a.v_bs, a.v_rs))) return rc;
   dim3 grid(p.tiles, a.B);
-  attention_meta_kernel<<<grid, kThreads, smem_bytes_for(p.nchunk), s>>>(tk, tv, p);
+  LMV_CUDA_OK(launch_kernel(attention_meta_kernel, dim3(grid), dim3(kThreads), (size_t)(smem_bytes_for(p.nchunk)), s, tk, tv, p));
   LMV_CUDA_OK(cudaGetLastError());
   const long long mrows = (long long)a.B * p.R;
-  attention_meta_merge_kernel<<<(unsigned)((mrows + 7) / 8), 256, 0, s>>>(p.part_o, p.part_ml, a.out, a.o_bs, a.o_rs, a.B, p.tiles, p.R, a.Lq);
+  LMV_CUDA_OK(launch_kernel(attention_meta_merge_kernel, dim3((unsigned)((mrows + 7) / 8)), dim3(256), (size_t)(0), s, p.part_o, p.part_ml, a.out, a.o_bs, a.o_rs, a.B, p.tiles, p.R, a.Lq));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

@@ -115,9 +115,11 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tmem_alloc(&ctrl->tmem_base, 512);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = ctrl->tmem_base;
   const bool two = p.qtiles > 1;                 // does query tile 1 of a pair ever exist
   const uint32_t kv_bytes = (uint32_t)(p.Lkp * kD * 2);
@@ -413,7 +415,7 @@ int attention_self_run(const AttnArgs& a, int T, int N, cudaStream_t s) {
   if ((rc = enc(&tk, a.k, a.k_bs, a.k_rs, p.Lkp))) return rc;
   if ((rc = enc(&tv, a.v, a.v_bs, a.v_rs, p.Lkp))) return rc;
   const int grid = (int)std::min<long long>(p.items, device_sm_count());
-  attention_self_kernel<<<grid, kThreads, kSmemBytes, s>>>(tq, tk, tv, p);
+  LMV_CUDA_OK(launch_kernel(attention_self_kernel, dim3(grid), dim3(kThreads), (size_t)(kSmemBytes), s, tq, tk, tv, p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

@@ -16,6 +16,8 @@ constexpr int kThreads = 128;
 
 __global__ void __launch_bounds__(kThreads)
 attention_simt_kernel(AttnArgs a, int QT, int nsplit) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float sK[kKeysPerTile][kD];
   __shared__ __align__(16) float sV[kKeysPerTile][kD];
   __shared__ float sM[kThreads], sL[kThreads];
@@ -111,7 +113,7 @@ int attention_simt_run(const AttnArgs& a, cudaStream_t s) {
   else if (a.Lq <= 64) QT = 64;
   const int nsplit = kThreads / QT;
   dim3 grid((a.Lq + QT - 1) / QT, a.heads, a.B);
-  attention_simt_kernel<<<grid, kThreads, 0, s>>>(a, QT, nsplit);
+  LMV_CUDA_OK(launch_kernel(attention_simt_kernel, dim3(grid), dim3(kThreads), (size_t)(0), s, a, QT, nsplit));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

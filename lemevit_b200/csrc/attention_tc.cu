@@ -78,9 +78,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_alloc(&ctrl->tmem_base, kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = ctrl->tmem_base;
 
   if (threadIdx.x == 0) {
@@ -215,7 +217,7 @@ int attention_tc_run(const AttnArgs& a, cudaStream_t s) {
   p.out = a.out; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.Lq = a.Lq; p.Lk = a.Lk; p.Lkp = Lkp;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   dim3 grid((a.Lq + kQTile - 1) / kQTile, a.heads, a.B);
-  attention_tc_kernel<<<grid, kThreads, smem_bytes_for(Lkp), s>>>(tq, tk, tv, p);
+  LMV_CUDA_OK(launch_kernel(attention_tc_kernel, dim3(grid), dim3(kThreads), (size_t)(smem_bytes_for(Lkp)), s, tq, tk, tv, p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

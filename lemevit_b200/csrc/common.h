@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <string>
+#include <utility>
 
 #include "../../include/lemevit_b200.h"
 
@@ -39,6 +41,25 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle_bytes);
 
 int device_sm_count();
+
+// Every kernel goes through this launcher: programmatic stream serialization (PDL) lets consecutive kernels of the forward overlap
+// the prologue of kernel n+1 with the tail of kernel n (each kernel calls pdl_wait() before touching dependent global memory).
+// LMV_PDL=0 in the environment turns the attribute off (plain stream order).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // GEMM:  out[M,N] = epilogue( A[M,K] * W[N,K]^T )     (gemm.cu — tcgen05 / TMEM / TMA)

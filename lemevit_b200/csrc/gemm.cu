@@ -152,9 +152,11 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tmem_alloc(&ctrl->tmem_base, 512);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
   const uint32_t tmem_base = ctrl->tmem_base;
   const int num_tiles = p.tiles_m * p.tiles_n;
 
@@ -366,6 +368,8 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // Bring-up / cross-check kernel: one thread per output element, fp32 accumulate.  Tests only.
 __global__ void gemm_simt_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw,
                                  GemmParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)p.M * p.N) return;
   const int row = (int)(idx / p.N), col = (int)(idx % p.N);
@@ -471,7 +475,7 @@ int gemm_run(const GemmOp& op, cudaStream_t stream) {
     g_attr_err = cudaFuncSetAttribute(gemm_bf16_tn_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   });
   LMV_CUDA_OK(g_attr_err);
-  gemm_bf16_tn_tcgen05<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tmA, op.tmB, op.tmR, op.p);
+  LMV_CUDA_OK(launch_kernel(gemm_bf16_tn_tcgen05, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmA, op.tmB, op.tmR, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -485,7 +489,7 @@ int gemm_simt_run(const GemmArgs& a, cudaStream_t stream) {
   p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1;
   p.stats_out = nullptr;   // the SIMT path gets its row statistics from row_stats_run (kernels.h)
   const long long total = (long long)a.M * a.N;
-  gemm_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a.A, a.lda, a.W, a.ldw, p);
+  LMV_CUDA_OK(launch_kernel(gemm_simt_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), stream, a.A, a.lda, a.W, a.ldw, p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

@@ -68,6 +68,9 @@ struct StemArgs {
   int B, Cin, H, W;
 };
 int stem_im2col_run(const StemArgs& a, cudaStream_t s);
+// direct first stem convolution + folded BN + GELU: a.out receives token-major [B, Ho*Wo, C1] (no im2col detour)
+bool stem_conv1_supported(int Cin, int C1);
+int stem_conv1_run(const StemArgs& a, const bf16* w, const float* bias, int C1, cudaStream_t s);
 
 struct Im2colArgs {
   const bf16* in;  // [B, T, C], first H*W rows of each image

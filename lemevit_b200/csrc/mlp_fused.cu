@@ -124,6 +124,8 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tmem_alloc(&ctrl->tmem_base, 512);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
+  pdl_wait();   // barrier init / TMEM allocation above overlapped the previous kernel's tail
   // epilogue constants -> shared memory (read on every chunk by every epilogue warp)
   for (int i = threadIdx.x; i < p.Hd / 2; i += kThreads) {
     const float2 b = __ldg(reinterpret_cast<const float2*>(p.b1) + i);
@@ -439,7 +441,7 @@ int mlp_fused_run(const MlpOp& op, cudaStream_t stream) {
     g_attr = cudaFuncSetAttribute(mlp_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
   });
   LMV_CUDA_OK(g_attr);
-  mlp_fused_tcgen05<<<op.grid, kThreads, op.smem_bytes, stream>>>(op.tmX, op.tmW1, op.tmW2, op.p);
+  LMV_CUDA_OK(launch_kernel(mlp_fused_tcgen05, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmX, op.tmW1, op.tmW2, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

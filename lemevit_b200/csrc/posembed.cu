@@ -49,6 +49,8 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
   const int C = p.C, V = C >> 3, HW = p.H * p.W;
   const int b = blockIdx.y;
   const int ntiles = p.tiles_x * p.tiles_y;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if ((int)blockIdx.x >= ntiles) {
     // ---- meta-token rows of a unified buffer: copy + statistics, one warp per row ----
@@ -211,7 +213,7 @@ int posembed_tile_run(const PosEmbedOp& op, cudaStream_t s) {
   p.TW = op.TW; p.TH = op.TH; p.tiles_x = op.tiles_x; p.tiles_y = op.tiles_y; p.cbox = op.cbox; p.ncb = op.ncb;
   p.sub_bytes = op.sub_bytes;
   dim3 grid(op.tiles_x * op.tiles_y + (a.T > a.H * a.W ? 1 : 0), a.B);
-  posembed_tile_kernel<<<grid, op.threads, op.smem, s>>>(op.tm, p);
+  LMV_CUDA_OK(launch_kernel(posembed_tile_kernel, dim3(grid), dim3(op.threads), (size_t)(op.smem), s, op.tm, p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

@@ -26,6 +26,8 @@ constexpr int kMaxPairs = 8;
 
 __global__ void __launch_bounds__(256)
 posembed_ln_kernel(PosLnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= (long long)a.B * a.T) return;
@@ -114,6 +116,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 template <int G, int ITERS>
 __global__ void __launch_bounds__(256)
 posembed_ln_v2_kernel(PosLnArgs a, int iters) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int SLOTS = 256 / G;
   const int slot = threadIdx.x / G, gl = threadIdx.x % G;
   const int C = a.C, V = C >> 3, HW = a.H * a.W;
@@ -254,6 +258,8 @@ posembed_ln_v2_kernel(PosLnArgs a, int iters) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 layernorm_kernel(LnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= a.R) return;
@@ -308,6 +314,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const T* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int H, int W, int Ho, int Wo,
                    int Kp) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one thread per (output pixel, group of 8 k values)
   const int groups = Kp >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,11 +343,94 @@ stem_im2col_kernel(const T* __restrict__ x, bf16* __restrict__ out, int B, int C
 }
 
 // ------------------------------------------------------------------------------------------------
+// first stem convolution, direct: x NCHW (f32|bf16, 3 channels) -> conv3x3/s2/p1 (+ folded BatchNorm) -> GELU -> token-major
+// [B, Ho*Wo, C1] bf16.  reference: nn.Conv2d(in_chans, C0/2, 3, 2, 1) + BatchNorm2d + GELU (models/lemevit.py:699-701).
+// K = 27 is far too small for a tensor-core tile and the im2col detour writes 2.7x the output volume; here one thread owns two
+// output pixels: their 2 x 27 inputs sit in registers, the folded weights are broadcast from shared memory ([k][C1] fp32), and the C1
+// results leave as one contiguous 2*C1-byte run (neighbouring threads -> neighbouring runs).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2_(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+template <typename T, int C1>
+__global__ void __launch_bounds__(128)
+stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp], k = ci*9 + ky*3 + kx*/, const float* __restrict__ bias,
+                  bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int Kp) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 sw[27 * (C1 / 4)];     // [k][C1]
+  __shared__ float4 sb[C1 / 4];
+  for (int i = threadIdx.x; i < 27 * C1; i += blockDim.x) {
+    const int k = i / C1, c = i - k * C1;
+    reinterpret_cast<float*>(sw)[i] = __bfloat162float(w[c * Kp + k]);
+  }
+  for (int i = threadIdx.x; i < C1; i += blockDim.x) reinterpret_cast<float*>(sb)[i] = bias[i];
+  __syncthreads();
+  // two output pixels per thread: every broadcast weight vector read from shared memory feeds 8 FMAs instead of 4
+  const long long total = (long long)B * Ho * Wo;
+  const long long pix0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (pix0 >= total) return;
+  const bool two = pix0 + 1 < total;
+  float in[2][27];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const long long pix = pix0 + ((q && two) ? 1 : 0);
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+          in[q][ci * 9 + ky * 3 + kx] =
+              (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ld_as_float<T>(x + (((long long)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+        }
+  }
+  float4 acc[2][C1 / 4];
+#pragma unroll
+  for (int c = 0; c < C1 / 4; ++c) { acc[0][c] = sb[c]; acc[1][c] = sb[c]; }
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    const float v0 = in[0][k], v1 = in[1][k];
+#pragma unroll
+    for (int c = 0; c < C1 / 4; ++c) {
+      const float4 wv = sw[k * (C1 / 4) + c];     // same address in every lane: broadcast
+      float2 a;
+      a = ffma2_(make_float2(v0, v0), make_float2(wv.x, wv.y), make_float2(acc[0][c].x, acc[0][c].y)); acc[0][c].x = a.x; acc[0][c].y = a.y;
+      a = ffma2_(make_float2(v0, v0), make_float2(wv.z, wv.w), make_float2(acc[0][c].z, acc[0][c].w)); acc[0][c].z = a.x; acc[0][c].w = a.y;
+      a = ffma2_(make_float2(v1, v1), make_float2(wv.x, wv.y), make_float2(acc[1][c].x, acc[1][c].y)); acc[1][c].x = a.x; acc[1][c].y = a.y;
+      a = ffma2_(make_float2(v1, v1), make_float2(wv.z, wv.w), make_float2(acc[1][c].z, acc[1][c].w)); acc[1][c].z = a.x; acc[1][c].w = a.y;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (q && !two) break;
+    uint4* dst = reinterpret_cast<uint4*>(out + (pix0 + q) * C1);
+#pragma unroll
+    for (int c = 0; c < C1 / 8; ++c) {
+      uint4 u;
+      u.x = pack_bf16x2(gelu_fast(acc[q][2 * c].x), gelu_fast(acc[q][2 * c].y));
+      u.y = pack_bf16x2(gelu_fast(acc[q][2 * c].z), gelu_fast(acc[q][2 * c].w));
+      u.z = pack_bf16x2(gelu_fast(acc[q][2 * c + 1].x), gelu_fast(acc[q][2 * c + 1].y));
+      u.w = pack_bf16x2(gelu_fast(acc[q][2 * c + 1].z), gelu_fast(acc[q][2 * c + 1].w));
+      dst[c] = u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // im2col for conv3x3 stride 2 pad 1 on token-major activations: out[(b,oy,ox), tap*C + ci]
 // reference: stem conv 2 and downsample convs (models/lemevit.py:702,715)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col_3x3s2_kernel(Im2colArgs a, int Ho, int Wo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int vecs = a.C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)a.B * Ho * Wo * 9 * vecs;
@@ -361,6 +452,8 @@ im2col_3x3s2_kernel(Im2colArgs a, int Ho, int Wo) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 tail_kernel(TailArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // mu[M], rstd[M]
   float* mu = sm;
   float* rs = sm + a.M;
@@ -398,6 +491,8 @@ tail_kernel(TailArgs a) {
 template <typename TO>
 __global__ void __launch_bounds__(256)
 tokens_to_nchw_kernel(const bf16* __restrict__ tok, TO* __restrict__ out, int N, int T, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -416,6 +511,8 @@ tokens_to_nchw_kernel(const bf16* __restrict__ tok, TO* __restrict__ out, int N,
 
 __global__ void __launch_bounds__(256)
 broadcast_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int per_image_vecs, int B, long long dst_bs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * per_image_vecs) return;
   const int b = (int)(idx / per_image_vecs), v = (int)(idx % per_image_vecs);
@@ -425,6 +522,8 @@ broadcast_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int 
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int rows, int vecs, int C, int grp_rows,
                    int grp_stride, int grp_off) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)rows * vecs) return;
   const int r = (int)(idx / vecs), v = (int)(idx % vecs);
@@ -434,6 +533,8 @@ gather_rows_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int row
 
 __global__ void __launch_bounds__(256)
 row_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int R, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= R) return;
@@ -459,7 +560,7 @@ static void launch_posln_v2(const PosLnArgs& a, cudaStream_t s) {
   const long long want_blocks = 2LL * device_sm_count();            // keep at least two waves of blocks
   while (iters > 1 && (rows + (long long)SLOTS * iters - 1) / (SLOTS * iters) < want_blocks) --iters;
   const long long per_block = (long long)SLOTS * iters;
-  posembed_ln_v2_kernel<G, ITERS><<<(unsigned)((rows + per_block - 1) / per_block), 256, 0, s>>>(a, iters);
+  (void)launch_kernel(posembed_ln_v2_kernel<G, ITERS>, dim3((unsigned)((rows + per_block - 1) / per_block)), dim3(256), (size_t)(0), s, a, iters);   // error surfaces through cudaGetLastError in the caller
 }
 
 int posembed_ln_run(const PosLnArgs& a, cudaStream_t s) {
@@ -482,7 +583,7 @@ int posembed_ln_run(const PosLnArgs& a, cudaStream_t s) {
     else launch_posln_v2<32, 2>(a, s);
   } else {
     LMV_REQUIRE(a.stats_out == nullptr, "posembed_layernorm: statistics output needs C % 8 == 0");
-    posembed_ln_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(a);
+    LMV_CUDA_OK(launch_kernel(posembed_ln_kernel, dim3(blocks_for(rows, 8)), dim3(256), (size_t)(0), s, a));
   }
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
@@ -490,7 +591,7 @@ int posembed_ln_run(const PosLnArgs& a, cudaStream_t s) {
 
 int row_stats_run(const bf16* x, float* stats, int R, int C, cudaStream_t s) {
   if (R == 0) return LMV_OK;
-  row_stats_kernel<<<blocks_for(R, 8), 256, 0, s>>>(x, stats, R, C);
+  LMV_CUDA_OK(launch_kernel(row_stats_kernel, dim3(blocks_for(R, 8)), dim3(256), (size_t)(0), s, x, stats, R, C));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -498,7 +599,7 @@ int row_stats_run(const bf16* x, float* stats, int R, int C, cudaStream_t s) {
 int layernorm_run(const LnArgs& a, cudaStream_t s) {
   LMV_REQUIRE(a.C % 2 == 0, "layernorm: C must be even");
   if (a.R == 0) return LMV_OK;
-  layernorm_kernel<<<blocks_for(a.R, 8), 256, 0, s>>>(a);
+  LMV_CUDA_OK(launch_kernel(layernorm_kernel, dim3(blocks_for(a.R, 8)), dim3(256), (size_t)(0), s, a));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -509,9 +610,28 @@ int stem_im2col_run(const StemArgs& a, cudaStream_t s) {
   const long long total = (long long)a.B * Ho * Wo * (Kp / 8);
   if (total == 0) return LMV_OK;
   if (a.x_dtype == LMV_DTYPE_F32)
-    stem_im2col_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>((const float*)a.x, a.out, a.B, a.Cin, a.H, a.W, Ho, Wo, Kp);
+    LMV_CUDA_OK(launch_kernel(stem_im2col_kernel<float>, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), s, (const float*)a.x, a.out, a.B, a.Cin, a.H, a.W, Ho, Wo, Kp));
   else
-    stem_im2col_kernel<bf16><<<blocks_for(total, 256), 256, 0, s>>>((const bf16*)a.x, a.out, a.B, a.Cin, a.H, a.W, Ho, Wo, Kp);
+    LMV_CUDA_OK(launch_kernel(stem_im2col_kernel<bf16>, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), s, (const bf16*)a.x, a.out, a.B, a.Cin, a.H, a.W, Ho, Wo, Kp));
+  LMV_CUDA_OK(cudaGetLastError());
+  return LMV_OK;
+}
+
+bool stem_conv1_supported(int Cin, int C1) { return Cin == 3 && (C1 == 32 || C1 == 48); }
+
+int stem_conv1_run(const StemArgs& a, const bf16* w, const float* bias, int C1, cudaStream_t s) {
+  LMV_REQUIRE(stem_conv1_supported(a.Cin, C1), "stem_conv1: needs 3 input channels and 32 or 48 output channels");
+  const int Ho = (a.H + 1) / 2, Wo = (a.W + 1) / 2, Kp = ((a.Cin * 9 + 7) / 8) * 8;
+  const long long total = (long long)a.B * Ho * Wo;
+  if (total == 0) return LMV_OK;
+  const unsigned grid = blocks_for((total + 1) / 2, 128);   // two output pixels per thread
+  if (a.x_dtype == LMV_DTYPE_F32) {
+    if (C1 == 32) LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<float, 32>, dim3(grid), dim3(128), (size_t)(0), s, (const float*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
+    else LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<float, 48>, dim3(grid), dim3(128), (size_t)(0), s, (const float*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
+  } else {
+    if (C1 == 32) LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<bf16, 32>, dim3(grid), dim3(128), (size_t)(0), s, (const bf16*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
+    else LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<bf16, 48>, dim3(grid), dim3(128), (size_t)(0), s, (const bf16*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
+  }
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -521,14 +641,14 @@ int im2col_run(const Im2colArgs& a, cudaStream_t s) {
   const int Ho = (a.H + 1) / 2, Wo = (a.W + 1) / 2;
   const long long total = (long long)a.B * Ho * Wo * 9 * (a.C / 8);
   if (total == 0) return LMV_OK;
-  im2col_3x3s2_kernel<<<blocks_for(total, 256), 256, 0, s>>>(a, Ho, Wo);
+  LMV_CUDA_OK(launch_kernel(im2col_3x3s2_kernel, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), s, a, Ho, Wo));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
 
 int tail_run(const TailArgs& a, cudaStream_t s) {
   if (a.B == 0) return LMV_OK;
-  tail_kernel<<<a.B, 256, 2 * a.M * sizeof(float), s>>>(a);
+  LMV_CUDA_OK(launch_kernel(tail_kernel, dim3(a.B), dim3(256), (size_t)(2 * a.M * sizeof(float)), s, a));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -538,9 +658,9 @@ int tokens_to_nchw_run(const ToNchwArgs& a, cudaStream_t s) {
   if (a.B == 0 || N == 0) return LMV_OK;
   dim3 grid((N + 31) / 32, (a.C + 31) / 32, a.B), block(32, 8);
   if (a.out_dtype == LMV_DTYPE_F32)
-    tokens_to_nchw_kernel<float><<<grid, block, 0, s>>>(a.tokens, (float*)a.out, N, a.T, a.C);
+    LMV_CUDA_OK(launch_kernel(tokens_to_nchw_kernel<float>, dim3(grid), dim3(block), (size_t)(0), s, a.tokens, (float*)a.out, N, a.T, a.C));
   else
-    tokens_to_nchw_kernel<bf16><<<grid, block, 0, s>>>(a.tokens, (bf16*)a.out, N, a.T, a.C);
+    LMV_CUDA_OK(launch_kernel(tokens_to_nchw_kernel<bf16>, dim3(grid), dim3(block), (size_t)(0), s, a.tokens, (bf16*)a.out, N, a.T, a.C));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -550,7 +670,7 @@ int broadcast_rows_run(const bf16* src, bf16* dst, int rows, int C, int B, long 
   const int vecs = rows * C / 8;
   const long long total = (long long)B * vecs;
   if (total == 0) return LMV_OK;
-  broadcast_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, dst, vecs, B, dst_bs);
+  LMV_CUDA_OK(launch_kernel(broadcast_rows_kernel, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), s, src, dst, vecs, B, dst_bs));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -560,7 +680,7 @@ int gather_rows_run(const bf16* src, bf16* dst, int rows, int C, int grp_rows, i
   LMV_REQUIRE(C % 8 == 0 && grp_rows > 0, "gather_rows: C must be a multiple of 8");
   const long long total = (long long)rows * (C / 8);
   if (total == 0) return LMV_OK;
-  gather_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(src, dst, rows, C / 8, C, grp_rows, grp_stride, grp_off);
+  LMV_CUDA_OK(launch_kernel(gather_rows_kernel, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), s, src, dst, rows, C / 8, C, grp_rows, grp_stride, grp_off));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

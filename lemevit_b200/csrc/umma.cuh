@@ -17,6 +17,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (every kernel of the library is launched with programmatic stream serialization, common.h):
+// pdl_launch_dependents() lets the NEXT kernel's CTAs become resident and run their prologue (barrier init, TMEM allocation,
+// descriptor prefetch) while this grid drains; pdl_wait() blocks until every prerequisite grid has completed and its memory is
+// visible — it must precede the first global-memory access that depends on (or could overwrite inputs of) an earlier kernel.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

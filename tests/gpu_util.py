@@ -122,6 +122,19 @@ def attention(q, k, v, scale, impl=0):
     return out
 
 
+def stem_conv1(x, w, bias):
+    """First stem conv (3 -> C1, 3x3 / s2 / p1) + bias + GELU, direct kernel; x NCHW f32|bf16, w [C1, 3, 3, 3] fp32."""
+    B, Cin, H, W = x.shape
+    C1 = w.shape[0]
+    wp = torch.zeros(C1, 32, device=x.device)
+    wp[:, :27] = w.reshape(C1, 27)
+    wp = bf(wp)
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    out = torch.empty((B, Ho * Wo, C1), dtype=torch.bfloat16, device=x.device)
+    ok(lib().lmv_stem_conv1(ptr(x), BF16 if x.dtype == torch.bfloat16 else F32, ptr(wp), ptr(bias), ptr(out), B, Cin, C1, H, W, stream()))
+    return out, wp
+
+
 def attention_self(qkv, heads, N, scale):
     """qkv [B, T, 3C] packed (q | k | v, heads x 32 each): rows < N and rows >= N attend within their own segment."""
     B, T, C3 = qkv.shape

@@ -9,5 +9,5 @@ run() { local name=$1 t=$2; shift 2
   tail -n ${TAILN:-15} gpurun_out/$name.log | tee -a gpurun_out/summary.txt
 }
 K="$1"; shift
-[ -n "$K" ] && run pytest_sel 900 python -m pytest tests -m gpu -x -q -k "$K"
-if [ $# -gt 0 ]; then TAILN=90 run ops 300 python tools/quick_bench.py "$@"; fi
+[ -n "$K" ] && run pytest_sel ${PYTEST_TIMEOUT:-240} python -m pytest tests -m gpu -x -q -k "$K"
+if [ $# -gt 0 ]; then TAILN=90 run ops 200 python tools/quick_bench.py "$@"; fi
