@@ -53,8 +53,29 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel event profile (roofline object)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end loop (used for the ncu launch list)")
     ap.add_argument("--cpu-batch", type=int, default=32)
     return ap.parse_args()
+
+
+# kernel class (native plan profile) -> kernel symbol in the ncu summaries under profiles/
+_CLASS_SYMBOL = {"gemm_tcgen05": "gemm_bf16_tn_tcgen05", "mlp_fused_tcgen05": "mlp_fused_tcgen05", "attention_self_tcgen05": "attention_self_kernel",
+                 "attention_tcgen05": "attention_tc_kernel", "attention_meta_tcgen05": "attention_meta_kernel", "posembed_layernorm": "posembed_tile_kernel"}
+
+
+def ncu_traffic(kernel_class: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu launch list of this bench command
+    (profiles/*_kernels.json, written by tools/ncu_summarize.py); None when no capture is committed."""
+    import glob
+    sym = _CLASS_SYMBOL.get(kernel_class)
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernels.json")), reverse=True):
+        try:
+            k = json.load(open(path))["kernels"].get(sym)
+            if k:
+                return {"bytes_per_launch": k["dram_bytes_per_launch"], "share_of_step_under_ncu": k["share"], "source": os.path.relpath(path, ROOT)}
+        except Exception:
+            continue
+    return None
 
 
 def peaks():
@@ -69,6 +90,30 @@ def peaks():
         return out, "measured"
     except Exception:
         return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# distributed plumbing (one process per GPU; no data-path collective: the batch is sharded)
+# ------------------------------------------------------------------------------------------------
+def shard_seed(rank: int) -> int:
+    """Seed of the synthetic shard a rank generates for itself (every rank gets different images)."""
+    return 1234 + int(rank)
+
+
+def max_over_ranks(value: float, world: int, device=None) -> float:
+    """Whole-job time = the slowest rank's time (all-reduce MAX; NCCL on GPUs, gloo in the CPU tests)."""
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_rate(images_per_rank: int, world: int, ms_max: float) -> float:
+    """img/s of the whole job: every rank processes `images_per_rank` per step (weak scaling), timed by the slowest rank."""
+    return world * images_per_rank / ms_max * 1e3
 
 
 # ------------------------------------------------------------------------------------------------
@@ -227,7 +272,7 @@ def run_ours(args):
     gflop_img = O.algorithmic_flops_per_image(O.VARIANTS[args.model], R, R) / 1e9
 
     # two rotating device-resident batches (2 x 77 MB > L2) + a multi-GB activation workspace streamed every step
-    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    g = torch.Generator(device="cpu").manual_seed(shard_seed(rank))
     xs = [torch.randn(B, 3, R, R, generator=g).to(dev, torch.bfloat16) for _ in range(2)]
     with torch.no_grad():
         y = model(xs[0])
@@ -262,14 +307,11 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         clocks.stop()
         barrier()
-        ms = e0.elapsed_time(e1) / K
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        value = world * B / ms * 1e3
+        ms = max_over_ranks(e0.elapsed_time(e1) / K, world, dev)
+        value = whole_job_rate(B, world, ms)
 
         # ---- end to end through the public API with pinned host buffers (double-buffered upload) ----
+        e2e = None
         hx = [torch.randn(B, 3, R, R, generator=g).to(torch.bfloat16).pin_memory() for _ in range(2)]
         hy = [torch.empty(B, model.num_classes, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
         dx = [torch.empty_like(xs[0]) for _ in range(2)]
@@ -297,20 +339,18 @@ def run_ours(args):
                 hy[cur].copy_(out, non_blocking=True)
             torch.cuda.synchronize(dev)
 
-        e2e_loop(max(2, W // 2))
-        barrier()
-        t0 = time.perf_counter()
-        e2e_loop(K)
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / K
-        barrier()
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        e2e = {"value": world * B / e2e_ms * 1e3, "unit": UNIT, "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": world * hx[0].numel() * hx[0].element_size(),
-               "d2h_bytes_per_step": world * hy[0].numel() * hy[0].element_size(),
-               "api": "lemevit_b200.lemevit_base()(x): pinned host bf16 batch -> H2D -> native forward -> D2H logits, uploads double-buffered on a copy stream"}
+        if not args.no_e2e:
+            e2e_loop(max(2, W // 2))
+            barrier()
+            t0 = time.perf_counter()
+            e2e_loop(K)
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+            barrier()
+            e2e_ms = max_over_ranks(e2e_ms, world, dev)
+            e2e = {"value": whole_job_rate(B, world, e2e_ms), "unit": UNIT, "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": world * hx[0].numel() * hx[0].element_size(),
+                   "d2h_bytes_per_step": world * hy[0].numel() * hy[0].element_size(),
+                   "api": "lemevit_b200.lemevit_base()(x): pinned host bf16 batch -> H2D -> native forward -> D2H logits, uploads double-buffered on a copy stream"}
 
         # ---- per-kernel-class device time (CUDA events between consecutive launches on the launching stream)
         roof = None
@@ -327,7 +367,8 @@ def run_ours(args):
             ach = dom["flops"] / (dom["device_ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops_sustained"], "peak_source": f"bf16_tflops_sustained of {pk_src}",
-                    "traffic": None, "kernel_share_of_step": dom["device_ms"] / tot_ms,
+                    "traffic": (ncu_traffic(dom["name"]) or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(dom["name"]),
+                    "kernel_share_of_step": dom["device_ms"] / tot_ms,
                     "launches_per_step": dom["launches"] // 3, "avg_launch_us": dom["device_ms"] / dom["launches"] * 1e3,
                     "flops_per_launch": dom["flops"] / dom["launches"],
                     "step_achieved": value / world * gflop_img / 1e3, "step_frac": value / world * gflop_img / 1e3 / pk["bf16_tflops_sustained"],

@@ -54,31 +54,7 @@ struct Ctrl {
 };
 static_assert(sizeof(Ctrl) <= 1024, "control block");
 
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
-                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2*>(&rd);
-}
 
-// gelu_fast (umma.cuh) on two values with the packed fp32 pipe (FFMA2 / FMUL2): same polynomial, same MUFU.TANH
-__device__ __forceinline__ float2 gelu_fast2(float2 x) {
-  float2 t = fmul2(x, x);
-  t.x = fminf(t.x, 64.f);   // |x| > 8: the argument stays > 13.8 -> tanh = +-1 exactly
-  t.y = fminf(t.y, 64.f);
-  float2 p = ffma2(t, make_float2(-0.00035151678863588117f, -0.00035151678863588117f),
-                   make_float2(0.037005646022512585f, 0.037005646022512585f));
-  p = ffma2(p, t, make_float2(0.7975078842853727f, 0.7975078842853727f));
-  const float2 u = fmul2(x, p);
-  const float2 th = make_float2(tanh_approx(u.x), tanh_approx(u.y));
-  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
-  return ffma2(hx, th, hx);
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,

@@ -349,12 +349,6 @@ stem_im2col_kernel(const T* __restrict__ x, bf16* __restrict__ out, int B, int C
 // output pixels: their 2 x 27 inputs sit in registers, the folded weights are broadcast from shared memory ([k][C1] fp32), and the C1
 // results leave as one contiguous 2*C1-byte run (neighbouring threads -> neighbouring runs).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 ffma2_(float2 a, float2 b, float2 c) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
-                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  return *reinterpret_cast<float2*>(&rd);
-}
 
 template <typename T, int C1>
 __global__ void __launch_bounds__(128)
@@ -401,10 +395,10 @@ stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp]
     for (int c = 0; c < C1 / 4; ++c) {
       const float4 wv = sw[k * (C1 / 4) + c];     // same address in every lane: broadcast
       float2 a;
-      a = ffma2_(make_float2(v0, v0), make_float2(wv.x, wv.y), make_float2(acc[0][c].x, acc[0][c].y)); acc[0][c].x = a.x; acc[0][c].y = a.y;
-      a = ffma2_(make_float2(v0, v0), make_float2(wv.z, wv.w), make_float2(acc[0][c].z, acc[0][c].w)); acc[0][c].z = a.x; acc[0][c].w = a.y;
-      a = ffma2_(make_float2(v1, v1), make_float2(wv.x, wv.y), make_float2(acc[1][c].x, acc[1][c].y)); acc[1][c].x = a.x; acc[1][c].y = a.y;
-      a = ffma2_(make_float2(v1, v1), make_float2(wv.z, wv.w), make_float2(acc[1][c].z, acc[1][c].w)); acc[1][c].z = a.x; acc[1][c].w = a.y;
+      a = ffma2(make_float2(v0, v0), make_float2(wv.x, wv.y), make_float2(acc[0][c].x, acc[0][c].y)); acc[0][c].x = a.x; acc[0][c].y = a.y;
+      a = ffma2(make_float2(v0, v0), make_float2(wv.z, wv.w), make_float2(acc[0][c].z, acc[0][c].w)); acc[0][c].z = a.x; acc[0][c].w = a.y;
+      a = ffma2(make_float2(v1, v1), make_float2(wv.x, wv.y), make_float2(acc[1][c].x, acc[1][c].y)); acc[1][c].x = a.x; acc[1][c].y = a.y;
+      a = ffma2(make_float2(v1, v1), make_float2(wv.z, wv.w), make_float2(acc[1][c].z, acc[1][c].w)); acc[1][c].z = a.x; acc[1][c].w = a.y;
     }
   }
 #pragma unroll
