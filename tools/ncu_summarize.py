@@ -13,9 +13,10 @@ import sys
 
 
 def short(name: str) -> str:
+    name = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
     name = name.split("(")[0]
     name = re.sub(r"<.*", "", name)
-    return name.split("::")[-1].strip()
+    return name.split("::")[-1].split()[-1].strip()
 
 
 def launches(path, out):
