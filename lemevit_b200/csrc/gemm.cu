@@ -313,31 +313,26 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int cj = (lane & 3) * 2;
           const float4 a = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj) ^ (rl & 7)) << 2));
           const float4 b = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj + 1) ^ (rl & 7)) << 2));
-          // packed fp32 math (FFMA2 / FMUL2 / FADD2): two output columns per instruction
-          float2 o[4] = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w)};
-          const float2 r2 = make_float2(lnr[it], lnr[it]), n2 = make_float2(lnn[it], lnn[it]);
+          float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = ffma2(r2, o[j], ffma2(n2, make_float2(cs[2 * j], cs[2 * j + 1]), make_float2(bs[2 * j], bs[2 * j + 1])));
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(lnr[it], o[j], fmaf(lnn[it], cs[j], bs[j]));
           if (p.act == 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = gelu_fast2(o[j]);
+            for (int j = 0; j < 8; ++j) o[j] = gelu_fast(o[j]);
           }
           if (p.residual) {
-            o[0] = fadd2(o[0], unpack_bf16x2(res[it].x));
-            o[1] = fadd2(o[1], unpack_bf16x2(res[it].y));
-            o[2] = fadd2(o[2], unpack_bf16x2(res[it].z));
-            o[3] = fadd2(o[3], unpack_bf16x2(res[it].w));
+            const float2 r0 = unpack_bf16x2(res[it].x), r1 = unpack_bf16x2(res[it].y), r2 = unpack_bf16x2(res[it].z),
+                         r3 = unpack_bf16x2(res[it].w);
+            o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y; o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
           }
           uint4 w;
-          w.x = pack_bf16x2(o[0].x, o[0].y); w.y = pack_bf16x2(o[1].x, o[1].y);
-          w.z = pack_bf16x2(o[2].x, o[2].y); w.w = pack_bf16x2(o[3].x, o[3].y);
+          w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+          w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
           if (p.stats_out) {   // statistics of the STORED (bf16-rounded) values
             const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z), f3 = unpack_bf16x2(w.w);
-            const float2 sa = fadd2(fadd2(f0, f1), fadd2(f2, f3));
-            const float2 sb = ffma2(f0, f0, ffma2(f1, f1, ffma2(f2, f2, fmul2(f3, f3))));
-            st1[it] += sa.x + sa.y;
-            st2[it] += sb.x + sb.y;
+            st1[it] += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+            st2[it] = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, st2[it]))));
+            st2[it] = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, fmaf(f3.y, f3.y, st2[it]))));
           }
           if (rok_t[it]) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow_t[it] * (long long)p.ldc + col0 + lc) = w;
         }
