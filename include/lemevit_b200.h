@@ -153,13 +153,16 @@ int lmv_layernorm(const void* in, void* out, const float* gamma, const float* be
 int lmv_attention(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
                   long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
                   float scale, int impl, void* stream);
-/* Self-attention of an 'S' block (StandardAttention, models/lemevit.py:199-205) over T <= 224 rows per image, head_dim 32, in ONE
+/* Self-attention of an 'S' block (StandardAttention, models/lemevit.py:199-205) over T rows per image, head_dim 32, in ONE
  * persistent tcgen05 kernel: rows [0, N) (image tokens) attend keys [0, N); rows [N, T) (the meta tokens of a unified
- * [B, N+M, 3C] qkv buffer, forward_with_x :634) attend keys [N, T).  N == T: plain self-attention.  Same pointer / stride
- * conventions as lmv_attention. */
+ * [B, N+M, 3C] qkv buffer, forward_with_x :634) attend keys [N, T).  N == T: plain self-attention.  T > 224 (e.g. the 1024 tokens
+ * of stage 3 at 512x512): N must equal T and ceil(T/128) be even; the keys are split into blocks of <= 224 whose partial
+ * (max, sum, output) go through `workspace` (lmv_attention_self_workspace bytes, 0 for T <= 224) and a merge kernel.  Same pointer /
+ * stride conventions as lmv_attention. */
+size_t lmv_attention_self_workspace(int B, int heads, int T);
 int lmv_attention_self(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
                        long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int T, int N, float scale,
-                       void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* The meta-token side of CrossAttention / DualCrossAttention (models/lemevit.py:484, :300-302): Lq = M (16) queries
  * per head over Lk = N image tokens, heads * Lq <= 128, heads * 32 <= 256.  Split-N tcgen05 kernel (one CTA per image
  * and 128-token tile, block-diagonal Q so that all heads share one accumulation) + deterministic merge of the

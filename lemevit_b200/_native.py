@@ -68,7 +68,8 @@ SIGNATURES = {
     "lmv_posembed_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "lmv_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),
     "lmv_attention": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp]),
-    "lmv_attention_self": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp]),
+    "lmv_attention_self_workspace": (_sz, [_i, _i, _i]),
+    "lmv_attention_self": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "lmv_attention_meta_workspace": (_sz, [_i, _i, _i, _i]),
     "lmv_attention_meta": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "lmv_stem_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),

@@ -349,6 +349,8 @@ static void ws_layout(const lmv_config& c, const Geo& g, int B, WsLayout* L) {
   for (int i = 0; i < c.num_stages; ++i)
     if (c.attn_type[i] != 'S')
       cpart = std::max(cpart, (size_t)B * ((g.N[i] + 127) / 128) * (c.embed_dim[i] / c.head_dim) * M * (32 * 4 + 8));
+  for (int i = 0; i < c.num_stages; ++i)
+    if (c.attn_type[i] == 'S') cpart = std::max(cpart, attention_self_workspace(B, c.embed_dim[i] / c.head_dim, g.T[i]));
   L->cpart_bytes = cpart;
   L->cpart = take((cpart + 1) / 2);
   L->total = off;
@@ -445,10 +447,12 @@ struct Builder {
     a.q_bs = a.k_bs = a.v_bs = (long long)T * 3 * C; a.o_bs = (long long)T * C;
     a.q_rs = a.k_rs = a.v_rs = 3 * C; a.o_rs = C;
     a.B = B; a.heads = heads; a.Lq = T; a.Lk = T; a.scale = scale;
-    if (!simt && plan->fused_self_attn && attention_self_supported(a, T, N)) {
+    if (!simt && plan->fused_self_attn && attention_self_supported(a, T, N) && attention_self_workspace(B, heads, T) <= cpart_bytes) {
+      void* wsp = cpart;
+      const size_t wsb = cpart_bytes;
       const double fl = 4.0 * B * heads * 32.0 * ((double)N * N + (double)(T - N) * (T - N));
       const double by = 2.0 * B * T * 4.0 * C;
-      sc->push([a, T, N](cudaStream_t s) { return attention_self_run(a, T, N, s); }, OP_ATTN_SELF, fl, by,
+      sc->push([a, T, N, wsp, wsb](cudaStream_t s) { return attention_self_run(a, T, N, wsp, wsb, s); }, OP_ATTN_SELF, fl, by,
                "attn_self B=" + std::to_string(B) + " h=" + std::to_string(heads) + " T=" + std::to_string(T) + " N=" + std::to_string(N));
       return;
     }
@@ -1040,11 +1044,13 @@ static AttnArgs make_attn_args(const void* q, long long q_bs, int q_rs, const vo
 
 int lmv_attention_self(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
                        long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int T, int N, float scale,
-                       void* stream) {
+                       void* workspace, size_t workspace_bytes, void* stream) {
   if (!q || !k || !v || !out) return fail(LMV_ERR_INVALID, "attention_self: null pointer");
   AttnArgs a = make_attn_args(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, out, o_bs, o_rs, B, heads, T, T, scale);
-  return attention_self_run(a, T, N, static_cast<cudaStream_t>(stream));
+  return attention_self_run(a, T, N, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
+
+size_t lmv_attention_self_workspace(int B, int heads, int T) { return attention_self_workspace(B, heads, T); }
 
 size_t lmv_attention_meta_workspace(int B, int heads, int Lq, int Lk) {
   AttnArgs a{};

@@ -45,6 +45,9 @@ struct SelfParams {
   long long o_bs;
   int o_rs;
   int B, heads, T, N, Lkp, pairs, qtiles;
+  int nkv, KB;               // key blocks per (image, head) and keys per block (nkv > 1: split-KV, partials merged by a second kernel)
+  float* part_o;             // [B*heads][qtiles*128][nkv][32] unnormalised outputs of every key block (nkv > 1)
+  float2* part_ml;           // [B*heads][qtiles*128][nkv] (row max * scale * log2e, row sum)
   long long items;
   float scale_log2e;
 };
@@ -113,9 +116,11 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const bool two = p.qtiles > 1;                 // does query tile 1 of a pair ever exist
   const uint32_t kv_bytes = (uint32_t)(p.Lkp * kD * 2);
 
-  // item -> (b, h, pair)
-  auto decode = [&](long long it, int& b, int& h, int& pr) {
-    const long long item = blockIdx.x + it * gridDim.x;
+  // item -> (b, h, pair of query tiles, key block); the key block is the fastest index: neighbouring CTAs share Q in L2
+  auto decode = [&](long long it, int& b, int& h, int& pr, int& kvb) {
+    long long item = blockIdx.x + it * gridDim.x;
+    kvb = (int)(item % p.nkv);
+    item /= p.nkv;
     pr = (int)(item % p.pairs);
     const long long bh = item / p.pairs;
     h = (int)(bh % p.heads);
@@ -128,16 +133,16 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (long long it = 0; it < n_my; ++it) {
         const int s = (int)(it & 1);
         const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-        int b, h, pr;
-        decode(it, b, h, pr);
+        int b, h, pr, kvb;
+        decode(it, b, h, pr, kvb);
         const bool has1 = (2 * pr + 1) < p.qtiles;
         mbar_wait_lean(&ctrl->ld_empty[s], ph ^ 1u);
         uint8_t* st = sStage + (size_t)s * kStageBytes;
         mbar_expect_tx(&ctrl->ld_full[s], (uint32_t)(kQBytes * (has1 ? 2 : 1)) + 2u * kv_bytes);
         tma_load_3d(st, &tmQ, &ctrl->ld_full[s], h * kD, (2 * pr) * kQTile, b);
         if (has1) tma_load_3d(st + kQBytes, &tmQ, &ctrl->ld_full[s], h * kD, (2 * pr + 1) * kQTile, b);
-        tma_load_3d(st + 2 * kQBytes, &tmK, &ctrl->ld_full[s], h * kD, 0, b);
-        tma_load_3d(st + 2 * kQBytes + kKVBytes, &tmV, &ctrl->ld_full[s], h * kD, 0, b);
+        tma_load_3d(st + 2 * kQBytes, &tmK, &ctrl->ld_full[s], h * kD, kvb * p.KB, b);   // rows past T are zero-filled
+        tma_load_3d(st + 2 * kQBytes + kKVBytes, &tmV, &ctrl->ld_full[s], h * kD, kvb * p.KB, b);
       }
     }
   } else if (warp == 1) {
@@ -219,8 +224,10 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(kGroupWarps * 32) : "memory"); };
     // deferred output epilogue state of the previous item
     float prev_ps = 0.f;          // this warp's partial row sum
+    float prev_mxs = 0.f;         // row max * scale * log2e (split-KV partials)
     uint32_t prev_par = 0;        // which x_sum / y_sum slot holds the previous item's partial sums
-    bf16* prev_out = nullptr;
+    bf16* prev_out = nullptr;     // final output row (single key block)
+    long long prev_prow = -1;     // partial row index (split-KV)
     bool prev_any = false;
     uint32_t n_done = 0;          // items this group has processed (phase counter of its barriers)
     auto output_epilogue = [&]() {
@@ -243,32 +250,44 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
           reinterpret_cast<uint4*>(prev_out + hcol * 16)[j] = u;
         }
+      } else if (prev_prow >= 0) {
+        // split-KV: unnormalised partial of this key block; the merge kernel rescales and sums the blocks
+        float4* dst = reinterpret_cast<float4*>(p.part_o + prev_prow * kD + hcol * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        if (hcol == 0) p.part_ml[prev_prow] = make_float2(prev_mxs, prev_ps + y_sum[prev_par * kQTile + r]);
       }
     };
-    // The key range of a row depends only on (tile, row) — identical for every item: classify the 32-column chunks once.
-    // bit c of full_mask: every lane of this warp sees all 32 keys of chunk c (no masking code needed).
-    const int tile = g;                                // T <= 224: one pair per (image, head), query tile == group
-    const int row = tile * kQTile + r;
-    const bool rok = row < p.T;
-    // image tokens attend image tokens, meta tokens attend meta tokens (rows that do not exist behave like image rows)
-    const int kbeg = (rok && row >= p.N) ? p.N : 0;
-    const int kend = (rok && row >= p.N) ? p.T : p.N;
-    const bool warp_active = tile * kQTile + q * 32 < p.T;   // warp-uniform: any valid row in this warp
-    uint32_t full_mask = 0;
-    for (int c = 0; c < nchunk; ++c) {
-      const int c0 = c * 32;
-      if (__all_sync(0xffffffffu, kbeg <= c0 && c0 + 32 <= kend)) full_mask |= 1u << c;
-    }
-
     const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
 
     for (long long it = 0; it < n_my; ++it) {
-      if (tile >= p.qtiles) break;                     // no second query tile: nothing for group 1
-      int b, h, pr;
-      decode(it, b, h, pr);
+      if (g >= p.qtiles) break;                        // a single query tile per (image, head): nothing for group 1
+      int b, h, pr, kvb;
+      decode(it, b, h, pr, kvb);
+      const int tile = 2 * pr + g;
+      const int row = tile * kQTile + r;
+      const bool rok = row < p.T;
+      // key range of this row inside the key block.  One block (T <= 224): image tokens attend image tokens, meta tokens attend
+      // meta tokens (rows that do not exist behave like image rows).  Split-KV: every row sees the block's keys below T.
+      int kbeg, kend;
+      if (p.nkv == 1) {
+        kbeg = (rok && row >= p.N) ? p.N : 0;
+        kend = (rok && row >= p.N) ? p.T : p.N;
+      } else {
+        kbeg = 0;
+        kend = max(0, min(p.KB, p.T - kvb * p.KB));
+      }
+      const bool warp_active = tile * kQTile + q * 32 < p.T;   // warp-uniform: any valid row in this warp
+      // bit c of full_mask: every lane of this warp sees all 32 keys of chunk c (no masking code needed)
+      uint32_t full_mask = 0;
+      for (int c = cbeg; c < cend; ++c) {
+        const int c0 = c * 32;
+        if (__all_sync(0xffffffffu, kbeg <= c0 && c0 + 32 <= kend)) full_mask |= 1u << c;
+      }
       mbar_wait_lean(&ctrl->s_full[g], n_done & 1u);
       tc_fence_after();
-      float psum = 0.f;
+      float psum = 0.f, mxs_item = 0.f;
       float pm = -INFINITY;
       auto mask_chunk = [&](uint32_t (&v)[32], int c0) {
         // keys outside this row's segment get a score of -inf (exp2 -> exactly 0); applied to the loaded registers of the few
@@ -302,6 +321,7 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait_lean(&ctrl->p_empty[g], (n_done & 1u) ^ 1u);
       if (warp_active) {
         const float mxs = fmaxf(pm, y_max[r]) * p.scale_log2e;
+        mxs_item = mxs;
         const float2 nm2 = make_float2(-mxs, -mxs);
         // ---- pass 2: p = exp2(s * scale - max), partial row sum (two packed chains), bf16 P tile ----
         float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
@@ -352,8 +372,14 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ++n_done;
       prev_any = true;
       prev_ps = psum;
+      prev_mxs = mxs_item;
       prev_par = par;
-      prev_out = (rok && warp_active) ? p.out + (long long)b * p.o_bs + (long long)row * p.o_rs + h * kD : nullptr;
+      prev_out = nullptr;
+      prev_prow = -1;
+      if (rok && warp_active) {
+        if (p.nkv == 1) prev_out = p.out + (long long)b * p.o_bs + (long long)row * p.o_rs + h * kD;
+        else prev_prow = (((long long)b * p.heads + h) * (p.qtiles * kQTile) + row) * p.nkv + kvb;
+      }
     }
     if (prev_any) {
       group_sync();                                     // the partner's partial sums of the last item
@@ -365,21 +391,63 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+// split-KV merge: one warp per (image, head, query row), lane = channel; fixed block order (deterministic)
+__global__ void __launch_bounds__(256)
+attention_self_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, bf16* __restrict__ out, long long o_bs, int o_rs,
+                            int B, int heads, int T, int Tpad, int nkv) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (idx >= (long long)B * heads * T) return;
+  const int row = (int)(idx % T);
+  const long long bh = idx / T;
+  const int h = (int)(bh % heads), b = (int)(bh / heads);
+  const long long base = (bh * Tpad + row) * nkv;
+  float m = -INFINITY;
+  for (int k = 0; k < nkv; ++k) m = fmaxf(m, part_ml[base + k].x);
+  float l = 0.f, o = 0.f;
+  for (int k = 0; k < nkv; ++k) {
+    const float2 ml = part_ml[base + k];
+    const float w = exp2f(ml.x - m);
+    l = fmaf(ml.y, w, l);
+    o = fmaf(part_o[(base + k) * kD + lane], w, o);
+  }
+  out[(long long)b * o_bs + (long long)row * o_rs + h * kD + lane] = __float2bfloat16(o / l);
+}
+
 std::once_flag g_once;
 cudaError_t g_attr = cudaSuccess;
 
 }  // namespace
 
+// T <= 224: one key block (image + meta segments allowed).  Larger T (e.g. 1024 tokens at 512x512): split-KV over
+// ceil(T / 224) key blocks, plain self-attention only (N == T) and an even number of 128-row query tiles.
+static int self_nkv(int T) { return (T + kMaxKeys - 1) / kMaxKeys; }
+static int self_kb(int T) { const int n = self_nkv(T); return (((T + n - 1) / n) + 15) & ~15; }
+
 bool attention_self_supported(const AttnArgs& a, int T, int N) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  return T >= 1 && T <= kMaxKeys && N >= 1 && N <= T && a.B >= 1 && a.heads >= 1 && al16(a.q) && al16(a.k) && al16(a.v) && al16(a.out) &&
+  const int qtiles = (T + kQTile - 1) / kQTile;
+  const bool shape_ok = T >= 1 && N >= 1 && N <= T && (T <= kMaxKeys || (N == T && qtiles % 2 == 0 && self_kb(T) <= kMaxKeys));
+  return shape_ok && a.B >= 1 && a.heads >= 1 && al16(a.q) && al16(a.k) && al16(a.v) && al16(a.out) &&
          a.q_rs % 8 == 0 && a.k_rs % 8 == 0 && a.v_rs % 8 == 0 && a.o_rs % 8 == 0 && a.q_bs % 8 == 0 && a.k_bs % 8 == 0 &&
          a.v_bs % 8 == 0 && a.o_bs % 8 == 0 && a.q_rs >= a.heads * kD && a.k_rs >= a.heads * kD && a.v_rs >= a.heads * kD;
 }
 
+size_t attention_self_workspace(int B, int heads, int T) {
+  const int nkv = self_nkv(T);
+  if (nkv <= 1) return 0;
+  const size_t rows = (size_t)B * heads * (((T + kQTile - 1) / kQTile) * kQTile) * nkv;
+  return rows * (kD * sizeof(float) + sizeof(float2));
+}
+
 // a.Lq / a.Lk are ignored: T rows per image, the first N attend among themselves, the remaining T - N among themselves
-int attention_self_run(const AttnArgs& a, int T, int N, cudaStream_t s) {
+int attention_self_run(const AttnArgs& a, int T, int N, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   if (!attention_self_supported(a, T, N)) return fail(LMV_ERR_UNSUPPORTED, "attention_self: unsupported shape / alignment");
+  LMV_REQUIRE(attention_self_workspace(a.B, a.heads, T) == 0 ||
+                  (workspace && workspace_bytes >= attention_self_workspace(a.B, a.heads, T) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0),
+              "attention_self: split-KV workspace missing or too small");
   std::call_once(g_once, [] {
     g_attr = cudaFuncSetAttribute(attention_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   });
@@ -387,10 +455,18 @@ int attention_self_run(const AttnArgs& a, int T, int N, cudaStream_t s) {
   SelfParams p;
   p.out = a.out; p.o_bs = a.o_bs; p.o_rs = a.o_rs;
   p.B = a.B; p.heads = a.heads; p.T = T; p.N = N;
-  p.Lkp = (T + 15) & ~15;
+  p.nkv = self_nkv(T);
+  p.KB = p.nkv == 1 ? ((T + 15) & ~15) : self_kb(T);
+  p.Lkp = p.KB;
   p.qtiles = (T + kQTile - 1) / kQTile;
   p.pairs = (p.qtiles + 1) / 2;
-  p.items = (long long)a.B * a.heads * p.pairs;
+  p.items = (long long)a.B * a.heads * p.pairs * p.nkv;
+  p.part_o = nullptr; p.part_ml = nullptr;
+  if (p.nkv > 1) {
+    const size_t rows = (size_t)a.B * a.heads * (p.qtiles * kQTile) * p.nkv;
+    p.part_o = static_cast<float*>(workspace);
+    p.part_ml = reinterpret_cast<float2*>(p.part_o + rows * kD);
+  }
   p.scale_log2e = a.scale * 1.4426950408889634f;
   CUtensorMap tq, tk, tv;
   auto enc = [&](CUtensorMap* m, const bf16* base, long long bs, int rs, int box_rows) {
@@ -406,6 +482,12 @@ int attention_self_run(const AttnArgs& a, int T, int N, cudaStream_t s) {
   const int grid = (int)std::min<long long>(p.items, device_sm_count());
   LMV_CUDA_OK(launch_kernel(attention_self_kernel, dim3(grid), dim3(kThreads), (size_t)(kSmemBytes), s, tq, tk, tv, p));
   LMV_CUDA_OK(cudaGetLastError());
+  if (p.nkv > 1) {
+    const long long mrows = (long long)a.B * a.heads * T;
+    LMV_CUDA_OK(launch_kernel(attention_self_merge_kernel, dim3((unsigned)((mrows + 7) / 8)), dim3(256), (size_t)0, s, p.part_o, p.part_ml, a.out, a.o_bs,
+                              a.o_rs, a.B, a.heads, T, p.qtiles * kQTile, p.nkv));
+    LMV_CUDA_OK(cudaGetLastError());
+  }
   return LMV_OK;
 }
 

@@ -52,10 +52,11 @@ struct AttnArgs {
 int attention_simt_run(const AttnArgs& a, cudaStream_t s);
 int attention_tc_run(const AttnArgs& a, cudaStream_t s);      // tcgen05 self/cross attention (attention.cu)
 bool attention_tc_supported(const AttnArgs& a);
-// persistent self-attention over T <= 224 rows per image in two independent segments: rows [0, N) among themselves (image tokens)
+// persistent self-attention; T <= 224 rows per image in two independent segments (T > 224: plain self-attention, split over key blocks): rows [0, N) among themselves (image tokens)
 // and rows [N, T) among themselves (the meta tokens of a unified [B, N+M, 3C] qkv buffer); a.Lq / a.Lk are ignored (attention_self.cu)
 bool attention_self_supported(const AttnArgs& a, int T, int N);
-int attention_self_run(const AttnArgs& a, int T, int N, cudaStream_t s);
+size_t attention_self_workspace(int B, int heads, int T);   // split-KV partials (T > 224), 0 otherwise
+int attention_self_run(const AttnArgs& a, int T, int N, void* workspace, size_t workspace_bytes, cudaStream_t s);
 // few queries (meta tokens) x many keys (image tokens): split-N tcgen05 kernel + partial merge (attention_meta.cu)
 bool attention_meta_supported(const AttnArgs& a);
 size_t attention_meta_workspace(const AttnArgs& a);

@@ -141,8 +141,10 @@ def attention_self(qkv, heads, N, scale):
     Cc = C3 // 3
     out = torch.empty((B, T, Cc), dtype=torch.bfloat16, device=qkv.device)
     q, k, v = qkv[:, :, :Cc], qkv[:, :, Cc:2 * Cc], qkv[:, :, 2 * Cc:]
+    need = int(lib().lmv_attention_self_workspace(B, heads, T))
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=qkv.device)
     ok(lib().lmv_attention_self(ptr(q), qkv.stride(0), qkv.stride(1), ptr(k), qkv.stride(0), qkv.stride(1), ptr(v), qkv.stride(0), qkv.stride(1),
-                                ptr(out), out.stride(0), out.stride(1), B, heads, T, N, float(scale), stream()))
+                                ptr(out), out.stride(0), out.stride(1), B, heads, T, N, float(scale), ptr(ws), need, stream()))
     return out
 
 
