@@ -30,3 +30,15 @@ if kind == "attn_self":
         G.attention_self(qkv, h, N, 32 ** -0.5)
     torch.cuda.synchronize()
     print("done attn_self")
+if kind == "posln":
+    B, H, W, C, M = (int(v) for v in sys.argv[2:7])
+    T = H * W + M
+    tok = G.bf(torch.randn(B, T, C, device="cuda"))
+    w9 = torch.randn(9, C, device="cuda") * 0.1
+    db = torch.randn(C, device="cuda") * 0.1
+    out = torch.empty_like(tok)
+    stats = torch.empty(B * T, 2, device="cuda")
+    for _ in range(3):
+        G.ok(G.lib().lmv_posembed_layernorm(G.ptr(tok), G.ptr(w9), G.ptr(db), G.ptr(out), None, G.ptr(stats), B, H, W, T, C, 1e-6, G.stream()))
+    torch.cuda.synchronize()
+    print("done posln")
