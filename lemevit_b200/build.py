@@ -40,6 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("LMV_NVCC_EXTRA", "").split()   # debug builds, e.g. -DLMV_GEMM_TRACE (tools/gemm_trace.py)
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

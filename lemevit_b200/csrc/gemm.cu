@@ -122,6 +122,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
+// Debug build (-DLMV_GEMM_TRACE): per-warp cycle accounting of the three roles, read back with lmv_debug_gemm_trace().
+#ifdef LMV_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[148 * 10 * 8];
+#define TR_INIT unsigned long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t = clock64(); const long long tr_t0 = tr_t;
+#define TR(i) { const long long now_ = clock64(); tr[i] += (unsigned long long)(now_ - tr_t); tr_t = now_; }
+#define TR_FLUSH { tr[7] = (unsigned long long)(clock64() - tr_t0); if (lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_gemm_trace[((size_t)blockIdx.x * 10 + warp) * 8 + i_] += tr[i_]; }
+#else
+#define TR_INIT
+#define TR(i)
+#define TR_FLUSH
+#endif
+
+// EPI >= 0: the fast-path epilogue features are fixed at compile time (bit set below: less code, fewer live registers,
+// no speculated residual unpack); EPI = -1 decides them at run time from GemmParams (any other combination).
+constexpr int kEpiLn = 1, kEpiGelu = 2, kEpiRes = 4, kEpiStats = 8;
+
+template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
@@ -165,12 +182,15 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      TR_INIT
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
         // pull the residual tile into L2 while the mainloop of this tile runs: the epilogue reads it ~2 tiles later
         if (p.prefetch_res) tma_prefetch_l2_2d(&tmR, n_blk * p.BN, m_blk * BM);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          TR(1)
           mbar_wait(&ctrl->empty[stage], phase ^ 1u, 1);
+          TR(0)
           uint8_t* sa = tiles + (size_t)stage * stage_bytes;
           mbar_expect_tx(&ctrl->full[stage], (uint32_t)stage_bytes);
           tma_load_2d(sa, &tmA, &ctrl->full[stage], kb * BK, m_blk * BM);
@@ -178,6 +198,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
+      TR_FLUSH
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
@@ -185,12 +206,17 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t idesc = make_idesc_bf16(BM, p.BN);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
+      TR_INIT
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        TR(2)
         mbar_wait(&ctrl->acc_empty[as], aphase ^ 1u, 2);
+        TR(0)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          TR(2)
           mbar_wait(&ctrl->full[stage], phase, 3);
+          TR(1)
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
           const uint64_t da = make_kmajor_desc<128>(sa);
@@ -207,11 +233,16 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
+      TR_FLUSH
     }
   } else {
     // ---------------- epilogue (warps 2..9) ----------------
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // the two warps of a quarter take alternate 32-column chunks
+    const bool f_ln = EPI < 0 ? (p.ln_stats != nullptr) : ((EPI & kEpiLn) != 0);
+    const bool f_gelu = EPI < 0 ? (p.act == 1) : ((EPI & kEpiGelu) != 0);
+    const bool f_res = EPI < 0 ? (p.residual != nullptr) : ((EPI & kEpiRes) != 0);
+    const bool f_stats = EPI < 0 ? (p.stats_out != nullptr) : ((EPI & kEpiStats) != 0);
     const bool vec_ok = (p.ldc % 8 == 0);
     const bool fast_ok = vec_ok && !p.out_fp32;
     float* stg = reinterpret_cast<float*>(smem + 1024 + (size_t)(warp - 2) * kStageF32);
@@ -232,14 +263,15 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (k < p.ln_parts) nst[k] = __ldg(st + k);
       }
     };
-    if (p.ln_stats && (int)blockIdx.x < num_tiles) load_stats(blockIdx.x);
+    if (f_ln && (int)blockIdx.x < num_tiles) load_stats(blockIdx.x);
+    TR_INIT
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
       long long orow_t[4];
       bool rok_t[4];
       float lnr[4], lnn[4];   // LayerNorm fold: v = r * acc + (-r * mu) * colsum[n] + bias[n]
       float own_r = 1.f, own_n = 0.f;
-      if (p.ln_stats) {
+      if (f_ln) {
         const float s1 = (nst[0].x + nst[1].x) + (nst[2].x + nst[3].x), s2 = (nst[0].y + nst[1].y) + (nst[2].y + nst[3].y);
         const float mu = s1 * p.ln_inv_k;
         const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mu * mu), 0.f);
@@ -256,7 +288,8 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         lnn[it] = __shfl_sync(0xffffffffu, own_n, it * 8 + lr);
       }
       float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
-      bool waited = false;
+      bool waited = false, loaded = false, released = false;
+      uint32_t r[32];   // accumulator chunk in flight: the next chunk's tcgen05.ld is issued as soon as this one sits in smem
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride);
       for (int c0 = half * 32; c0 < p.BN; c0 += 64) {
         const int col0 = n_blk * p.BN + c0;
@@ -273,31 +306,34 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + lc) + 1);
             bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
           }
-          if (p.ln_stats) {
+          if (f_ln) {
             const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + lc));
             const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + lc) + 1);
             cs[0] = s0.x; cs[1] = s0.y; cs[2] = s0.z; cs[3] = s0.w; cs[4] = s1.x; cs[5] = s1.y; cs[6] = s1.z; cs[7] = s1.w;
           }
-          if (p.residual) {
+          if (f_res) {
 #pragma unroll
             for (int it = 0; it < 4; ++it)
               res[it] = rok_t[it] ? *reinterpret_cast<const uint4*>(p.residual + orow_t[it] * (long long)p.ldc + col0 + lc)
                                   : make_uint4(0u, 0u, 0u, 0u);   // plain load: residual may alias out
           }
         }
+        TR(4)   // tile setup + chunk prologue (bias / colsum / residual loads issued)
         if (!waited) {
           mbar_wait(&ctrl->acc_full[as], aphase, 4);
           tc_fence_after();
           waited = true;
         }
-        uint32_t r[32];
-        tmem_ld_x32(taddr + (uint32_t)c0, r);
+        TR(0)
+        if (!loaded) tmem_ld_x32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
+        TR(1)
         if (!fast) {
           const int row = m_blk * BM + q * 32 + lane;
           long long orow = row;
           if (p.grp_rows > 0) orow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows);
           epilogue_chunk(p, r, row, orow, col0, vec_ok, own_r, own_n);
+          loaded = false;
           continue;
         }
         // ---- transpose the raw fp32 accumulators through the per-warp staging buffer ----
@@ -307,6 +343,19 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
+        {
+          const int c1 = c0 + 64;
+          loaded = c1 < p.BN && n_blk * p.BN + c1 < p.N;
+          if (loaded) {
+            tmem_ld_x32(taddr + (uint32_t)c1, r);   // lands while this chunk goes through math and stores
+          } else {
+            // the accumulator stage is fully read (every lane passed its tcgen05.wait::ld before the __syncwarp): hand it back now
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
+            released = true;
+          }
+        }
+        TR(2)   // transpose stores
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int rl = it * 8 + lr;
@@ -314,13 +363,18 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const float4 a = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj) ^ (rl & 7)) << 2));
           const float4 b = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj + 1) ^ (rl & 7)) << 2));
           float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (f_ln) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = fmaf(lnr[it], o[j], fmaf(lnn[it], cs[j], bs[j]));
-          if (p.act == 1) {
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(lnr[it], o[j], fmaf(lnn[it], cs[j], bs[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += bs[j];
+          }
+          if (f_gelu) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = gelu_fast(o[j]);
           }
-          if (p.residual) {
+          if (f_res) {
             const float2 r0 = unpack_bf16x2(res[it].x), r1 = unpack_bf16x2(res[it].y), r2 = unpack_bf16x2(res[it].z),
                          r3 = unpack_bf16x2(res[it].w);
             o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y; o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
@@ -328,7 +382,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint4 w;
           w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
           w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-          if (p.stats_out) {   // statistics of the STORED (bf16-rounded) values
+          if (f_stats) {   // statistics of the STORED (bf16-rounded) values
             const float2 f0 = unpack_bf16x2(w.x), f1 = unpack_bf16x2(w.y), f2 = unpack_bf16x2(w.z), f3 = unpack_bf16x2(w.w);
             st1[it] += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
             st2[it] = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, st2[it]))));
@@ -336,15 +390,18 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           if (rok_t[it]) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow_t[it] * (long long)p.ldc + col0 + lc) = w;
         }
+        TR(3)   // transposed reads + math + global stores
       }
       if (!waited) {   // this warp had no chunk in this tile (BN == 32): still consume the phase
         mbar_wait(&ctrl->acc_full[as], aphase, 4);
         tc_fence_after();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
-      if (p.stats_out) {
+      if (!released) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
+      }
+      if (f_stats) {
         // deterministic partials (no atomics): slot (n_blk, half) of every row this warp covers
         const int parts = 2 * p.tiles_n, part = 2 * n_blk + half;
 #pragma unroll
@@ -358,7 +415,9 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
+      TR(5)   // accumulator release + statistics partials
     }
+    TR_FLUSH
   }
   tc_fence_before();
   __syncthreads();
@@ -470,12 +529,33 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   return LMV_OK;
 }
 
+using GemmKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+// the epilogue combinations the LeMeViT schedule uses get their own instantiation; everything else runs the run-time one
+static const struct { int flags; GemmKernel fn; } kGemmVariants[] = {
+    {0, gemm_bf16_tn_tcgen05<0>},                                   // bias only (convolutions as GEMM, c-path q/kv)
+    {kEpiLn, gemm_bf16_tn_tcgen05<kEpiLn>},                         // LN-folded qkv
+    {kEpiLn | kEpiGelu, gemm_bf16_tn_tcgen05<kEpiLn | kEpiGelu>},   // LN-folded fc1 + GELU
+    {kEpiGelu, gemm_bf16_tn_tcgen05<kEpiGelu>},                     // fc1 + GELU on already-normalised input
+    {kEpiRes, gemm_bf16_tn_tcgen05<kEpiRes>},                       // fc2 + residual
+    {kEpiRes | kEpiStats, gemm_bf16_tn_tcgen05<kEpiRes | kEpiStats>},   // proj + residual + statistics for the next LN
+    {-1, gemm_bf16_tn_tcgen05<-1>},
+};
+
 int gemm_run(const GemmOp& op, cudaStream_t stream) {
   std::call_once(g_attr_once, [] {
-    g_attr_err = cudaFuncSetAttribute(gemm_bf16_tn_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    for (const auto& v : kGemmVariants) {
+      const cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+      if (e != cudaSuccess) g_attr_err = e;
+    }
   });
   LMV_CUDA_OK(g_attr_err);
-  LMV_CUDA_OK(launch_kernel(gemm_bf16_tn_tcgen05, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmA, op.tmB, op.tmR, op.p));
+  const GemmParams& gp = op.p;
+  const int flags = (gp.ln_stats ? kEpiLn : 0) | (gp.act == 1 ? kEpiGelu : 0) | (gp.residual ? kEpiRes : 0) | (gp.stats_out ? kEpiStats : 0);
+  GemmKernel fn = gemm_bf16_tn_tcgen05<-1>;
+  if (gp.act == 0 || gp.act == 1)
+    for (const auto& v : kGemmVariants)
+      if (v.flags == flags) { fn = v.fn; break; }
+  LMV_CUDA_OK(launch_kernel(fn, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmA, op.tmB, op.tmR, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
@@ -495,3 +575,14 @@ int gemm_simt_run(const GemmArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace lmv
+
+#ifdef LMV_GEMM_TRACE
+// copies out and clears the [148 CTAs][10 warps][8 counters] cycle table of the traced GEMM launches (debug builds only)
+extern "C" int lmv_debug_gemm_trace(unsigned long long* host, int n) {
+  static unsigned long long zero[148 * 10 * 8];
+  if (n > 148 * 10 * 8) n = 148 * 10 * 8;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(host, lmv::g_gemm_trace, sizeof(unsigned long long) * n) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(lmv::g_gemm_trace, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif

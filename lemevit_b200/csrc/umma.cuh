@@ -211,6 +211,12 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // registers -> TMEM (32x32b, 16 columns)
@@ -247,10 +253,9 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float xc = fminf(fmaxf(x, -8.f), 8.f);   // keeps the odd polynomial monotone; gelu(|x| > 8) = x or 0 to 1e-15
-  const float x2 = xc * xc;
+  const float x2 = fminf(x * x, 64.f);   // keeps the odd polynomial monotone; |x| > 8: the argument stays > 13.8 -> tanh = +-1
   const float p = fmaf(x2, fmaf(x2, -0.00035151678863588117f, 0.037005646022512585f), 0.7975078842853727f);
-  const float t = tanh_approx(xc * p);
+  const float t = tanh_approx(x * p);
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
