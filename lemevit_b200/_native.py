@@ -93,7 +93,12 @@ def load() -> C.CDLL:
     with _lock:
         if _lib is None:
             path = _build.LIB
-            if not os.path.isfile(path) or (os.environ.get("LEMEVIT_B200_REBUILD") == "1"):
+            override = os.environ.get("LEMEVIT_B200_LIB")   # debug builds (e.g. the GEMM cycle-trace build) by explicit path
+            if override:
+                if not os.path.isfile(override):
+                    raise RuntimeError(f"LEMEVIT_B200_LIB={override} does not exist")
+                path = override
+            elif not os.path.isfile(path) or (os.environ.get("LEMEVIT_B200_REBUILD") == "1"):
                 path = _build.build(force=True)
             else:
                 try:

@@ -34,22 +34,26 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None) -> str:
+    if out is not None:
+        force = True
+    lib_path = out or LIB
     if not force and not _stale():
         return LIB
     cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += os.environ.get("LMV_NVCC_EXTRA", "").split()   # debug builds, e.g. -DLMV_GEMM_TRACE (tools/gemm_trace.py)
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", lib_path + ".tmp"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    os.replace(LIB + ".tmp", LIB)
+    os.replace(lib_path + ".tmp", lib_path)
     if verbose:
         print(proc.stderr)
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out[0] if _out else None))

@@ -243,6 +243,9 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool f_gelu = EPI < 0 ? (p.act == 1) : ((EPI & kEpiGelu) != 0);
     const bool f_res = EPI < 0 ? (p.residual != nullptr) : ((EPI & kEpiRes) != 0);
     const bool f_stats = EPI < 0 ? (p.stats_out != nullptr) : ((EPI & kEpiStats) != 0);
+    constexpr bool kPackedMath = EPI >= 0 && (EPI & kEpiGelu) != 0;
+    // the residual + statistics variant has no registers to spare for a second accumulator chunk in flight
+    constexpr bool kPipelineLd = !(EPI >= 0 && (EPI & kEpiRes) != 0 && (EPI & kEpiStats) != 0);
     const bool vec_ok = (p.ldc % 8 == 0);
     const bool fast_ok = vec_ok && !p.out_fp32;
     float* stg = reinterpret_cast<float*>(smem + 1024 + (size_t)(warp - 2) * kStageF32);
@@ -284,8 +287,8 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int rr = m_blk * BM + q * 32 + it * 8 + lr;
         rok_t[it] = rr < p.M;
         orow_t[it] = (p.grp_rows > 0) ? (long long)(rr / p.grp_rows) * p.grp_stride + (rr % p.grp_rows) : (long long)rr;
-        lnr[it] = __shfl_sync(0xffffffffu, own_r, it * 8 + lr);
-        lnn[it] = __shfl_sync(0xffffffffu, own_n, it * 8 + lr);
+        lnr[it] = f_ln ? __shfl_sync(0xffffffffu, own_r, it * 8 + lr) : 1.f;
+        lnn[it] = f_ln ? __shfl_sync(0xffffffffu, own_n, it * 8 + lr) : 0.f;
       }
       float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
       bool waited = false, loaded = false, released = false;
@@ -345,10 +348,11 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
         {
           const int c1 = c0 + 64;
-          loaded = c1 < p.BN && n_blk * p.BN + c1 < p.N;
+          const bool more = c1 < p.BN && n_blk * p.BN + c1 < p.N;
+          loaded = kPipelineLd && more;
           if (loaded) {
             tmem_ld_x32(taddr + (uint32_t)c1, r);   // lands while this chunk goes through math and stores
-          } else {
+          } else if (!more) {
             // the accumulator stage is fully read (every lane passed its tcgen05.wait::ld before the __syncwarp): hand it back now
             tc_fence_before();
             if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
@@ -363,16 +367,29 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const float4 a = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj) ^ (rl & 7)) << 2));
           const float4 b = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj + 1) ^ (rl & 7)) << 2));
           float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          if (f_ln) {
+          if (kPackedMath) {
+            // GELU variants: LayerNorm fold + GELU on the packed fp32 pipe (fma.rn.f32x2: same rounding as the scalar path)
+            const float2 r2 = make_float2(lnr[it], lnr[it]), n2 = make_float2(lnn[it], lnn[it]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(lnr[it], o[j], fmaf(lnn[it], cs[j], bs[j]));
+            for (int j = 0; j < 4; ++j) {
+              float2 v = make_float2(o[2 * j], o[2 * j + 1]);
+              const float2 c2 = make_float2(cs[2 * j], cs[2 * j + 1]), b2 = make_float2(bs[2 * j], bs[2 * j + 1]);
+              v = f_ln ? ffma2(r2, v, ffma2(n2, c2, b2)) : fadd2(v, b2);
+              v = gelu_fast2(v);
+              o[2 * j] = v.x; o[2 * j + 1] = v.y;
+            }
           } else {
+            if (f_ln) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] += bs[j];
-          }
-          if (f_gelu) {
+              for (int j = 0; j < 8; ++j) o[j] = fmaf(lnr[it], o[j], fmaf(lnn[it], cs[j], bs[j]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = gelu_fast(o[j]);
+              for (int j = 0; j < 8; ++j) o[j] += bs[j];
+            }
+            if (f_gelu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o[j] = gelu_fast(o[j]);
+            }
           }
           if (f_res) {
             const float2 r0 = unpack_bf16x2(res[it].x), r1 = unpack_bf16x2(res[it].y), r2 = unpack_bf16x2(res[it].z),

@@ -54,6 +54,11 @@ def run(name, M, N, K, ln=False, gelu=False, res=False, stats=False):
 
 
 if __name__ == "__main__":
+    if "--short" in sys.argv:
+        run("plain 54272x1536x384", 54272, 1536, 384)
+        run("qkv  ln", 54272, 1152, 384, ln=True)
+        run("fc1  ln+gelu", 54272, 1536, 384, ln=True, gelu=True)
+        sys.exit(0)
     run("fc1  ln+gelu", 54272, 1536, 384, ln=True, gelu=True)
     run("qkv  ln", 54272, 1152, 384, ln=True)
     run("proj res+stats", 54272, 384, 384, res=True, stats=True)
