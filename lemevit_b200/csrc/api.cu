@@ -344,11 +344,15 @@ static void ws_layout(const lmv_config& c, const Geo& g, int B, WsLayout* L) {
   for (int i = 0; i < c.num_stages; ++i) rows_max = std::max(rows_max, (size_t)B * g.T[i]);
   L->stats1 = take(rows_max * 4);    // [rows][1][2] fp32 (take() counts 2-byte elements)
   L->stats2 = take(rows_max * 16);   // [rows][parts <= 4][2] fp32
-  // split-softmax partials of the meta-token attention (attention_meta.cu): per C/D stage B x ceil(N/128) x heads*M rows
+  // split-softmax partials of the meta-token attention (attention_meta.cu): a few partial rows per image and (head, query)
   size_t cpart = 0;
   for (int i = 0; i < c.num_stages; ++i)
     if (c.attn_type[i] != 'S')
-      cpart = std::max(cpart, (size_t)B * ((g.N[i] + 127) / 128) * (c.embed_dim[i] / c.head_dim) * M * (32 * 4 + 8));
+    {
+      AttnArgs ma{};
+      ma.B = B; ma.heads = c.embed_dim[i] / c.head_dim; ma.Lq = M; ma.Lk = g.N[i];
+      cpart = std::max(cpart, attention_meta_workspace(ma));
+    }
   for (int i = 0; i < c.num_stages; ++i)
     if (c.attn_type[i] == 'S') cpart = std::max(cpart, attention_self_workspace(B, c.embed_dim[i] / c.head_dim, g.T[i]));
   L->cpart_bytes = cpart;

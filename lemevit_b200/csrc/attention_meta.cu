@@ -3,21 +3,27 @@
 //   CrossAttention        (models/lemevit.py:477-486, stage 0):  c <- softmax(q(c) k(x)^T / sqrt(32)) v(x)
 //   DualCrossAttention    (models/lemevit.py:300-302, stages 1-2): dc = softmax(q2 k1^T * C^-0.5) v1
 // FlashAttention-style kernels waste >75 % of their tiles on 16 query rows; here the roles are arranged so that
-// the tcgen05 M dimension is filled by (head, query) pairs and the N/K dimensions by image tokens.
+// the tcgen05 M dimension is filled by (head, query) pairs and the N/K dimensions by image tokens.  The op is
+// HBM-bound (K and V are read once, 2 * N * C bf16 per image), so the kernel is a persistent stream over token tiles.
 //
-// sm_100a design, split-N: one CTA per (image, 128-token tile):
+// sm_100a design: one persistent CTA per SM walks a contiguous range of (image, 128-token tile) items:
+//   * warp 4 (one thread) is the control thread: TMA loads of the K / V tiles [128 tokens x C] straight out of the packed
+//     kv / qkv activation (64B swizzle, 32-channel boxes, rows past the end of the image zero-filled) into a 1-2 deep
+//     ring, and both MMAs of every tile;
 //   * Q is expanded in shared memory to a block-diagonal operand Qbd[(h, j), C] (row (h, j) holds q_j restricted to the
 //     32 channels of head h), so ONE accumulation over the full channel dim gives every head's scores:
 //         S[(h, j), n] = sum_c Qbd[(h, j), c] K[n, c]                tcgen05.mma M=128, N=128, K=C   (A, B K-major, SW64)
-//   * K and V tiles [128 tokens x C] arrive by TMA straight out of the packed kv / qkv activation (64B swizzle, 32-channel
-//     boxes; rows past the end of the image are zero-filled by TMA and masked in the softmax);
-//   * softmax over the tile's tokens is thread-local (thread r owns TMEM lane r = row (h, j)); P (bf16) goes to a 128B
+//     S is double-buffered in TMEM so the scores of tile i+1 are computed while tile i is in its softmax;
+//   * warps 0-3 do the softmax, thread r owning TMEM lane r = row (h, j).  With heads * Lq <= 64 the rows are duplicated
+//     at lanes 64.. and each copy takes half of the tile's tokens, so all four warps work;  P (bf16) goes to a 128B
 //     swizzled K-major smem tile;
 //   * O[(h, j), c] = sum_n P[(h, j), n] V[n, c]                      tcgen05.mma M=128, N=32 per head chunk, K=128 tokens
-//     (B = V as loaded: MN-major);
-//   * per tile the kernel emits the split-softmax partial (m, l, O[32]) of every (h, j); a small second kernel merges
-//     the partials of all tiles of an image (fixed order, deterministic) and writes merged-heads bf16 output.
-// The same partial structure is what a fully fused DualCrossAttention block kernel emits for its meta-token branch.
+//     (B = V as loaded: MN-major); each thread folds its row of O into a running (m, l, O[32]) in registers;
+//   * an image's tiles are cut into fixed segments (a function of N only); at the end of a segment the running state is
+//     written as one split-softmax partial and a small second kernel merges the segments x copies partials of an image
+//     in a fixed order, so every output bit is independent of batch size, batch position and SM count.
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "kernels.h"
@@ -28,23 +34,37 @@ namespace lmv {
 namespace {
 
 constexpr int kD = 32;
-constexpr int kTile = 128;      // image tokens per CTA
-constexpr int kThreads = 128;
+constexpr int kTile = 128;        // image tokens per item
+constexpr int kThreads = 160;     // 4 softmax warps + 1 control warp
+constexpr int kChunkBytes = kTile * kD * 2;   // [128 rows x 32 ch] bf16 = 8 KB
+constexpr int kTmemS = 0, kTmemO = 2 * kTile; // S[2]: columns [0, 256), O: [256, 256 + C)
 
 struct MetaParams {
   const bf16* q;
   long long q_bs;
   int q_rs;
-  float* part_o;     // [B][tiles][R][32]
-  float2* part_ml;   // [B][tiles][R]
-  int heads, Lq, Lk, R, C, tiles, nchunk, tmem_cols;
+  float* part_o;     // [B][parts][R][32]
+  float2* part_ml;   // [B][parts][R]
+  int heads, Lq, Lk, R, C, tiles, nchunk;
+  int dup;           // rows duplicated at lanes 64..: copy 0 takes tokens [0, 64) of a tile, copy 1 tokens [64, 128)
+  int seg_tiles, segs;         // an image's tiles are cut into `segs` segments of seg_tiles tiles: one partial per segment,
+                               // so the summation order (and every output bit) is independent of batch size and position
+  int total_tiles;             // B * tiles: CTAs take contiguous, tile-balanced runs of whole segments
+  int kst, vst;      // K / V ring depth
   float scale_log2e;
 };
 
 struct Ctrl {
-  uint64_t bar_load, bar_s, bar_o;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], s_empty[2], p_full, o_full, o_empty, q_ready;
   uint32_t tmem_base;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ uint64_t make_mnmajor_sw64_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -62,156 +82,291 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
-  const int chunk_bytes = kTile * kD * 2;                  // [128 rows x 32 ch] bf16 = 8 KB
+  const int kv_bytes = p.nchunk * kChunkBytes;
   uint8_t* sQ = smem + 1024;
-  uint8_t* sK = sQ + (size_t)p.nchunk * chunk_bytes;
-  uint8_t* sV = sK + (size_t)p.nchunk * chunk_bytes;
-  uint8_t* sP = sV + (size_t)p.nchunk * chunk_bytes;        // 2 tiles of [128 x 64] bf16, 128B swizzle
-  const int warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x, b = blockIdx.y;
-  const int n0 = tile * kTile;
-  const int valid = min(kTile, p.Lk - n0);
+  uint8_t* sK = sQ + kv_bytes;
+  uint8_t* sV = sK + (size_t)p.kst * kv_bytes;
+  uint8_t* sP = sV + (size_t)p.vst * kv_bytes;               // 2 tiles of [128 x 64] bf16, 128B swizzle
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto seg_first_tile = [&](int sidx) {   // flattened tile index at which flattened segment sidx starts
+    const int b = sidx / p.segs, sg = sidx - b * p.segs;
+    return b * p.tiles + min(sg * p.seg_tiles, p.tiles);
+  };
+  // CTA c starts at the first segment boundary at or after tile c * total / grid: whole segments, tile-balanced
+  auto cta_first_seg = [&](int c) {
+    const long long tau = (long long)c * p.total_tiles / (long long)gridDim.x;
+    const int b = (int)(tau / p.tiles), within = (int)(tau - (long long)b * p.tiles);
+    return b * p.segs + (within + p.seg_tiles - 1) / p.seg_tiles;
+  };
+  const int s_begin = cta_first_seg(blockIdx.x), s_end = cta_first_seg(blockIdx.x + 1);
+  const int t_begin = seg_first_tile(s_begin), t_end = seg_first_tile(s_end);
+  const int n = t_end - t_begin;
 
-  pdl_launch_dependents();
-  pdl_wait();   // the TMA loads below are issued right away
   if (threadIdx.x == 0) {
-    mbar_init(&ctrl->bar_load, 1);
-    mbar_init(&ctrl->bar_s, 1);
-    mbar_init(&ctrl->bar_o, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->k_full[i], 1); mbar_init(&ctrl->k_empty[i], 1);
+      mbar_init(&ctrl->v_full[i], 1); mbar_init(&ctrl->v_empty[i], 1);
+      mbar_init(&ctrl->s_full[i], 1); mbar_init(&ctrl->s_empty[i], 4);
+    }
+    mbar_init(&ctrl->p_full, 4);
+    mbar_init(&ctrl->o_full, 1);
+    mbar_init(&ctrl->o_empty, 4);
+    mbar_init(&ctrl->q_ready, 4);
     fence_mbar_init();
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_expect_tx(&ctrl->bar_load, (uint32_t)(2 * p.nchunk * chunk_bytes));
-    for (int c = 0; c < p.nchunk; ++c) {
-      tma_load_3d(sK + (size_t)c * chunk_bytes, &tmK, &ctrl->bar_load, c * kD, n0, b);
-      tma_load_3d(sV + (size_t)c * chunk_bytes, &tmV, &ctrl->bar_load, c * kD, n0, b);
-    }
   }
-  if (warp == 0) {
-    tmem_alloc(&ctrl->tmem_base, (uint32_t)p.tmem_cols);
+  if (warp == 4) {
+    tmem_alloc(&ctrl->tmem_base, 512);
     tmem_relinquish();
   }
-  // ---- block-diagonal Q operand: zero, then row (h, j) <- q[j, 32h .. 32h+31] into chunk h (64B-swizzled K-major) ----
-  {
-    const int n16 = p.nchunk * chunk_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += kThreads) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  __syncthreads();
-  const int r = threadIdx.x;                 // row (h, j) == TMEM lane
-  const int h = r / p.Lq, j = r - h * p.Lq;
-  if (r < p.R) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.q + (long long)b * p.q_bs + (long long)j * p.q_rs + h * kD);
-    uint8_t* dst = sQ + (size_t)h * chunk_bytes + (size_t)r * 64;
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst + ((ch ^ ((r >> 1) & 3)) << 4)) = __ldg(src + ch);
-  }
-  fence_proxy_async_smem();
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = ctrl->tmem_base;
-  const uint32_t tmemO = tmem + kTile;       // S: columns [0, 128), O: [128, 128 + C)
-
-  if (threadIdx.x == 0) {
-    mbar_wait(&ctrl->bar_load, 0, 30);
-    tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, kTile);
-    for (int c = 0; c < p.nchunk; ++c) {
-      const uint64_t dq = make_kmajor_desc<64>(smem_u32(sQ + (size_t)c * chunk_bytes));
-      const uint64_t dk = make_kmajor_desc<64>(smem_u32(sK + (size_t)c * chunk_bytes));
-#pragma unroll
-      for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tmem, dq + 2ull * k, dk + 2ull * k, idesc, (uint32_t)((c | k) != 0));
-    }
-    umma_commit(&ctrl->bar_s);
+  if (n <= 0) {   // (only when the grid was rounded up)
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem, 512);
+    return;
   }
-  mbar_wait(&ctrl->bar_s, 0, 31);
-  tc_fence_after();
 
-  // ---- softmax over this tile's tokens (row r) ----
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
-  float mx = -INFINITY, sum = 0.f;
-  if (warp * 32 < p.R) {                       // warp-uniform: tcgen05.ld is .sync.aligned
-    for (int c0 = 0; c0 < kTile; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(t_row + (uint32_t)c0, v);
-      tmem_ld_wait();
+  if (warp == 4) {
+    // ---------------- control thread: TMA loads + both MMAs of every tile ----------------
+    if (lane == 0) {
+      auto img = [&](int i) { return (t_begin + i) / p.tiles; };
+      auto load_kv = [&](const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int i) {
+        const int t = t_begin + i, b = t / p.tiles, n0 = (t - b * p.tiles) * kTile;
+        mbar_expect_tx(bar, (uint32_t)kv_bytes);
+        for (int c = 0; c < p.nchunk; ++c) tma_load_3d(dst + (size_t)c * kChunkBytes, tm, bar, c * kD, n0, b);
+      };
+      auto load_k = [&](int i) { load_kv(&tmK, sK + (size_t)(i % p.kst) * kv_bytes, &ctrl->k_full[i % p.kst], i); };
+      auto load_v = [&](int i) { load_kv(&tmV, sV + (size_t)(i % p.vst) * kv_bytes, &ctrl->v_full[i % p.vst], i); };
+      const uint32_t idesc_s = make_idesc_bf16(128, kTile);
+      const uint32_t idesc_o = make_idesc_bf16(128, kD) | (1u << 16);   // b_major = MN
+      auto issue_s = [&](int i) {
+        const int kb = i % p.kst;
+        mbar_wait(&ctrl->k_full[kb], (uint32_t)((i / p.kst) & 1), 30);
+        if (i >= 2) mbar_wait(&ctrl->s_empty[i & 1], (uint32_t)(((i >> 1) - 1) & 1), 31);
+        tc_fence_after();
+        const uint32_t d = tmem + (uint32_t)(kTmemS + (i & 1) * kTile);
+        for (int c = 0; c < p.nchunk; ++c) {
+          const uint64_t dq = make_kmajor_desc<64>(smem_u32(sQ + (size_t)c * kChunkBytes));
+          const uint64_t dk = make_kmajor_desc<64>(smem_u32(sK + (size_t)kb * kv_bytes + (size_t)c * kChunkBytes));
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c0 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-    }
-    const float mxs = mx * p.scale_log2e;
-    for (int c0 = 0; c0 < kTile; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_x32(t_row + (uint32_t)c0, v);
-      tmem_ld_wait();
-      uint8_t* tile_p = sP + (size_t)(c0 >> 6) * (kTile * 128) + (size_t)r * 128;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int col = c0 + g * 8 + i;
-          e[i] = (col < valid) ? exp2f(fmaf(__uint_as_float(v[g * 8 + i]), p.scale_log2e, -mxs)) : 0.f;
+          for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(d, dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)((c | k) != 0));
         }
-        uint4 u;
-        u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
-        u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
-        // the row sum must describe exactly the bf16 probabilities the tensor core multiplies
-        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-        sum += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-        const int ch = ((c0 & 63) >> 3) + g;
-        *reinterpret_cast<uint4*>(tile_p + ((ch ^ (r & 7)) << 4)) = u;
+        umma_commit(&ctrl->s_full[i & 1]);
+        umma_commit(&ctrl->k_empty[kb]);
+      };
+      for (int i = 0; i < min(p.kst, n); ++i) load_k(i);
+      for (int i = 0; i < min(p.vst, n); ++i) load_v(i);
+      mbar_wait(&ctrl->q_ready, 0, 32);   // Qbd of the first image written, P tile zeroed
+      issue_s(0);
+      for (int i = 0; i < n; ++i) {
+        if (i + p.kst < n) {   // the ring slot S(i) just read
+          mbar_wait(&ctrl->k_empty[i % p.kst], (uint32_t)((i / p.kst) & 1), 33);
+          load_k(i + p.kst);
+        }
+        // scores of the next tile while this one is in its softmax (a new image needs its Qbd first: written before p_full)
+        const bool early = (i + 1 < n) && img(i + 1) == img(i);
+        if (early) issue_s(i + 1);
+        mbar_wait(&ctrl->p_full, (uint32_t)(i & 1), 34);
+        mbar_wait(&ctrl->v_full[i % p.vst], (uint32_t)((i / p.vst) & 1), 35);
+        if (i > 0) mbar_wait(&ctrl->o_empty, (uint32_t)((i - 1) & 1), 36);
+        tc_fence_after();
+        // O[:, 32c .. 32c+31] = P V_c : A = P tiles (K-major, 128B swizzle), B = V chunk as loaded (MN-major, 64B swizzle)
+        const uint32_t pbase = smem_u32(sP);
+        for (int c = 0; c < p.nchunk; ++c) {
+          const uint32_t vbase = smem_u32(sV + (size_t)(i % p.vst) * kv_bytes + (size_t)c * kChunkBytes);
+#pragma unroll
+          for (int s = 0; s < kTile / 16; ++s) {
+            const uint64_t da = make_kmajor_desc<128>(pbase + (uint32_t)(s >> 2) * (kTile * 128)) + 2ull * (s & 3);
+            const uint64_t db = make_mnmajor_sw64_desc(vbase + (uint32_t)s * (16 * kD * 2));
+            umma_bf16_ss(tmem + (uint32_t)(kTmemO + c * kD), da, db, idesc_o, (uint32_t)(s != 0));
+          }
+        }
+        umma_commit(&ctrl->o_full);
+        umma_commit(&ctrl->v_empty[i % p.vst]);
+        if (i + p.vst < n) {
+          mbar_wait(&ctrl->v_empty[i % p.vst], (uint32_t)((i / p.vst) & 1), 37);
+          load_v(i + p.vst);
+        }
+        if (!early && i + 1 < n) issue_s(i + 1);
       }
     }
-    if (r < p.R) p.part_ml[((long long)b * p.tiles + tile) * p.R + r] = make_float2(mxs, sum);
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
+  } else {
+    // ---------------- softmax warps: thread r owns TMEM lane r ----------------
+    const int r = threadIdx.x;
+    const int rr = p.dup ? (r & 63) : r;          // logical row (h, j)
+    const int copy = p.dup ? (r >> 6) : 0;
+    const int ncopy = p.dup ? 2 : 1;
+    const bool rvalid = rr < p.R;
+    const int h = rvalid ? rr / p.Lq : 0, j = rr - h * p.Lq;
+    const int c_lo = p.dup ? copy * 64 : 0;   // first token column of a tile this thread owns (64 columns with dup, else all 128)
+    // zero Qbd and the P tile once: the block-diagonal / copy structure never changes, only the written parts do
+    {
+      const int n16 = (kv_bytes) / 16;
+      for (int i = threadIdx.x; i < n16; i += 128) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = threadIdx.x; i < 2 * kTile * 128 / 16; i += 128) reinterpret_cast<uint4*>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    auto write_q = [&](int b) {
+      if (rvalid) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + (long long)b * p.q_bs + (long long)j * p.q_rs + h * kD);
+        uint8_t* dst = sQ + (size_t)h * kChunkBytes + (size_t)r * 64;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(dst + ((ch ^ ((r >> 1) & 3)) << 4)) = __ldg(src + ch);
+      }
+      fence_proxy_async_smem();
+    };
+    auto seg_of = [&](int t) { const int b = t / p.tiles; return b * p.segs + (t - b * p.tiles) / p.seg_tiles; };
+    int seg_cur = seg_of(t_begin);
+    write_q(t_begin / p.tiles);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctrl->q_ready);
 
-  if (threadIdx.x == 0) {
-    tc_fence_after();
-    // O[:, 32c .. 32c+31] = P V_c : A = P tiles (K-major, 128B swizzle), B = V chunk as loaded (MN-major, 64B swizzle)
-    const uint32_t idesc = make_idesc_bf16(128, kD) | (1u << 16);   // b_major = MN
-    const uint32_t pbase = smem_u32(sP);
-    for (int c = 0; c < p.nchunk; ++c) {
-      const uint32_t vbase = smem_u32(sV + (size_t)c * chunk_bytes);
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const int h_lo = ((warp * 32) & (p.dup ? 63 : 127)) / p.Lq;
+    const int h_hi = min(p.heads - 1, (((warp * 32) & (p.dup ? 63 : 127)) + 31) / p.Lq);
+    float m_run = -INFINITY, l_run = 0.f, o_run[kD];
 #pragma unroll
-      for (int s = 0; s < kTile / 16; ++s) {
-        const uint64_t da = make_kmajor_desc<128>(pbase + (uint32_t)(s >> 2) * (kTile * 128)) + 2ull * (s & 3);
-        const uint64_t db = make_mnmajor_sw64_desc(vbase + (uint32_t)s * (16 * kD * 2));
-        umma_bf16_ss(tmemO + (uint32_t)(c * kD), da, db, idesc, (uint32_t)(s != 0));
+    for (int i = 0; i < kD; ++i) o_run[i] = 0.f;
+    float m_prev = -INFINITY, l_prev = 0.f;   // (max, sum) of the tile whose O is still in flight
+
+    // fold O of tile `it` (already complete in TMEM) into the running state
+    auto fold = [&](int it) {
+      mbar_wait(&ctrl->o_full, (uint32_t)(it & 1), 38);
+      tc_fence_after();
+      const float m_new = fmaxf(m_run, m_prev);
+      const float a = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+      const float w = (m_prev == -INFINITY) ? 0.f : exp2f(m_prev - m_new);
+      for (int hh = h_lo; hh <= h_hi; ++hh) {   // h differs per lane: load lane-uniform chunks and select
+        uint32_t v[32];
+        tmem_ld_x32(t_row + (uint32_t)(kTmemO + hh * kD), v);
+        tmem_ld_wait();
+        if (hh == h) {
+#pragma unroll
+          for (int i = 0; i < kD; ++i) o_run[i] = fmaf(o_run[i], a, w * __uint_as_float(v[i]));
+        }
+      }
+      l_run = fmaf(l_run, a, w * l_prev);
+      m_run = m_new;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->o_empty);
+    };
+    auto flush = [&](int sidx) {
+      if (rvalid) {
+        const long long pr = ((long long)sidx * ncopy + copy) * p.R + rr;
+        p.part_ml[pr] = make_float2(m_run, l_run);
+        float4* dst = reinterpret_cast<float4*>(p.part_o + pr * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_float4(o_run[4 * i], o_run[4 * i + 1], o_run[4 * i + 2], o_run[4 * i + 3]);
+      }
+      m_run = -INFINITY; l_run = 0.f;
+#pragma unroll
+      for (int i = 0; i < kD; ++i) o_run[i] = 0.f;
+    };
+
+    for (int i = 0; i < n; ++i) {
+      const int t = t_begin + i, b = t / p.tiles, n0 = (t - b * p.tiles) * kTile;
+      const int valid = min(kTile, p.Lk - n0);
+      mbar_wait(&ctrl->s_full[i & 1], (uint32_t)((i >> 1) & 1), 39);
+      tc_fence_after();
+      // S(i) is complete, so every MMA that reads the current Qbd has retired: stage the next image's queries now
+      if (i + 1 < n && (t + 1) / p.tiles != b) write_q((t + 1) / p.tiles);
+      const uint32_t s_row = t_row + (uint32_t)(kTmemS + (i & 1) * kTile + c_lo);
+      const bool full = valid == kTile;   // every column is a real token: no masking
+      auto tile_max = [&](const uint32_t (&v)[32], int col0, float mx) {
+        if (full) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (col0 + k < valid) mx = fmaxf(mx, __uint_as_float(v[k]));
+        }
+        return mx;
+      };
+      float sum = 0.f, mxs;
+      // probabilities of one 32-column block -> P tile (bf16); the row sum adds exactly the values the tensor core multiplies
+      auto emit = [&](const uint32_t (&v)[32], int col0) {
+        uint8_t* tile_p = sP + (size_t)(col0 >> 6) * (kTile * 128) + (size_t)r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float e[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float x = ex2_approx(fmaf(__uint_as_float(v[g * 8 + k]), p.scale_log2e, -mxs));
+            e[k] = (full || col0 + g * 8 + k < valid) ? x : 0.f;
+          }
+          uint4 u;
+          u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
+          u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
+          const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+          sum += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+          const int ch = ((col0 & 63) >> 3) + g;
+          if (rvalid) *reinterpret_cast<uint4*>(tile_p + ((ch ^ (r & 7)) << 4)) = u;
+        }
+      };
+      // the previous tile's O must be folded before P (single buffer) is overwritten
+      auto fold_prev = [&]() {
+        if (i > 0) {
+          fold(i - 1);
+          if (seg_of(t) != seg_cur) { flush(seg_cur); seg_cur = seg_of(t); }
+        }
+      };
+      if (p.dup) {
+        // 64 columns per thread: the scores stay in registers between the maximum and the exponentials
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(s_row, va);
+        tmem_ld_x32(s_row + 32u, vb);
+        tmem_ld_wait();
+        const float mx = tile_max(vb, c_lo + 32, tile_max(va, c_lo, -INFINITY));
+        mxs = mx * p.scale_log2e;   // -inf when none of this thread's columns is a real token (then every e is masked to 0)
+        fold_prev();
+        emit(va, c_lo);
+        emit(vb, c_lo + 32);
+      } else {
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < kTile; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(s_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          mx = tile_max(v, c0, mx);
+        }
+        mxs = mx * p.scale_log2e;
+        fold_prev();
+        for (int c0 = 0; c0 < kTile; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_x32(s_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          emit(v, c0);
+        }
+      }
+      m_prev = mxs; l_prev = sum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&ctrl->s_empty[i & 1]);
+        mbar_arrive(&ctrl->p_full);
       }
     }
-    umma_commit(&ctrl->bar_o);
-  }
-  mbar_wait(&ctrl->bar_o, 0, 32);
-  tc_fence_after();
-  if (warp * 32 < p.R) {
-    // row (h, j) only needs its own head's 32 channels; h differs per lane, so load lane-uniform chunks and select
-    const int h_lo = (warp * 32) / p.Lq, h_hi = min(p.heads - 1, (warp * 32 + 31) / p.Lq);
-    float* dst = p.part_o + (((long long)b * p.tiles + tile) * p.R + r) * kD;
-    for (int hh = h_lo; hh <= h_hi; ++hh) {
-      uint32_t v[32];
-      tmem_ld_x32(t_row + (uint32_t)(kTile + hh * kD), v);
-      tmem_ld_wait();
-      if (r < p.R && hh == h) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                          __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-      }
-    }
+    fold(n - 1);
+    flush(seg_cur);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
-// merge the per-tile partials of one (image, head, query) row: one warp per row, lane = channel
+// merge the partials of one (image, head, query) row: one warp per row, lane = channel
 __global__ void __launch_bounds__(256)
 attention_meta_merge_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, bf16* __restrict__ out,
-                            long long o_bs, int o_rs, int B, int tiles, int R, int Lq) {
+                            long long o_bs, int o_rs, int B, int parts, int R, int Lq) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,13 +374,14 @@ attention_meta_merge_kernel(const float* __restrict__ part_o, const float2* __re
   if (idx >= (long long)B * R) return;
   const int b = (int)(idx / R), r = (int)(idx % R);
   const int h = r / Lq, j = r - h * Lq;
+  const long long base = (long long)b * parts;   // segments x copies partial rows per image, merged in a fixed order
   float m = -INFINITY;
-  for (int t = 0; t < tiles; ++t) m = fmaxf(m, part_ml[((long long)b * tiles + t) * R + r].x);
+  for (int t = 0; t < parts; ++t) m = fmaxf(m, part_ml[(base + t) * R + r].x);
   float l = 0.f, o = 0.f;
-  for (int t = 0; t < tiles; ++t) {
-    const long long pr = ((long long)b * tiles + t) * R + r;
+  for (int t = 0; t < parts; ++t) {
+    const long long pr = (base + t) * R + r;
     const float2 ml = part_ml[pr];
-    const float w = exp2f(ml.x - m);
+    const float w = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - m);
     l = fmaf(ml.y, w, l);
     o = fmaf(part_o[pr * kD + lane], w, o);
   }
@@ -235,7 +391,27 @@ attention_meta_merge_kernel(const float* __restrict__ part_o, const float2* __re
 std::once_flag g_once;
 cudaError_t g_attr = cudaSuccess;
 
-int smem_bytes_for(int nchunk) { return 2048 + 3 * nchunk * kTile * kD * 2 + 2 * kTile * 128; }
+struct MetaShape {
+  int nchunk, kst, vst, dup, tiles, seg_tiles, segs, grid, ncopy, smem;
+};
+
+MetaShape shape_for(const AttnArgs& a) {
+  MetaShape s;
+  s.nchunk = a.heads;
+  s.dup = (a.heads * a.Lq <= 64) ? 1 : 0;
+  s.ncopy = s.dup ? 2 : 1;
+  // Q + K ring + V ring + P (32 KB) + control/alignment (2 KB) within 227 KB
+  const int kv = s.nchunk * kChunkBytes, budget = 227 * 1024 - 2048 - 2 * kTile * 128 - kv;
+  s.kst = (budget >= 3 * kv) ? 2 : 1;
+  s.vst = (budget >= 4 * kv) ? 2 : 1;
+  s.smem = 2048 + kv * (1 + s.kst + s.vst) + 2 * kTile * 128;
+  s.tiles = (a.Lk + kTile - 1) / kTile;
+  static const int seg_env = [] { const char* e = getenv("LMV_META_SEG"); return e ? atoi(e) : 0; }();
+  s.seg_tiles = seg_env > 0 ? seg_env : (s.tiles >= 12 ? 6 : (s.tiles >= 6 ? 3 : 1));   // a function of Lk only (never of B): see MetaParams::seg_tiles
+  s.segs = (s.tiles + s.seg_tiles - 1) / s.seg_tiles;
+  s.grid = std::min(a.B * s.segs, device_sm_count());
+  return s;
+}
 
 }  // namespace
 
@@ -244,12 +420,13 @@ bool attention_meta_supported(const AttnArgs& a) {
   const int C = a.heads * kD;
   return a.Lq >= 1 && a.heads * a.Lq <= 128 && C <= 256 && a.Lk >= 1 && a.B >= 1 && al16(a.q) && al16(a.k) && al16(a.v) &&
          a.q_rs % 8 == 0 && a.q_bs % 8 == 0 && a.k_rs % 8 == 0 && a.v_rs % 8 == 0 && a.k_bs % 8 == 0 && a.v_bs % 8 == 0 &&
-         a.k_rs >= C && a.v_rs >= C && smem_bytes_for(a.heads) <= 227 * 1024;
+         a.k_rs >= C && a.v_rs >= C && (long long)a.B * ((a.Lk + kTile - 1) / kTile) < (1ll << 28) &&
+         shape_for(a).smem <= 227 * 1024;
 }
 
 size_t attention_meta_workspace(const AttnArgs& a) {
-  const size_t tiles = (a.Lk + kTile - 1) / kTile, R = (size_t)a.heads * a.Lq;
-  return (size_t)a.B * tiles * R * (kD * sizeof(float) + sizeof(float2));
+  const MetaShape s = shape_for(a);
+  return (size_t)a.B * s.segs * s.ncopy * ((size_t)a.heads * a.Lq) * (kD * sizeof(float) + sizeof(float2));
 }
 
 int attention_meta_run(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s) {
@@ -260,15 +437,14 @@ int attention_meta_run(const AttnArgs& a, void* workspace, size_t workspace_byte
     g_attr = cudaFuncSetAttribute(attention_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   LMV_CUDA_OK(g_attr);
+  const MetaShape sh = shape_for(a);
   MetaParams p;
   p.q = a.q; p.q_bs = a.q_bs; p.q_rs = a.q_rs;
   p.heads = a.heads; p.Lq = a.Lq; p.Lk = a.Lk; p.R = a.heads * a.Lq; p.C = a.heads * kD;
-  p.tiles = (a.Lk + kTile - 1) / kTile;
-  p.nchunk = a.heads;
-  const int need_cols = kTile + p.C;
-  p.tmem_cols = need_cols <= 256 ? 256 : 512;
+  p.tiles = sh.tiles; p.nchunk = sh.nchunk; p.dup = sh.dup;
+  p.seg_tiles = sh.seg_tiles; p.segs = sh.segs; p.total_tiles = a.B * sh.tiles; p.kst = sh.kst; p.vst = sh.vst;
   p.scale_log2e = a.scale * 1.4426950408889634f;
-  const size_t rows = (size_t)a.B * p.tiles * p.R;
+  const size_t rows = (size_t)a.B * sh.segs * sh.ncopy * p.R;
   p.part_o = static_cast<float*>(workspace);
   p.part_ml = reinterpret_cast<float2*>(p.part_o + rows * kD);
   CUtensorMap tk, tv;
@@ -281,11 +457,10 @@ int attention_meta_run(const AttnArgs& a, void* workspace, size_t workspace_byte
   int rc;
   if ((rc = enc(&tk, a.k, a.k_bs, a.k_rs))) return rc;
   if ((rc = enc(&tv, a.v, a.v_bs, a.v_rs))) return rc;
-  dim3 grid(p.tiles, a.B);
-  LMV_CUDA_OK(launch_kernel(attention_meta_kernel, dim3(grid), dim3(kThreads), (size_t)(smem_bytes_for(p.nchunk)), s, tk, tv, p));
+  LMV_CUDA_OK(launch_kernel(attention_meta_kernel, dim3(sh.grid), dim3(kThreads), (size_t)(sh.smem), s, tk, tv, p));
   LMV_CUDA_OK(cudaGetLastError());
   const long long mrows = (long long)a.B * p.R;
-  LMV_CUDA_OK(launch_kernel(attention_meta_merge_kernel, dim3((unsigned)((mrows + 7) / 8)), dim3(256), (size_t)(0), s, p.part_o, p.part_ml, a.out, a.o_bs, a.o_rs, a.B, p.tiles, p.R, a.Lq));
+  LMV_CUDA_OK(launch_kernel(attention_meta_merge_kernel, dim3((unsigned)((mrows + 7) / 8)), dim3(256), (size_t)(0), s, p.part_o, p.part_ml, a.out, a.o_bs, a.o_rs, a.B, sh.segs * sh.ncopy, p.R, a.Lq));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

@@ -243,7 +243,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool f_gelu = EPI < 0 ? (p.act == 1) : ((EPI & kEpiGelu) != 0);
     const bool f_res = EPI < 0 ? (p.residual != nullptr) : ((EPI & kEpiRes) != 0);
     const bool f_stats = EPI < 0 ? (p.stats_out != nullptr) : ((EPI & kEpiStats) != 0);
-    constexpr bool kPackedMath = EPI >= 0 && (EPI & kEpiGelu) != 0;
+    constexpr bool kPackedMath = EPI >= 0;
     // the residual + statistics variant has no registers to spare for a second accumulator chunk in flight
     constexpr bool kPipelineLd = !(EPI >= 0 && (EPI & kEpiRes) != 0 && (EPI & kEpiStats) != 0);
     const bool vec_ok = (p.ldc % 8 == 0);
@@ -368,14 +368,17 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const float4 b = *reinterpret_cast<const float4*>(stg + rl * 32 + (((cj + 1) ^ (rl & 7)) << 2));
           float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
           if (kPackedMath) {
-            // GELU variants: LayerNorm fold + GELU on the packed fp32 pipe (fma.rn.f32x2: same rounding as the scalar path)
+            // compile-time variants: LayerNorm fold, GELU and residual add on the packed fp32 pipe (fma.rn.f32x2 / add.rn.f32x2
+            // round like the scalar instructions, so both paths give the same bits)
             const float2 r2 = make_float2(lnr[it], lnr[it]), n2 = make_float2(lnn[it], lnn[it]);
+            const uint32_t rw[4] = {f_res ? res[it].x : 0u, f_res ? res[it].y : 0u, f_res ? res[it].z : 0u, f_res ? res[it].w : 0u};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 v = make_float2(o[2 * j], o[2 * j + 1]);
               const float2 c2 = make_float2(cs[2 * j], cs[2 * j + 1]), b2 = make_float2(bs[2 * j], bs[2 * j + 1]);
               v = f_ln ? ffma2(r2, v, ffma2(n2, c2, b2)) : fadd2(v, b2);
-              v = gelu_fast2(v);
+              if (f_gelu) v = gelu_fast2(v);
+              if (f_res) v = fadd2(v, unpack_bf16x2(rw[j]));
               o[2 * j] = v.x; o[2 * j + 1] = v.y;
             }
           } else {
@@ -391,7 +394,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
               for (int j = 0; j < 8; ++j) o[j] = gelu_fast(o[j]);
             }
           }
-          if (f_res) {
+          if (f_res && !kPackedMath) {
             const float2 r0 = unpack_bf16x2(res[it].x), r1 = unpack_bf16x2(res[it].y), r2 = unpack_bf16x2(res[it].z),
                          r3 = unpack_bf16x2(res[it].w);
             o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y; o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
