@@ -135,51 +135,69 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
   if (warp == 4) {
     // ---------------- control thread: TMA loads + both MMAs of every tile ----------------
     if (lane == 0) {
-      auto img = [&](int i) { return (t_begin + i) / p.tiles; };
-      auto load_kv = [&](const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int i) {
-        const int t = t_begin + i, b = t / p.tiles, n0 = (t - b * p.tiles) * kTile;
+      // (image, tile) cursors advance by one tile at a time: no divisions in the loops; ring depths are 1 or 2
+      struct Cur { int b, tile; };
+      const int b0 = t_begin / p.tiles;
+      const Cur c0 = {b0, t_begin - b0 * p.tiles};
+      auto step = [&](Cur& c) { if (++c.tile == p.tiles) { c.tile = 0; ++c.b; } };
+      const int ksh = p.kst - 1, vsh = p.vst - 1;   // slot = i & sh, use count = i >> sh
+      Cur ck = c0, cv = c0, cs = c0, ci = c0;       // next K load, next V load, next S issue, tile i
+      auto load_kv = [&](const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, Cur& c) {
         mbar_expect_tx(bar, (uint32_t)kv_bytes);
-        for (int c = 0; c < p.nchunk; ++c) tma_load_3d(dst + (size_t)c * kChunkBytes, tm, bar, c * kD, n0, b);
+#pragma unroll 1
+        for (int ch = 0; ch < p.nchunk; ++ch) tma_load_3d(dst + (size_t)ch * kChunkBytes, tm, bar, ch * kD, c.tile * kTile, c.b);
+        step(c);
       };
-      auto load_k = [&](int i) { load_kv(&tmK, sK + (size_t)(i % p.kst) * kv_bytes, &ctrl->k_full[i % p.kst], i); };
-      auto load_v = [&](int i) { load_kv(&tmV, sV + (size_t)(i % p.vst) * kv_bytes, &ctrl->v_full[i % p.vst], i); };
+      auto load_k = [&](int i) { load_kv(&tmK, sK + (size_t)(i & ksh) * kv_bytes, &ctrl->k_full[i & ksh], ck); };
+      auto load_v = [&](int i) { load_kv(&tmV, sV + (size_t)(i & vsh) * kv_bytes, &ctrl->v_full[i & vsh], cv); };
       const uint32_t idesc_s = make_idesc_bf16(128, kTile);
       const uint32_t idesc_o = make_idesc_bf16(128, kD) | (1u << 16);   // b_major = MN
-      auto issue_s = [&](int i) {
-        const int kb = i % p.kst;
-        mbar_wait(&ctrl->k_full[kb], (uint32_t)((i / p.kst) & 1), 30);
-        if (i >= 2) mbar_wait(&ctrl->s_empty[i & 1], (uint32_t)(((i >> 1) - 1) & 1), 31);
-        tc_fence_after();
-        const uint32_t d = tmem + (uint32_t)(kTmemS + (i & 1) * kTile);
-        for (int c = 0; c < p.nchunk; ++c) {
-          const uint64_t dq = make_kmajor_desc<64>(smem_u32(sQ + (size_t)c * kChunkBytes));
-          const uint64_t dk = make_kmajor_desc<64>(smem_u32(sK + (size_t)kb * kv_bytes + (size_t)c * kChunkBytes));
-#pragma unroll
-          for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(d, dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)((c | k) != 0));
-        }
-        umma_commit(&ctrl->s_full[i & 1]);
-        umma_commit(&ctrl->k_empty[kb]);
-      };
-      for (int i = 0; i < min(p.kst, n); ++i) load_k(i);
+      int k_next = 0;                       // next K tile to request
+      for (; k_next < min(p.kst, n); ++k_next) load_k(k_next);
       for (int i = 0; i < min(p.vst, n); ++i) load_v(i);
-      mbar_wait(&ctrl->q_ready, 0, 32);   // Qbd of the first image written, P tile zeroed
-      issue_s(0);
+      mbar_wait_lean(&ctrl->q_ready, 0);   // Qbd of the first image written, P tile zeroed
+      int s_next = 0;                       // next tile whose scores have not been issued
       for (int i = 0; i < n; ++i) {
-        if (i + p.kst < n) {   // the ring slot S(i) just read
-          mbar_wait(&ctrl->k_empty[i % p.kst], (uint32_t)((i / p.kst) & 1), 33);
-          load_k(i + p.kst);
+        // refill the K ring slots whose scores were issued in an earlier trip (their MMAs retired long ago)
+#pragma unroll 1
+        while (k_next < n && k_next - p.kst < s_next) {
+          const int js = k_next - p.kst;
+          mbar_wait_lean(&ctrl->k_empty[js & ksh], (uint32_t)((js >> ksh) & 1));
+          load_k(k_next++);
         }
-        // scores of the next tile while this one is in its softmax (a new image needs its Qbd first: written before p_full)
-        const bool early = (i + 1 < n) && img(i + 1) == img(i);
-        if (early) issue_s(i + 1);
-        mbar_wait(&ctrl->p_full, (uint32_t)(i & 1), 34);
-        mbar_wait(&ctrl->v_full[i % p.vst], (uint32_t)((i / p.vst) & 1), 35);
-        if (i > 0) mbar_wait(&ctrl->o_empty, (uint32_t)((i - 1) & 1), 36);
+        // scores: S(i) if still missing, and S(i+1) while tile i is in its softmax — unless it belongs to a new image,
+        // whose Qbd is only staged before p_full(i) (single issue site: the loop body exists once in the instruction stream)
+#pragma unroll 1
+        while (s_next < n && (s_next == i || (s_next == i + 1 && cs.b == ci.b))) {
+          const int js = s_next++, kb = js & ksh;
+          step(cs);
+          while (k_next <= js) {   // single-slot ring only: K(js) can be requested once S(js - 1), issued just now, has retired
+            const int jp = k_next - p.kst;
+            if (jp >= 0) mbar_wait_lean(&ctrl->k_empty[jp & ksh], (uint32_t)((jp >> ksh) & 1));
+            load_k(k_next++);
+          }
+          mbar_wait_lean(&ctrl->k_full[kb], (uint32_t)((js >> ksh) & 1));
+          if (js >= 2) mbar_wait_lean(&ctrl->s_empty[js & 1], (uint32_t)(((js >> 1) - 1) & 1));
+          tc_fence_after();
+          const uint32_t d = tmem + (uint32_t)(kTmemS + (js & 1) * kTile);
+#pragma unroll 1
+          for (int c = 0; c < p.nchunk; ++c) {
+            const uint64_t dq = make_kmajor_desc<64>(smem_u32(sQ + (size_t)c * kChunkBytes));
+            const uint64_t dk = make_kmajor_desc<64>(smem_u32(sK + (size_t)kb * kv_bytes + (size_t)c * kChunkBytes));
+#pragma unroll
+            for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(d, dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)((c | k) != 0));
+          }
+          umma_commit(&ctrl->s_full[js & 1]);
+          umma_commit(&ctrl->k_empty[kb]);
+        }
+        mbar_wait_lean(&ctrl->p_full, (uint32_t)(i & 1));
+        mbar_wait_lean(&ctrl->v_full[i & vsh], (uint32_t)((i >> vsh) & 1));
+        if (i > 0) mbar_wait_lean(&ctrl->o_empty, (uint32_t)((i - 1) & 1));
         tc_fence_after();
         // O[:, 32c .. 32c+31] = P V_c : A = P tiles (K-major, 128B swizzle), B = V chunk as loaded (MN-major, 64B swizzle)
         const uint32_t pbase = smem_u32(sP);
         for (int c = 0; c < p.nchunk; ++c) {
-          const uint32_t vbase = smem_u32(sV + (size_t)(i % p.vst) * kv_bytes + (size_t)c * kChunkBytes);
+          const uint32_t vbase = smem_u32(sV + (size_t)(i & vsh) * kv_bytes + (size_t)c * kChunkBytes);
 #pragma unroll
           for (int s = 0; s < kTile / 16; ++s) {
             const uint64_t da = make_kmajor_desc<128>(pbase + (uint32_t)(s >> 2) * (kTile * 128)) + 2ull * (s & 3);
@@ -188,12 +206,12 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
           }
         }
         umma_commit(&ctrl->o_full);
-        umma_commit(&ctrl->v_empty[i % p.vst]);
+        umma_commit(&ctrl->v_empty[i & vsh]);
         if (i + p.vst < n) {
-          mbar_wait(&ctrl->v_empty[i % p.vst], (uint32_t)((i / p.vst) & 1), 37);
+          mbar_wait_lean(&ctrl->v_empty[i & vsh], (uint32_t)((i >> vsh) & 1));
           load_v(i + p.vst);
         }
-        if (!early && i + 1 < n) issue_s(i + 1);
+        step(ci);
       }
     }
   } else {
@@ -204,7 +222,7 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
     const int ncopy = p.dup ? 2 : 1;
     const bool rvalid = rr < p.R;
     const int h = rvalid ? rr / p.Lq : 0, j = rr - h * p.Lq;
-    const int c_lo = p.dup ? copy * 64 : 0;   // first token column of a tile this thread owns (64 columns with dup, else all 128)
+    const int c_lo = p.dup ? copy * 64 : 0, c_n = p.dup ? 64 : 128;   // token columns of a tile this thread owns
     // zero Qbd and the P tile once: the block-diagonal / copy structure never changes, only the written parts do
     {
       const int n16 = (kv_bytes) / 16;
@@ -221,9 +239,11 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
       }
       fence_proxy_async_smem();
     };
-    auto seg_of = [&](int t) { const int b = t / p.tiles; return b * p.segs + (t - b * p.tiles) / p.seg_tiles; };
-    int seg_cur = seg_of(t_begin);
-    write_q(t_begin / p.tiles);
+    // cursor of tile i: image, tile in the image, segment id, tiles left in the segment (advanced once per trip, no divisions)
+    int cb = t_begin / p.tiles, ctile = t_begin - cb * p.tiles;
+    int seg_cur = cb * p.segs + ctile / p.seg_tiles;        // segment the running state belongs to
+    int seg_i = seg_cur, seg_pos = ctile % p.seg_tiles;     // segment of tile i and its position inside it
+    write_q(cb);
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctrl->q_ready);
 
@@ -237,7 +257,7 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
 
     // fold O of tile `it` (already complete in TMEM) into the running state
     auto fold = [&](int it) {
-      mbar_wait(&ctrl->o_full, (uint32_t)(it & 1), 38);
+      mbar_wait_lean(&ctrl->o_full, (uint32_t)(it & 1));
       tc_fence_after();
       const float m_new = fmaxf(m_run, m_prev);
       const float a = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
@@ -270,38 +290,59 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
       for (int i = 0; i < kD; ++i) o_run[i] = 0.f;
     };
 
-    for (int i = 0; i < n; ++i) {
-      const int t = t_begin + i, b = t / p.tiles, n0 = (t - b * p.tiles) * kTile;
-      const int valid = min(kTile, p.Lk - n0);
-      mbar_wait(&ctrl->s_full[i & 1], (uint32_t)((i >> 1) & 1), 39);
-      tc_fence_after();
-      // S(i) is complete, so every MMA that reads the current Qbd has retired: stage the next image's queries now
-      if (i + 1 < n && (t + 1) / p.tiles != b) write_q((t + 1) / p.tiles);
+    // One extra trip (i == n) folds and flushes the last tile, so fold / flush / the 32-column block bodies exist once in
+    // the instruction stream: the five warps of this kernel cannot hide instruction-cache misses.
+    for (int i = 0; i <= n; ++i) {
+      const bool last = (i == n);
+      const int valid = min(kTile, p.Lk - ctile * kTile);
       const uint32_t s_row = t_row + (uint32_t)(kTmemS + (i & 1) * kTile + c_lo);
-      const bool full = valid == kTile;   // every column is a real token: no masking
-      auto tile_max = [&](const uint32_t (&v)[32], int col0, float mx) {
-        if (full) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
-        } else {
+      float mx = -INFINITY;
+      // one 32-column block of scores; columns past the end of the image become -inf (-> probability 0)
+      auto load_block = [&](uint32_t (&v)[32], int c0) {
+        tmem_ld_x32(s_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int nv = valid - (c_lo + c0);
+        if (nv < 32) {
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            if (col0 + k < valid) mx = fmaxf(mx, __uint_as_float(v[k]));
+            if (k >= nv) v[k] = 0xff800000u;
         }
-        return mx;
       };
-      float sum = 0.f, mxs;
-      // probabilities of one 32-column block -> P tile (bf16); the row sum adds exactly the values the tensor core multiplies
-      auto emit = [&](const uint32_t (&v)[32], int col0) {
+      if (!last) {
+        mbar_wait_lean(&ctrl->s_full[i & 1], (uint32_t)((i >> 1) & 1));
+        tc_fence_after();
+        // S(i) is complete, so every MMA that reads the current Qbd has retired: stage the next image's queries now
+        if (i + 1 < n && ctile + 1 == p.tiles) write_q(cb + 1);
+        // ---- pass 1: tile maximum of this thread's columns ----
+#pragma unroll 1
+        for (int c0 = 0; c0 < c_n; c0 += 32) {
+          uint32_t v[32];
+          load_block(v, c0);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(v[k]));
+        }
+      }
+      // ---- previous tile: its O is needed before P (single buffer) can be overwritten ----
+      if (i > 0) {
+        fold(i - 1);
+        if (last || seg_i != seg_cur) { flush(seg_cur); seg_cur = seg_i; }
+      }
+      if (last) break;
+      // ---- pass 2: probabilities -> P tile (bf16), row sum of exactly the values the tensor core multiplies ----
+      const float mxs = mx * p.scale_log2e;
+      const float mxs_safe = (mx == -INFINITY) ? 0.f : mxs;   // no real token in this thread's columns: every p is exp2(-inf) = 0
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < c_n; c0 += 32) {
+        uint32_t v[32];
+        load_block(v, c0);
+        const int col0 = c_lo + c0;
         uint8_t* tile_p = sP + (size_t)(col0 >> 6) * (kTile * 128) + (size_t)r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float e[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float x = ex2_approx(fmaf(__uint_as_float(v[g * 8 + k]), p.scale_log2e, -mxs));
-            e[k] = (full || col0 + g * 8 + k < valid) ? x : 0.f;
-          }
+          for (int k = 0; k < 8; ++k) e[k] = ex2_approx(fmaf(__uint_as_float(v[g * 8 + k]), p.scale_log2e, -mxs_safe));
           uint4 u;
           u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
           u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
@@ -309,41 +350,6 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
           sum += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
           const int ch = ((col0 & 63) >> 3) + g;
           if (rvalid) *reinterpret_cast<uint4*>(tile_p + ((ch ^ (r & 7)) << 4)) = u;
-        }
-      };
-      // the previous tile's O must be folded before P (single buffer) is overwritten
-      auto fold_prev = [&]() {
-        if (i > 0) {
-          fold(i - 1);
-          if (seg_of(t) != seg_cur) { flush(seg_cur); seg_cur = seg_of(t); }
-        }
-      };
-      if (p.dup) {
-        // 64 columns per thread: the scores stay in registers between the maximum and the exponentials
-        uint32_t va[32], vb[32];
-        tmem_ld_x32(s_row, va);
-        tmem_ld_x32(s_row + 32u, vb);
-        tmem_ld_wait();
-        const float mx = tile_max(vb, c_lo + 32, tile_max(va, c_lo, -INFINITY));
-        mxs = mx * p.scale_log2e;   // -inf when none of this thread's columns is a real token (then every e is masked to 0)
-        fold_prev();
-        emit(va, c_lo);
-        emit(vb, c_lo + 32);
-      } else {
-        float mx = -INFINITY;
-        for (int c0 = 0; c0 < kTile; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(s_row + (uint32_t)c0, v);
-          tmem_ld_wait();
-          mx = tile_max(v, c0, mx);
-        }
-        mxs = mx * p.scale_log2e;
-        fold_prev();
-        for (int c0 = 0; c0 < kTile; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_x32(s_row + (uint32_t)c0, v);
-          tmem_ld_wait();
-          emit(v, c0);
         }
       }
       m_prev = mxs; l_prev = sum;
@@ -354,9 +360,10 @@ attention_meta_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_cons
         mbar_arrive(&ctrl->s_empty[i & 1]);
         mbar_arrive(&ctrl->p_full);
       }
+      // advance the cursor to tile i + 1
+      if (++ctile == p.tiles) { ctile = 0; ++cb; seg_pos = 0; ++seg_i; }
+      else if (++seg_pos == p.seg_tiles) { seg_pos = 0; ++seg_i; }
     }
-    fold(n - 1);
-    flush(seg_cur);
   }
   tc_fence_before();
   __syncthreads();

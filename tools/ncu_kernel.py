@@ -42,3 +42,15 @@ if kind == "posln":
         G.ok(G.lib().lmv_posembed_layernorm(G.ptr(tok), G.ptr(w9), G.ptr(db), G.ptr(out), None, G.ptr(stats), B, H, W, T, C, 1e-6, G.stream()))
     torch.cuda.synchronize()
     print("done posln")
+if kind == "attn_meta":
+    B, h, Lq, Lk = (int(v) for v in sys.argv[2:6])
+    C = h * 32
+    qc = G.bf(torch.randn(B, Lq, 3 * C, device="cuda"))
+    kvx = G.bf(torch.randn(B, Lk, 3 * C, device="cuda"))
+    q = qc[:, :, :C].unflatten(2, (h, 32))
+    k = kvx[:, :, C:2 * C].unflatten(2, (h, 32))
+    v = kvx[:, :, 2 * C:].unflatten(2, (h, 32))
+    for _ in range(3):
+        G.attention_meta(q, k, v, C ** -0.5)
+    torch.cuda.synchronize()
+    print("done attn_meta")
