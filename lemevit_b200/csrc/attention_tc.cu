@@ -7,9 +7,10 @@
 //   S = Q K^T   : tcgen05.mma M=128, N=Lkp, 2 K-steps, A/B K-major                 -> TMEM columns [0, Lkp)
 //   softmax     : thread r owns row r (TMEM lane r): two passes of tcgen05.ld, exp2 with the scale folded in,
 //                 P written as bf16 into 128B-swizzled K-major smem tiles (the A operand of the next MMA)
-//   O = P V     : tcgen05.mma M=128, N=32, Lkp/16 K-steps, A K-major (P), B MN-major (V as loaded) -> TMEM [224, 256)
+//   O = P V     : tcgen05.mma M=128, N=32, Lkp/16 K-steps, A K-major (P), B MN-major (V as loaded) -> TMEM columns [round32(Lkp), +32)
 //   epilogue    : tcgen05.ld O, 1/rowsum, bf16, 64-byte row stores into the merged-heads layout.
-// CTAs are small (<= ~100 KB smem, 256 TMEM columns) so two are resident per SM and overlap each other's phases.
+// CTAs are small (29 KB smem / 64 TMEM columns for the 16 meta-token keys, <= ~100 KB / 256 columns for 196 keys) so
+// 7-8 (resp. two) are resident per SM and overlap each other's phases.
 #include <mutex>
 
 #include "kernels.h"
@@ -22,8 +23,6 @@ namespace {
 constexpr int kD = 32;
 constexpr int kQTile = 128;
 constexpr int kMaxKeys = 224;
-constexpr int kOCol = 224;       // TMEM column of the O accumulator
-constexpr int kTmemCols = 256;
 constexpr int kThreads = 128;
 
 struct AttnTcParams {
@@ -31,6 +30,8 @@ struct AttnTcParams {
   long long o_bs;
   int o_rs;
   int Lq, Lk, Lkp;   // Lkp = Lk rounded up to 16
+  int o_col, tmem_cols;   // O accumulator at the first 32-column boundary past S; allocation = next power of two (>= 32):
+                          // 64 columns for the 16 meta-token keys, so eight CTAs fit the 512 TMEM columns of an SM
   float scale_log2e;
 };
 
@@ -41,6 +42,12 @@ struct Ctrl {
 
 // smem descriptor for an MN-major operand stored as rows of 64 bytes (32 bf16 along MN), 64B swizzle, rows = K index:
 // 8-row (8 k) atoms of 512 bytes follow each other -> stride byte offset 512; a single 32-wide MN group -> LBO unused.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint64_t make_mnmajor_sw64_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
@@ -75,7 +82,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmV);
   }
   if (warp == 0) {
-    tmem_alloc(&ctrl->tmem_base, kTmemCols);
+    tmem_alloc(&ctrl->tmem_base, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   pdl_launch_dependents();
@@ -90,7 +97,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_load_3d(sQ, &tmQ, &ctrl->bar_load, h * kD, q0, b);
     tma_load_3d(sK, &tmK, &ctrl->bar_load, h * kD, 0, b);
     tma_load_3d(sV, &tmV, &ctrl->bar_load, h * kD, 0, b);
-    mbar_wait(&ctrl->bar_load, 0, 10);
+    mbar_wait_lean(&ctrl->bar_load, 0);
     tc_fence_after();
     // S = Q K^T : both operands K-major, 64-byte rows (head_dim 32) -> 64B swizzle; 2 K-steps of 16
     const uint32_t idesc = make_idesc_bf16(kQTile, p.Lkp);
@@ -100,7 +107,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tmem, dq + 2ull * k, dk + 2ull * k, idesc, (uint32_t)(k != 0));
     umma_commit(&ctrl->bar_s);
   }
-  mbar_wait(&ctrl->bar_s, 0, 11);
+  mbar_wait_lean(&ctrl->bar_s, 0);
   tc_fence_after();
 
   // ---- softmax over the keys of row `r` ----
@@ -124,7 +131,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float e[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      e[j] = (c0 + j < p.Lk) ? exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs)) : 0.f;
+      e[j] = (c0 + j < p.Lk) ? ex2_approx(fmaf(__uint_as_float(v[j]), p.scale_log2e, -mxs)) : 0.f;
       sum += e[j];
     }
     // P[r, c0 .. c0+15] -> tile (c0 / 64), 16-byte chunks (c0 % 64) / 8 and +1, XOR-swizzled with (r % 8)
@@ -151,15 +158,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int s = 0; s < ksteps; ++s) {
       const uint64_t da = make_kmajor_desc<128>(pbase + (uint32_t)(s >> 2) * (kQTile * 128)) + 2ull * (s & 3);
       const uint64_t db = make_mnmajor_sw64_desc(vbase + (uint32_t)s * (16 * kD * 2));
-      umma_bf16_ss(tmem + kOCol, da, db, idesc, (uint32_t)(s != 0));
+      umma_bf16_ss(tmem + (uint32_t)p.o_col, da, db, idesc, (uint32_t)(s != 0));
     }
     umma_commit(&ctrl->bar_o);
   }
-  mbar_wait(&ctrl->bar_o, 0, 12);
+  mbar_wait_lean(&ctrl->bar_o, 0);
   tc_fence_after();
   {
     uint32_t v[32];
-    tmem_ld_x32(t_row + (uint32_t)kOCol, v);
+    tmem_ld_x32(t_row + (uint32_t)p.o_col, v);
     tmem_ld_wait();
     const int qrow = q0 + r;
     if (qrow < p.Lq) {
@@ -178,7 +185,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+  if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
 std::once_flag g_once;
@@ -215,6 +222,9 @@ int attention_tc_run(const AttnArgs& a, cudaStream_t s) {
   if ((rc = enc(&tv, a.v, a.v_bs, a.v_rs, a.Lk, Lkp))) return rc;
   AttnTcParams p;
   p.out = a.out; p.o_bs = a.o_bs; p.o_rs = a.o_rs; p.Lq = a.Lq; p.Lk = a.Lk; p.Lkp = Lkp;
+  p.o_col = (Lkp + 31) & ~31;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.o_col + kD) p.tmem_cols <<= 1;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   dim3 grid((a.Lq + kQTile - 1) / kQTile, a.heads, a.B);
   LMV_CUDA_OK(launch_kernel(attention_tc_kernel, dim3(grid), dim3(kThreads), (size_t)(smem_bytes_for(Lkp)), s, tq, tk, tv, p));

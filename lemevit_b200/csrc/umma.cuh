@@ -65,20 +65,24 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as
 // a hung GPU.  ~2^31 cycles is > 1 s at any clock; legitimate waits are microseconds.
+// -DLMV_VERBOSE_WAIT (debug builds) adds a printf naming the call site (`tag`) before the trap; release builds leave it
+// out because the ~35 instructions per call site inflate the instruction footprint of the multi-role kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > (1ll << 31)) {
+#ifdef LMV_VERBOSE_WAIT
       printf("[lemevit_b200] mbarrier wait timed out: block %d thread %d tag %d parity %u\n", (int)blockIdx.x,
              (int)threadIdx.x, tag, parity);
+#endif
+      (void)tag;
       __trap();
     }
   }
 }
 
-// Same bounded wait without the diagnostic printf (about 35 instructions per call site): for kernels whose instruction
-// footprint matters (many warp roles sharing the instruction cache).
+// Same bounded wait without a tag.
 __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
