@@ -342,7 +342,7 @@ static void ws_layout(const lmv_config& c, const Geo& g, int B, WsLayout* L) {
   L->feat = take((size_t)B * cmax);
   size_t rows_max = 0;
   for (int i = 0; i < c.num_stages; ++i) rows_max = std::max(rows_max, (size_t)B * g.T[i]);
-  L->stats1 = take(rows_max * 4);    // [rows][1][2] fp32 (take() counts 2-byte elements)
+  L->stats1 = take(rows_max * 16);   // [rows][parts <= 4][2] fp32 (take() counts 2-byte elements)
   L->stats2 = take(rows_max * 16);   // [rows][parts <= 4][2] fp32
   // split-softmax partials of the meta-token attention (attention_meta.cu): a few partial rows per image and (head, query)
   size_t cpart = 0;
@@ -467,10 +467,12 @@ struct Builder {
            (long long)T * C, C, B, heads, T - N, T - N, scale);
     }
   }
-  void posln(const bf16* tok, const float* dw_w, const float* dw_b, bf16* resid, bf16* norm, int B, int H, int W, int T,
-             int C, float* stats = nullptr) {
-    if (rc) return;
+  // returns the number of statistics partials per row written to `stats` ([B*T][parts][2], parts <= 4)
+  int posln(const bf16* tok, const float* dw_w, const float* dw_b, bf16* resid, bf16* norm, int B, int H, int W, int T,
+            int C, float* stats = nullptr) {
+    if (rc) return 1;
     PosLnArgs a{tok, dw_w, dw_b, resid, norm, B, H, W, T, C, 1e-6f, stats};
+    a.max_parts = 4;
     const double rows = (double)B * T;
     char d[160];
     snprintf(d, sizeof(d), "posln rows=%d C=%d conv=%d resid=%d norm=%d", B * T, C, dw_w ? 1 : 0, resid ? 1 : 0, norm ? 1 : 0);
@@ -478,11 +480,13 @@ struct Builder {
     if (posembed_tile_supported(a)) {
       PosEmbedOp op;
       rc = posembed_tile_prepare(a, &op);
-      if (rc) return;
+      if (rc) return 1;
       sc->push([op](cudaStream_t s) { return posembed_tile_run(op, s); }, OP_POSLN, fl, by, d);
-      return;
+      return op.parts;
     }
+    a.max_parts = 1;
     sc->push([a](cudaStream_t s) { return posembed_ln_run(a, s); }, OP_POSLN, fl, by, d);
+    return 1;
   }
   void ln(const bf16* in, bf16* out, const float* g, const float* b, int R, int C, float eps, int gelu = 0,
           int grp_rows = 0, int grp_stride = 0, int grp_off = 0) {
@@ -611,10 +615,10 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
       if (kind == 'C') {
         // forward_with_c (models/lemevit.py:584-613) + CrossAttention (:477-486); x is returned unchanged
         // xn <- x + dw(x) (raw; norm1 is folded into the kv GEMM through stats1)
-        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xn, nullptr, B, g.H[i], g.W[i], T, C, stats1);
+        const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xn, nullptr, B, g.H[i], g.W[i], T, C, stats1);
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.wa, bw.ba, B * M, C, C, cqkv, C);
-        b.ln_linear(xn, stats1, 1, bw.wb, bw.bb, bw.csb, B * N, 2 * C, C, qkv);
+        b.ln_linear(xn, stats1, sp, bw.wb, bw.bb, bw.csb, B * N, 2 * C, C, qkv);
         b.attn(cqkv, (long long)M * C, C, qkv, qkv + C, (long long)N * 2 * C, 2 * C, cn, (long long)M * C, C, B, heads, M, N,
                1.0f / sqrtf((float)c.head_dim));
         b.linear(cn, C, bw.wp1, bw.bp1, B * M, C, C, cc, C, 0, cc);
@@ -623,11 +627,11 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         b.linear(chid, Hd, bw.w2, bw.b2, B * M, C, Hd, cc, C, 0, cc);
       } else if (kind == 'D') {
         // forward_with_xc (models/lemevit.py:542-582) + DualCrossAttention (:252-256,288-302)
-        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
+        const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
         cur ^= 1;
         bf16* x = xbuf[cur];
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
-        b.ln_linear(x, stats1, 1, bw.wa, bw.ba, bw.csa, B * N, 3 * C, C, qkv);
+        b.ln_linear(x, stats1, sp, bw.wa, bw.ba, bw.csa, B * N, 3 * C, C, qkv);
         b.linear(cn, C, bw.wb, bw.bb, B * M, 3 * C, C, cqkv, 3 * C);
         const double scale = 1.0 / std::sqrt((double)C);                       // :235 full channel dim
         const double scale_x = std::log((double)M) / std::log((double)N) * scale;  // :255 math.log(M, N)
@@ -645,10 +649,10 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
       } else {
         // forward_with_x (models/lemevit.py:615-650) + StandardAttention (:199-205); image and meta tokens
         // share norm1/attn/norm2/mlp, so they travel in one [B, N+M, C] buffer (classification model only)
-        b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
+        const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
         cur ^= 1;
         bf16* x = xbuf[cur];
-        b.ln_linear(x, stats1, 1, bw.wa, bw.ba, bw.csa, B * T, 3 * C, C, qkv);
+        b.ln_linear(x, stats1, sp, bw.wa, bw.ba, bw.csa, B * T, 3 * C, C, qkv);
         b.self_attn(qkv, xn, B, heads, T, N, C, 1.0f / sqrtf((float)c.head_dim));
         int parts2 = 1;
         b.linear_res_stats(xn, bw.wp1, bw.bp1, B * T, C, C, x, stats2, &parts2);

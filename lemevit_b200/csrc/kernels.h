@@ -12,7 +12,8 @@ struct PosLnArgs {
   bf16* norm_out;       // nullable, [B, T, C]
   int B, H, W, T, C;
   float eps;
-  float* stats_out = nullptr;   // nullable, [B*T][2]: (sum_c v, sum_c v^2) of the bf16-rounded resid_out row (LayerNorm fold input)
+  float* stats_out = nullptr;   // nullable, [B*T][parts][2]: (sum_c v, sum_c v^2) of the bf16-rounded resid_out row (LayerNorm fold input)
+  int max_parts = 1;            // the tiled kernel may split the channels over up to this many CTAs, one statistics partial each
 };
 int posembed_ln_run(const PosLnArgs& a, cudaStream_t s);
 
@@ -21,6 +22,7 @@ struct PosEmbedOp {
   CUtensorMap tm;
   PosLnArgs a;
   int TW, TH, tiles_x, tiles_y, cbox, ncb, smem, sub_bytes, threads;
+  int parts;   // channel slices == statistics partials per row (stats_out is [B*T][parts][2])
 };
 bool posembed_tile_supported(const PosLnArgs& a);
 int posembed_tile_prepare(const PosLnArgs& a, PosEmbedOp* op);
