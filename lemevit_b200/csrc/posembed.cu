@@ -115,9 +115,11 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
 
   const int vpb = p.cbox >> 3;   // 16-byte vectors per channel box
   const int items = p.TW * p.TH * V;
+  // blockDim is a multiple of V: a thread's token index advances by blockDim / V per trip, so (tx, ty) are stepped
+  // instead of divided out of the item index
+  const int tok_step = blockDim.x / V;
+  int tx = (threadIdx.x / V) % p.TW, ty = (threadIdx.x / V) / p.TW;
   for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int tok = i / V;
-    const int tx = tok % p.TW, ty = tok / p.TW;
     const int x = x0 + tx, y = y0 + ty;
     float2 part = make_float2(0.f, 0.f);
     if (x < p.W && y < p.H) {
@@ -150,6 +152,8 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
       for (int j = 0; j < 8; ++j) { part.x += acc[j]; part.y = fmaf(acc[j], acc[j], part.y); }
     }
     if (p.stats) s_part[i] = part;
+    tx += tok_step;
+    while (tx >= p.TW) { tx -= p.TW; ++ty; }
   }
   if (p.stats) {
     __syncthreads();
