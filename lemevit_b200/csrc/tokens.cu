@@ -423,21 +423,27 @@ stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col_3x3s2_kernel(Im2colArgs a, int Ho, int Wo) {
+  // one warp per output pixel: its 9 * C/8 16-byte vectors are contiguous in the patch row, so lane j writes vector j
+  // (fully coalesced) and reads vector (j % vecs) of tap (j / vecs); the pixel is decomposed once per warp in 32-bit math
   pdl_launch_dependents();
   pdl_wait();
-  const int vecs = a.C >> 3;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)a.B * Ho * Wo * 9 * vecs;
-  if (idx >= total) return;
-  const int vec = (int)(idx % vecs);
-  const int tap = (int)((idx / vecs) % 9);
-  const long long pix = idx / (9 * vecs);
-  const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-  const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
-  uint4 u = make_uint4(0u, 0u, 0u, 0u);
-  if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-    u = __ldg(reinterpret_cast<const uint4*>(a.in + ((long long)b * a.T + (long long)iy * a.W + ix) * a.C) + vec);
-  reinterpret_cast<uint4*>(a.out + pix * (9LL * a.C) + (long long)tap * a.C)[vec] = u;
+  const int vecs = a.C >> 3, S = 9 * vecs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npix = a.B * Ho * Wo, HoWo = Ho * Wo;
+  const int pix = blockIdx.x * 8 + warp;
+  if (pix >= npix) return;
+  const int b = pix / HoWo, rem = pix - b * HoWo, oy = rem / Wo, ox = rem - oy * Wo;
+  const uint4* in_b = reinterpret_cast<const uint4*>(a.in + (long long)b * a.T * a.C);
+  uint4* out_p = reinterpret_cast<uint4*>(a.out + (long long)pix * (9LL * a.C));
+#pragma unroll 4
+  for (int j = lane; j < S; j += 32) {
+    const int tap = j / vecs, vec = j - tap * vecs;
+    const int ky = tap / 3, kx = tap - 3 * ky;
+    const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) u = __ldg(in_b + (long long)(iy * a.W + ix) * vecs + vec);
+    out_p[j] = u;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -633,9 +639,10 @@ int stem_conv1_run(const StemArgs& a, const bf16* w, const float* bias, int C1, 
 int im2col_run(const Im2colArgs& a, cudaStream_t s) {
   LMV_REQUIRE(a.C % 8 == 0, "im2col: C must be a multiple of 8");
   const int Ho = (a.H + 1) / 2, Wo = (a.W + 1) / 2;
-  const long long total = (long long)a.B * Ho * Wo * 9 * (a.C / 8);
-  if (total == 0) return LMV_OK;
-  LMV_CUDA_OK(launch_kernel(im2col_3x3s2_kernel, dim3(blocks_for(total, 256)), dim3(256), (size_t)(0), s, a, Ho, Wo));
+  const long long npix = (long long)a.B * Ho * Wo;
+  if (npix == 0) return LMV_OK;
+  LMV_REQUIRE(npix < (1ll << 31), "im2col: more than 2^31 output pixels");
+  LMV_CUDA_OK(launch_kernel(im2col_3x3s2_kernel, dim3((unsigned)((npix + 7) / 8)), dim3(256), (size_t)(0), s, a, Ho, Wo));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
