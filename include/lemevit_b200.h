@@ -164,9 +164,10 @@ int lmv_attention_self(const void* q, long long q_bs, int q_rs, const void* k, l
                        long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int T, int N, float scale,
                        void* workspace, size_t workspace_bytes, void* stream);
 /* The meta-token side of CrossAttention / DualCrossAttention (models/lemevit.py:484, :300-302): Lq = M (16) queries
- * per head over Lk = N image tokens, heads * Lq <= 128, heads * 32 <= 256.  Split-N tcgen05 kernel (one CTA per image
- * and 128-token tile, block-diagonal Q so that all heads share one accumulation) + deterministic merge of the
- * per-tile softmax partials.  workspace: lmv_attention_meta_workspace(...) bytes of device scratch, 16-byte aligned. */
+ * per head over Lk = N image tokens, heads * Lq <= 128, heads * 32 <= 256.  Persistent tcgen05 kernel (one CTA per SM
+ * streams 128-token K/V tiles, block-diagonal Q so that all heads share one accumulation, running softmax state in
+ * registers) + deterministic merge of the per-segment softmax partials; the bits of an image's output do not depend on
+ * B or on its position in the batch.  workspace: lmv_attention_meta_workspace(...) bytes of device scratch, 16-byte aligned. */
 size_t lmv_attention_meta_workspace(int B, int heads, int Lq, int Lk);
 int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
                        long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
