@@ -77,6 +77,10 @@ int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
  *   "direct_stem" (default 1): first stem convolution as a direct kernel (lmv_stem_conv1) instead of im2col + GEMM;
  *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self). */
 int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
+/* test hook (block-level parity against the reference's forward hooks): after block `block` of stage `stage` every forward
+ * copies the block's outputs to x_tokens_out [B, N, C] bf16 (token-major) and c_out [B, queries_len, C] bf16 (either may be
+ * null); stage < 0 turns the tap off.  The buffers must hold the batch of the forwards that follow. */
+int lmv_plan_set_tap(lmv_plan* plan, int stage, int block, void* x_tokens_out, void* c_out);
 /* bring-up switch: 1 routes every GEMM / attention through the plain SIMT cross-check kernels. */
 int lmv_plan_set_debug_simt(lmv_plan* plan, int enable);
 size_t lmv_workspace_bytes(const lmv_plan* plan, int batch, int H, int W);
@@ -102,6 +106,13 @@ int lmv_plan_profile_report(lmv_plan* plan, char* buf, int buf_bytes);
  * -> logits[B,num_classes] (bf16 or f32, per logits_dtype). */
 int lmv_forward_cls(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,
                     size_t workspace_bytes, void* logits, int logits_dtype, void* stream);
+/* replaces LeMeViT.forward_features(x, c) (models/lemevit.py:809-829) and, with `logits`, the head on top of it (:831-836):
+ * meta_tokens: nullable; [B, queries_len, embed_dim[0]] bf16 — the caller's own meta tokens, run through
+ *   meta_token_downsample[0] on the device (null: the model's `meta_tokens` parameter, as LeMeViT.forward does at :833);
+ * features: nullable; [B, embed_dim[-1]] bf16 = mean_HW(BN(x)) + mean_M(LN(c)) (:815-827);
+ * logits: nullable (must be null when num_classes == 0); [B, num_classes] in logits_dtype. */
+int lmv_forward_cls_features(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, const void* meta_tokens,
+                             void* workspace, size_t workspace_bytes, void* features, void* logits, int logits_dtype, void* stream);
 /* replaces the backbone copies' forward (semantic_segmentation/.../lemevit.py:822-827):
  * -> outs[k] = x after stage k+1 as contiguous NCHW [B, embed_dim[k+1], H/s, W/s], k = 0..3. */
 int lmv_forward_features(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,

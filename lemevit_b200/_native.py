@@ -52,6 +52,7 @@ SIGNATURES = {
     "lmv_plan_destroy": (None, [_vp]),
     "lmv_plan_set_chunk": (_i, [_vp, _i]),
     "lmv_plan_set_debug_simt": (_i, [_vp, _i]),
+    "lmv_plan_set_tap": (_i, [_vp, _i, _i, _vp, _vp]),
     "lmv_plan_set_option": (_i, [_vp, C.c_char_p, _i]),
     "lmv_plan_set_profile": (_i, [_vp, _i]),
     "lmv_plan_get_profile": (_i, [_vp, _vp, _i]),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "lmv_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "lmv_launch_count": (_i, [_vp, _i, _i, _i]),
     "lmv_forward_cls": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp, _i, _vp]),
+    "lmv_forward_cls_features": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _sz, _vp, _vp, _i, _vp]),
     "lmv_forward_features": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, C.POINTER(_vp), _i, _i, _vp]),
     "lmv_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "lmv_linear_fused": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _f, _vp, _i, _vp]),

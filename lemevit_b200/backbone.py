@@ -24,7 +24,7 @@ from .model import LeMeViT
 class LeMeViTBackbone(LeMeViT):
     backbone_mode = True
 
-    def __init__(self, *args, pretrained=None, init_cfg=None, frozen_stages=-1, out_dtype=None, **kwargs):
+    def __init__(self, *args, pretrained=None, init_cfg=None, frozen_stages=-1, norm_eval=None, out_dtype=None, **kwargs):
         kwargs.setdefault("num_classes", 1000)
         super().__init__(*args, **kwargs)
         assert not (init_cfg and pretrained), 'init_cfg and pretrained cannot be specified at the same time'
@@ -33,7 +33,14 @@ class LeMeViTBackbone(LeMeViT):
         elif pretrained is not None:
             raise TypeError('pretrained must be a str or None')
         self.init_cfg = init_cfg
-        self.frozen_stages = frozen_stages
+        # mmdet / change-detection configs pass a list of stage indices ([-1] = none, object_detection/.../lemevit.py:667,827-831);
+        # an int n is read the OpenMMLab way (stages 0..n frozen, -1 = none)
+        if isinstance(frozen_stages, int):
+            frozen_stages = list(range(frozen_stages + 1)) if frozen_stages >= 0 else [-1]
+        self.frozen_stages = list(frozen_stages)
+        # mmdet's train() keeps every BatchNorm / LayerNorm in eval mode (freeze_bn = True, :833-842); mmseg's does not (:874-882).
+        # None: decided by which registry built the module (register_backbones); False for direct construction.
+        self.norm_eval = norm_eval
         self.out_dtype = out_dtype
         # the backbone copies have no classifier (reference :786 commented out): drop it so the key set matches
         self.head = nn.Identity()
@@ -66,18 +73,49 @@ class LeMeViTBackbone(LeMeViT):
             log.info(self.load_state_dict(self._clean_state_dict(ckpt), strict=False))
         self._drop_engine()
 
+    def _freeze_stages(self):
+        # object_detection/mmdet/models/backbones/lemevit.py:827-831
+        for i in self.frozen_stages:
+            if i >= 0:
+                for param in self.stages[i].parameters():
+                    param.requires_grad = False
+
     def train(self, mode=True):
-        # the reference overrides return None (:874-882) — callers must not chain on .eval()/.train()
+        """mmdet semantics (:833-842): frozen stages lose requires_grad and, with ``norm_eval``, every BatchNorm2d / LayerNorm
+        stays in eval mode, so a ``train()``-ed detector backbone computes exactly the eval forward.  Like the reference
+        overrides (mmseg :874-882) this returns None — callers must not chain on .eval()/.train()."""
+        self._freeze_stages()
         super().train(mode)
+        if mode and self.norm_eval:
+            for m in self.modules():
+                if isinstance(m, (nn.BatchNorm2d, nn.LayerNorm)):
+                    m.eval()
+
+    def _check_inference(self):
+        # a backbone whose norms are frozen (mmdet) and that has no stochastic depth runs the same arithmetic in train mode
+        if self.training and self.norm_eval and not self.drop_path_rate and not self.drop_rate:
+            if not any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
+                if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                    raise RuntimeError("lemevit_b200 is inference-only: the backbone has trainable parameters but the native forward "
+                                       "builds no autograd graph. Freeze it (frozen_stages=[0,1,2,3,4] + torch.no_grad()) or train with "
+                                       "the reference implementation.")
+                return
+        super()._check_inference()
 
     def forward(self, x) -> List[torch.Tensor]:
         require_cuda(x)
+        self._check_inference()
         eng = self.native_engine(x.device)
         dt = self.out_dtype or (torch.bfloat16 if self.meta_tokens.dtype == torch.bfloat16 else torch.float32)
         return eng.forward_features(x, out_dtype=dt)
 
     def forward_features(self, x, c=None):
         return self.forward(x)
+
+
+def _mmdet_init(self, *args, **kwargs):
+    kwargs.setdefault("norm_eval", True)
+    LeMeViTBackbone.__init__(self, *args, **kwargs)
 
 
 def register_backbones(verbose: bool = False) -> List[str]:
@@ -90,7 +128,10 @@ def register_backbones(verbose: bool = False) -> List[str]:
         except Exception:
             continue
         try:
-            reg.register_module(name="LeMeViT", force=True, module=LeMeViTBackbone)
+            cls = LeMeViTBackbone
+            if pkg == "mmdet":      # the mmdet copy freezes its norms in train() (object_detection/.../lemevit.py:833-842)
+                cls = type("LeMeViT", (LeMeViTBackbone,), {"__init__": _mmdet_init, "__module__": __name__})
+            reg.register_module(name="LeMeViT", force=True, module=cls)
             done.append(pkg)
         except Exception as e:  # pragma: no cover
             if verbose:

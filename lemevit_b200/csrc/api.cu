@@ -77,12 +77,14 @@ bool pdl_enabled() {
 }
 
 int device_sm_count() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
+  static std::atomic<int> cache[PerDeviceOnce::kMaxDevices];   // zero-initialised: 0 = unknown
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const bool cached = dev >= 0 && dev < PerDeviceOnce::kMaxDevices;
+  if (cached && (v = cache[dev].load(std::memory_order_relaxed)) > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  if (cached) cache[dev].store(v, std::memory_order_relaxed);
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -120,6 +122,8 @@ struct OpRec {
 
 struct IoSlots {
   const void* x = nullptr;
+  const void* c_in = nullptr;   // caller-supplied meta tokens [B, M, C0] bf16 (forward_features(x, c), models/lemevit.py:809)
+  void* feat = nullptr;         // pre-head features [B, C_last] bf16 (nullable)
   void* logits = nullptr;
   void* outs[LMV_MAX_STAGES] = {nullptr};
 };
@@ -153,10 +157,12 @@ struct lmv_plan {
   int fused_self_attn = 1;
   int direct_stem = 1;
   int profile = 0;
+  int tap_stage = -1, tap_block = -1;       // test hook: copy (x, c) after this block to tap_x / tap_c
+  void *tap_x = nullptr, *tap_c = nullptr;
   std::vector<cudaEvent_t> events;          // profile mode: one event between consecutive launches
   std::vector<const lmv::OpRec*> pending;   // ops whose events have not been harvested yet
   lmv::ProfAcc acc;
-  std::map<std::tuple<int, int, int, const void*, int, int, int>, std::unique_ptr<lmv::Schedule>> cache;
+  std::map<std::tuple<int, int, int, const void*, int, int, int, int>, std::unique_ptr<lmv::Schedule>> cache;
 };
 
 namespace lmv {
@@ -222,9 +228,11 @@ static void walk(const lmv_config& c, PackWalker& w, lmv_plan* plan) {
     StageW tmp;
     StageW& s = plan ? plan->stages[i] : tmp;
     const int C = c.embed_dim[i], Hd = c.mlp_hidden[i];
-    if (i > 0) {
-      const int Cp = c.embed_dim[i - 1];
-      if (c.attn_type[i - 1] != 'C') {
+    {
+      // meta_token_downsample[i] (models/lemevit.py:729-745); [0] maps C0 -> C0 and is only run when the caller supplies
+      // its own meta tokens (otherwise its output on `meta_tokens` is the pack-time constant c0_init)
+      const int Cp = c.embed_dim[i > 0 ? i - 1 : 0];
+      if (i > 0 && c.attn_type[i - 1] != 'C') {
         s.ds_w = w.h((int64_t)C * 9 * Cp, "ds_w");
         s.ds_b = w.f(C, "ds_b");
       }
@@ -512,6 +520,12 @@ struct Builder {
       return;
     }
     const bool tc = !simt && attention_tc_supported(a);
+    if (!tc && !simt) {
+      // no silent drop to the SIMT cross-check kernel (100x slower): an attention shape outside the tcgen05 kernels is an error
+      rc = fail(LMV_ERR_UNSUPPORTED, "attention: no tcgen05 kernel covers B=" + std::to_string(B) + " heads=" + std::to_string(heads) + " Lq=" +
+                                         std::to_string(Lq) + " Lk=" + std::to_string(Lk) + " (lmv_plan_set_debug_simt(1) runs it on the SIMT cross-check kernel)");
+      return;
+    }
     sc->push([a, tc](cudaStream_t s) { return tc ? attention_tc_run(a, s) : attention_simt_run(a, s); },
              tc ? OP_ATTN_TC : OP_ATTN_SIMT, fl, by,
              std::string(tc ? "attn_tc" : "attn_simt") + " B=" + std::to_string(B) + " h=" + std::to_string(heads) + " Lq=" +
@@ -519,7 +533,12 @@ struct Builder {
   }
 };
 
-static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int x_dtype, int out_dtype, Schedule* sc) {
+// schedule flags (part of the cache key)
+constexpr int kFlagCustomC = 1;   // meta tokens come from io->c_in and go through meta_token_downsample[0] at run time
+constexpr int kFlagFeat = 2;      // copy the pre-head features to io->feat
+constexpr int kFlagLogits = 4;    // run the classifier head into io->logits
+
+static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int x_dtype, int out_dtype, int flags, Schedule* sc) {
   const lmv_config& c = plan->cfg;
   Geo g;
   int rc = geometry(c, H, W, &g);
@@ -586,15 +605,26 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
     }
     // ---- meta-token path into this stage (models/lemevit.py:729-745, :833)
     if (g.c_alive[i]) {
-      if (i == 0) {
+      if (i == 0 && !(flags & kFlagCustomC)) {
         // meta_ds_0(meta_tokens) is batch-invariant: folded at pack time into c0_init
         bf16* dst = uni ? xbuf[cur] + (size_t)N * C : cbuf[ccur];
         const long long bs = uni ? (long long)T * C : (long long)M * C;
         const bf16* src = plan->c0_init;
         sc->push([src, dst, M, C, B, bs](cudaStream_t s) { return broadcast_rows_run(src, dst, M, C, B, bs, s); });
       } else {
-        const int Cp = c.embed_dim[i - 1];
+        const int Cp = c.embed_dim[i > 0 ? i - 1 : 0];
         const bf16* cprev = cbuf[ccur];
+        if (i == 0) {
+          // forward_features(x, c) with the caller's own meta tokens (models/lemevit.py:809-813): stage them next to the
+          // other meta-token buffers (the GEMM's tensor map is encoded once per schedule, the caller's pointer changes)
+          bf16* dst = cbuf[ccur];
+          const size_t bytes = (size_t)B * M * Cp * sizeof(bf16);
+          sc->push([io, dst, bytes](cudaStream_t s) {
+            if (!io->c_in) return fail(LMV_ERR_INVALID, "forward: this schedule expects caller-supplied meta tokens");
+            LMV_CUDA_OK(cudaMemcpyAsync(dst, io->c_in, bytes, cudaMemcpyDeviceToDevice, s));
+            return LMV_OK;
+          });
+        }
         if (c_prev_unified) {
           const bf16* src = c_prev_unified;
           bf16* dst = cbuf[ccur];
@@ -658,6 +688,18 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         b.linear_res_stats(xn, bw.wp1, bw.bp1, B * T, C, C, x, stats2, &parts2);
         b.mlp(x, stats2, parts2, bw, B * T, C, Hd, hid);
       }
+      if (i == plan->tap_stage && j == plan->tap_block) {
+        // test hook (lmv_plan_set_tap): dense copies of the block's outputs, x as tokens [B, N, C], c as [B, M, C]
+        const bf16* xs = xbuf[cur];
+        const bf16* cs = uni ? xbuf[cur] + (size_t)N * C : cc;
+        const size_t xpitch = (size_t)T * C * 2, cpitch = uni ? xpitch : (size_t)M * C * 2;
+        void *tx = plan->tap_x, *tc = plan->tap_c;
+        sc->push([=](cudaStream_t s) {
+          if (tx) LMV_CUDA_OK(cudaMemcpy2DAsync(tx, (size_t)N * C * 2, xs, xpitch, (size_t)N * C * 2, B, cudaMemcpyDeviceToDevice, s));
+          if (tc) LMV_CUDA_OK(cudaMemcpy2DAsync(tc, (size_t)M * C * 2, cs, cpitch, (size_t)M * C * 2, B, cudaMemcpyDeviceToDevice, s));
+          return LMV_OK;
+        });
+      }
     }
     // ---- backbone outputs: x after stages 1..S-1 as NCHW (semantic_segmentation/.../lemevit.py:800-820)
     if (c.backbone && i >= 1) {
@@ -679,7 +721,16 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
     ta.bn_scale = plan->bn_scale; ta.bn_shift = plan->bn_shift; ta.ln_gamma = plan->lnc_g; ta.ln_beta = plan->lnc_b;
     ta.eps = 1e-5f; ta.feat = feat; ta.B = B;
     sc->push([ta](cudaStream_t s) { return tail_run(ta, s); });
-    if (c.num_classes > 0) {
+    if (flags & kFlagFeat) {
+      const size_t bytes = (size_t)B * C * sizeof(bf16);
+      sc->push([io, feat, bytes](cudaStream_t s) {
+        if (!io->feat) return fail(LMV_ERR_INVALID, "forward: this schedule expects a feature output buffer");
+        LMV_CUDA_OK(cudaMemcpyAsync(io->feat, feat, bytes, cudaMemcpyDeviceToDevice, s));
+        return LMV_OK;
+      });
+    }
+    if (flags & kFlagLogits) {
+      if (c.num_classes <= 0) return fail(LMV_ERR_INVALID, "forward: logits requested from a model without a classifier (num_classes == 0)");
       GemmArgs ga;
       ga.A = feat; ga.lda = C; ga.W = plan->head_w; ga.ldw = C; ga.M = B; ga.N = c.num_classes; ga.K = C;
       ga.bias = plan->head_b; ga.ldc = c.num_classes; ga.out_fp32 = (out_dtype == LMV_DTYPE_F32);
@@ -695,8 +746,6 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         if (rc) return rc;
         sc->push([op, io](cudaStream_t s) { GemmOp o = op; o.p.out = io->logits; return gemm_run(o, s); }, OP_GEMM, hfl, 0);
       }
-    } else {
-      return fail(LMV_ERR_UNSUPPORTED, "num_classes == 0 (features only) is not implemented for the classification model");
     }
   }
   return LMV_OK;
@@ -704,7 +753,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
 
 static int harvest_profile(lmv_plan* plan);
 
-static int get_schedule(lmv_plan* plan, int B, int H, int W, void* ws, size_t ws_bytes, int x_dtype, int out_dtype,
+static int get_schedule(lmv_plan* plan, int B, int H, int W, void* ws, size_t ws_bytes, int x_dtype, int out_dtype, int flags,
                         Schedule** out) {
   Geo g;
   int rc = geometry(plan->cfg, H, W, &g);
@@ -713,7 +762,7 @@ static int get_schedule(lmv_plan* plan, int B, int H, int W, void* ws, size_t ws
   ws_layout(plan->cfg, g, B, &L);
   if (ws_bytes < L.total) return fail(LMV_ERR_INVALID, "workspace too small: need " + std::to_string(L.total) + " bytes");
   LMV_REQUIRE(ws && (reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
-  auto key = std::make_tuple(B, H, W, (const void*)ws, x_dtype, out_dtype, plan->debug_simt);
+  auto key = std::make_tuple(B, H, W, (const void*)ws, x_dtype, out_dtype, plan->debug_simt, flags);
   auto it = plan->cache.find(key);
   if (it == plan->cache.end()) {
     if (plan->cache.size() >= 16) {
@@ -722,7 +771,7 @@ static int get_schedule(lmv_plan* plan, int B, int H, int W, void* ws, size_t ws
       plan->cache.clear();
     }
     std::unique_ptr<Schedule> sc(new Schedule());
-    rc = build_schedule(plan, B, H, W, static_cast<uint8_t*>(ws), x_dtype, out_dtype, sc.get());
+    rc = build_schedule(plan, B, H, W, static_cast<uint8_t*>(ws), x_dtype, out_dtype, flags, sc.get());
     if (rc) return rc;
     it = plan->cache.emplace(key, std::move(sc)).first;
   }
@@ -750,7 +799,8 @@ static int harvest_profile(lmv_plan* plan) {
 }
 
 static int run_forward(lmv_plan* plan, const void* x, int x_dtype, int B, int H, int W, void* ws, size_t ws_bytes,
-                       void* logits, void* const* outs, int n_outs, int out_dtype, cudaStream_t stream) {
+                       void* logits, void* const* outs, int n_outs, int out_dtype, cudaStream_t stream,
+                       const void* c_in = nullptr, void* feat = nullptr) {
   LMV_REQUIRE(plan && x && B > 0, "forward: null plan/input or empty batch");
   LMV_REQUIRE(x_dtype == LMV_DTYPE_BF16 || x_dtype == LMV_DTYPE_F32, "forward: x dtype");
   LMV_REQUIRE(out_dtype == LMV_DTYPE_BF16 || out_dtype == LMV_DTYPE_F32, "forward: output dtype");
@@ -763,8 +813,12 @@ static int run_forward(lmv_plan* plan, const void* x, int x_dtype, int B, int H,
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int bc = std::min(chunk, B - b0);
     Schedule* sc = nullptr;
-    rc = get_schedule(plan, bc, H, W, ws, ws_bytes, x_dtype, out_dtype, &sc);
+    const int flags = (c_in ? kFlagCustomC : 0) | (feat ? kFlagFeat : 0) | (logits ? kFlagLogits : 0);
+    rc = get_schedule(plan, bc, H, W, ws, ws_bytes, x_dtype, out_dtype, flags, &sc);
     if (rc) return rc;
+    const int CL = c.embed_dim[c.num_stages - 1];
+    sc->io->c_in = c_in ? static_cast<const uint8_t*>(c_in) + (size_t)b0 * c.queries_len * c.embed_dim[0] * sizeof(bf16) : nullptr;
+    sc->io->feat = feat ? static_cast<uint8_t*>(feat) + (size_t)b0 * CL * sizeof(bf16) : nullptr;
     sc->io->x = static_cast<const uint8_t*>(x) + (size_t)b0 * c.in_chans * H * W * xe;
     if (logits) sc->io->logits = static_cast<uint8_t*>(logits) + (size_t)b0 * c.num_classes * oe;
     for (int k = 0; k < n_outs; ++k)
@@ -895,6 +949,14 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   plan->cache.clear();   // schedules are rebuilt with the new setting
   return LMV_OK;
 }
+int lmv_plan_set_tap(lmv_plan* plan, int stage, int block, void* x_tokens_out, void* c_out) {
+  if (!plan) return fail(LMV_ERR_INVALID, "null plan");
+  int rc = harvest_profile(plan);
+  if (rc) return rc;
+  plan->tap_stage = stage; plan->tap_block = block; plan->tap_x = x_tokens_out; plan->tap_c = c_out;
+  plan->cache.clear();
+  return LMV_OK;
+}
 int lmv_plan_set_debug_simt(lmv_plan* plan, int enable) {
   if (!plan) return fail(LMV_ERR_INVALID, "null plan");
   plan->debug_simt = enable ? 1 : 0;
@@ -934,6 +996,15 @@ int lmv_forward_cls(lmv_plan* plan, const void* x, int x_dtype, int batch, int H
   if (!logits) return fail(LMV_ERR_INVALID, "forward_cls: null logits");
   return run_forward(plan, x, x_dtype, batch, H, W, workspace, workspace_bytes, logits, nullptr, 0, logits_dtype,
                      static_cast<cudaStream_t>(stream));
+}
+
+int lmv_forward_cls_features(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, const void* meta_tokens,
+                             void* workspace, size_t workspace_bytes, void* features, void* logits, int logits_dtype, void* stream) {
+  if (!plan || plan->cfg.backbone) return fail(LMV_ERR_INVALID, "forward_cls_features: plan was created for the backbone variant");
+  if (!features && !logits) return fail(LMV_ERR_INVALID, "forward_cls_features: neither features nor logits requested");
+  if (logits && plan->cfg.num_classes <= 0) return fail(LMV_ERR_INVALID, "forward_cls_features: the model has no classifier (num_classes == 0)");
+  return run_forward(plan, x, x_dtype, batch, H, W, workspace, workspace_bytes, logits, nullptr, 0, logits ? logits_dtype : LMV_DTYPE_BF16,
+                     static_cast<cudaStream_t>(stream), meta_tokens, features);
 }
 
 int lmv_forward_features(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,

@@ -395,8 +395,7 @@ attention_meta_merge_kernel(const float* __restrict__ part_o, const float2* __re
   out[(long long)b * o_bs + (long long)j * o_rs + h * kD + lane] = __float2bfloat16(o / l);
 }
 
-std::once_flag g_once;
-cudaError_t g_attr = cudaSuccess;
+PerDeviceOnce g_attr_once;
 
 struct MetaShape {
   int nchunk, kst, vst, dup, tiles, seg_tiles, segs, grid, ncopy, smem;
@@ -440,10 +439,7 @@ int attention_meta_run(const AttnArgs& a, void* workspace, size_t workspace_byte
   if (!attention_meta_supported(a)) return fail(LMV_ERR_UNSUPPORTED, "attention_meta: unsupported shape / alignment");
   LMV_REQUIRE(workspace && workspace_bytes >= attention_meta_workspace(a) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
               "attention_meta: partial-softmax workspace missing or too small");
-  std::call_once(g_once, [] {
-    g_attr = cudaFuncSetAttribute(attention_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  LMV_CUDA_OK(g_attr);
+  LMV_CUDA_OK(g_attr_once.run([] { return cudaFuncSetAttribute(attention_meta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   const MetaShape sh = shape_for(a);
   MetaParams p;
   p.q = a.q; p.q_bs = a.q_bs; p.q_rs = a.q_rs;

@@ -416,8 +416,7 @@ attention_self_merge_kernel(const float* __restrict__ part_o, const float2* __re
   out[(long long)b * o_bs + (long long)row * o_rs + h * kD + lane] = __float2bfloat16(o / l);
 }
 
-std::once_flag g_once;
-cudaError_t g_attr = cudaSuccess;
+PerDeviceOnce g_attr_once;
 
 }  // namespace
 
@@ -448,10 +447,7 @@ int attention_self_run(const AttnArgs& a, int T, int N, void* workspace, size_t 
   LMV_REQUIRE(attention_self_workspace(a.B, a.heads, T) == 0 ||
                   (workspace && workspace_bytes >= attention_self_workspace(a.B, a.heads, T) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0),
               "attention_self: split-KV workspace missing or too small");
-  std::call_once(g_once, [] {
-    g_attr = cudaFuncSetAttribute(attention_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  });
-  LMV_CUDA_OK(g_attr);
+  LMV_CUDA_OK(g_attr_once.run([] { return cudaFuncSetAttribute(attention_self_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes); }));
   SelfParams p;
   p.out = a.out; p.o_bs = a.o_bs; p.o_rs = a.o_rs;
   p.B = a.B; p.heads = a.heads; p.T = T; p.N = N;

@@ -188,8 +188,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
 }
 
-std::once_flag g_once;
-cudaError_t g_attr = cudaSuccess;
+PerDeviceOnce g_attr_once;
 
 int smem_bytes_for(int Lkp) { return 2048 + kQTile * kD * 2 + 2 * Lkp * kD * 2 + ((Lkp + 63) / 64) * kQTile * 128; }
 
@@ -204,10 +203,7 @@ bool attention_tc_supported(const AttnArgs& a) {
 
 int attention_tc_run(const AttnArgs& a, cudaStream_t s) {
   if (!attention_tc_supported(a)) return fail(LMV_ERR_UNSUPPORTED, "attention_tc: unsupported shape / alignment");
-  std::call_once(g_once, [] {
-    g_attr = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(kMaxKeys));
-  });
-  LMV_CUDA_OK(g_attr);
+  LMV_CUDA_OK(g_attr_once.run([] { return cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(kMaxKeys)); }));
   const int Lkp = (a.Lk + 15) & ~15;
   CUtensorMap tq, tk, tv;
   auto enc = [&](CUtensorMap* m, const bf16* base, long long bs, int rs, int rows, int box_rows) {

@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <utility>
 
@@ -40,7 +42,37 @@ int fail(int code, const std::string& msg);  // records msg, returns code
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes);
 
-int device_sm_count();
+int device_sm_count();   // SM count of the CURRENT device (cached per device)
+
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) are per device: a process that runs the model on a second
+// GPU (nn.DataParallel replicas — reference validate.py:260-261 — or cuda:1 after cuda:0) must set them again there.
+// PerDeviceOnce runs `fn` the first time it is called with each device current (thread-safe, lock-free afterwards) and
+// remembers that device's result.
+struct PerDeviceOnce {
+  static constexpr int kMaxDevices = 64;
+  std::atomic<int> state[kMaxDevices];     // 0 = not run, 1 = ok, 2 = failed
+  cudaError_t err[kMaxDevices];
+  std::mutex mu;
+  PerDeviceOnce() { for (auto& s : state) s.store(0); }
+  template <typename F>
+  cudaError_t run(F&& fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return fn();   // beyond the cache: just do it every time
+    int st = state[dev].load(std::memory_order_acquire);
+    if (st == 0) {
+      std::lock_guard<std::mutex> lock(mu);
+      st = state[dev].load(std::memory_order_relaxed);
+      if (st == 0) {
+        err[dev] = fn();
+        st = err[dev] == cudaSuccess ? 1 : 2;
+        state[dev].store(st, std::memory_order_release);
+      }
+    }
+    return st == 1 ? cudaSuccess : err[dev];
+  }
+};
 
 // Every kernel goes through this launcher: programmatic stream serialization (PDL) lets consecutive kernels of the forward overlap
 // the prologue of kernel n+1 with the tail of kernel n (each kernel calls pdl_wait() before touching dependent global memory).

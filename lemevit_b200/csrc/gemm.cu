@@ -484,8 +484,7 @@ int pick_bn(int N) {
   return std::min(256, ((N + 31) / 32) * 32);
 }
 
-std::once_flag g_attr_once;
-cudaError_t g_attr_err = cudaSuccess;
+PerDeviceOnce g_attr_once;
 
 }  // namespace
 
@@ -562,13 +561,14 @@ static const struct { int flags; GemmKernel fn; } kGemmVariants[] = {
 };
 
 int gemm_run(const GemmOp& op, cudaStream_t stream) {
-  std::call_once(g_attr_once, [] {
+  LMV_CUDA_OK(g_attr_once.run([] {
+    cudaError_t err = cudaSuccess;
     for (const auto& v : kGemmVariants) {
       const cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-      if (e != cudaSuccess) g_attr_err = e;
+      if (e != cudaSuccess) err = e;
     }
-  });
-  LMV_CUDA_OK(g_attr_err);
+    return err;
+  }));
   const GemmParams& gp = op.p;
   const int flags = (gp.ln_stats ? kEpiLn : 0) | (gp.act == 1 ? kEpiGelu : 0) | (gp.residual ? kEpiRes : 0) | (gp.stats_out ? kEpiStats : 0);
   GemmKernel fn = gemm_bf16_tn_tcgen05<-1>;

@@ -342,8 +342,7 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-std::once_flag g_once;
-cudaError_t g_attr = cudaSuccess;
+PerDeviceOnce g_attr_once;
 
 }  // namespace
 
@@ -413,10 +412,7 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
 }
 
 int mlp_fused_run(const MlpOp& op, cudaStream_t stream) {
-  std::call_once(g_once, [] {
-    g_attr = cudaFuncSetAttribute(mlp_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-  });
-  LMV_CUDA_OK(g_attr);
+  LMV_CUDA_OK(g_attr_once.run([] { return cudaFuncSetAttribute(mlp_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit); }));
   LMV_CUDA_OK(launch_kernel(mlp_fused_tcgen05, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmX, op.tmW1, op.tmW2, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;

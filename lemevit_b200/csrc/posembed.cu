@@ -219,11 +219,8 @@ int posembed_tile_prepare(const PosLnArgs& a, PosEmbedOp* op) {
 int posembed_tile_run(const PosEmbedOp& op, cudaStream_t s) {
   const PosLnArgs& a = op.a;
   if (a.B == 0) return LMV_OK;
-  static int attr_done = 0;
-  if (!attr_done) {
-    LMV_CUDA_OK(cudaFuncSetAttribute(posembed_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = 1;
-  }
+  static PerDeviceOnce attr_once;
+  LMV_CUDA_OK(attr_once.run([] { return cudaFuncSetAttribute(posembed_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
   PosTileParams p;
   p.tokens = a.tokens; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.out = a.resid_out; p.stats = a.stats_out;
   p.H = a.H; p.W = a.W; p.T = a.T; p.C = a.C;

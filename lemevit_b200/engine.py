@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -48,7 +49,14 @@ class Engine:
         self._plan = C.c_void_p()
         _native.check(self.lib.lmv_plan_create(C.byref(self.cfg), arr, n, C.byref(self._plan)))
         self._ws: Optional[torch.Tensor] = None
-        self._graphs: Dict[Tuple, Tuple] = {}
+        # captured graphs: key -> (static_x, static_out, graph, workspaces, packed).  A graph bakes raw device pointers of its
+        # workspace and of the packed weights into its kernel nodes, so every entry OWNS its workspace tensors and holds a
+        # reference to the packed list: neither can be freed or reallocated while the graph (or a replay callable handed to
+        # a caller) is alive.  close() bumps the generation, after which stale replay callables raise instead of running.
+        self._graphs: "OrderedDict[Tuple, Tuple]" = OrderedDict()
+        self.max_graphs = int(os.environ.get("LEMEVIT_B200_MAX_GRAPHS", "8"))
+        self._generation = 0
+        self._closed = False
         # concurrent sub-batches per forward: two streams measured +4 % on Base b256 (four: -0.5 %); small batches stay on one
         self.lanes = int(os.environ.get("LEMEVIT_B200_LANES", "2"))
         self.lane_min_batch = 128
@@ -58,10 +66,24 @@ class Engine:
 
     # -- lifecycle ---------------------------------------------------------------------------------
     def close(self):
+        """Destroy the native plan.  Captured graphs die with it: replay callables obtained from graphed() raise afterwards."""
+        self._closed = True
+        self._invalidate_graphs()
         if getattr(self, "_plan", None) is not None and self._plan.value:
             self.lib.lmv_plan_destroy(self._plan)
             self._plan = C.c_void_p()
-        self._graphs.clear()
+
+    def _invalidate_graphs(self):
+        self._generation = getattr(self, "_generation", 0) + 1
+        if getattr(self, "_graphs", None):
+            # a graph that is still replaying must finish before its workspace can go back to the allocator
+            torch.cuda.synchronize(self.device)
+            self._graphs.clear()
+
+    def _check_open(self):
+        if self._closed:
+            raise RuntimeError("lemevit_b200: this engine was closed (the module's weights changed or it was re-created); "
+                               "call model.native_engine(device) again")
 
     def __del__(self):  # pragma: no cover
         try:
@@ -72,16 +94,23 @@ class Engine:
     def set_chunk(self, images_per_chunk: int):
         _native.check(self.lib.lmv_plan_set_chunk(self._plan, int(images_per_chunk)))
         self.chunk = int(images_per_chunk)
-        self._graphs.clear()
+        self._invalidate_graphs()
 
     def set_debug_simt(self, enable: bool):
         _native.check(self.lib.lmv_plan_set_debug_simt(self._plan, int(bool(enable))))
-        self._graphs.clear()
+        self._invalidate_graphs()
+
+    def set_tap(self, stage: int, block: int, x_tokens: Optional[torch.Tensor] = None, c: Optional[torch.Tensor] = None):
+        """Test hook: copy (x tokens [B, N, C], c [B, M, C]) after block (stage, block) into the given bf16 buffers on every
+        following forward; stage < 0 turns it off.  The caller keeps the buffers alive."""
+        _native.check(self.lib.lmv_plan_set_tap(self._plan, int(stage), int(block), x_tokens.data_ptr() if x_tokens is not None else None,
+                                                c.data_ptr() if c is not None else None))
+        self._invalidate_graphs()
 
     def set_option(self, name: str, value: int):
         """Schedule A/B switches of the native plan (lmv_plan_set_option), e.g. ``fused_mlp``."""
         _native.check(self.lib.lmv_plan_set_option(self._plan, name.encode(), int(value)))
-        self._graphs.clear()
+        self._invalidate_graphs()
 
     def set_profile(self, enable: bool):
         """Per-kernel-class CUDA-event timing of every following forward (see lmv_plan_set_profile)."""
@@ -144,34 +173,59 @@ class Engine:
         return shapes
 
     # -- forward -----------------------------------------------------------------------------------
-    def forward_cls(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _use_lanes(self, B: int) -> int:
+        return self.lanes if (not self.backbone and self.lanes > 1 and B >= self.lane_min_batch and B % self.lanes == 0) else 1
+
+    def forward_cls(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None, *,
+                    meta_tokens: Optional[torch.Tensor] = None, features: Optional[torch.Tensor] = None,
+                    want_logits: bool = True, _ws=None) -> Optional[torch.Tensor]:
+        """logits[B, num_classes] (``want_logits``) and / or the pre-head features[B, C_last] (bf16, written into ``features``).
+        ``meta_tokens`` [B, M, C0]: the caller's own meta tokens (forward_features(x, c) of the reference); None = the model's."""
+        self._check_open()
         x = self._prep_input(x)
         B, _, H, W = x.shape
+        if meta_tokens is not None:
+            require_cuda(meta_tokens)
+            if tuple(meta_tokens.shape) != (B, self.cfg.queries_len, self.embed_dim[0]):
+                raise RuntimeError(f"expected meta tokens [{B}, {self.cfg.queries_len}, {self.embed_dim[0]}], got {tuple(meta_tokens.shape)}")
+            meta_tokens = meta_tokens.to(torch.bfloat16).contiguous()
+        if features is not None and (features.dtype != torch.bfloat16 or tuple(features.shape) != (B, self.embed_dim[-1])
+                                     or not features.is_contiguous()):
+            raise RuntimeError("features buffer must be a contiguous bf16 [B, embed_dim[-1]] tensor")
+        if want_logits and self.num_classes <= 0:
+            raise RuntimeError("lemevit_b200: the model has no classifier (num_classes == 0); use forward_features")
         with torch.cuda.device(self.device):
-            if out is None:
+            if want_logits and out is None:
                 out = torch.empty((B, self.num_classes), dtype=out_dtype, device=self.device)
-            lanes = self.lanes if (self.lanes > 1 and B >= self.lane_min_batch and B % self.lanes == 0) else 1
+            lanes = self._use_lanes(B)
             cur = torch.cuda.current_stream(self.device)
+
+            def launch(xi, ci, fi, oi, nb, ws, stream):
+                _native.check(self.lib.lmv_forward_cls_features(
+                    self._plan, xi.data_ptr(), _TORCH2LMV[x.dtype], nb, H, W, ci.data_ptr() if ci is not None else None,
+                    ws.data_ptr(), ws.numel(), fi.data_ptr() if fi is not None else None,
+                    oi.data_ptr() if oi is not None else None, _TORCH2LMV[oi.dtype] if oi is not None else _native.DTYPE_BF16,
+                    stream.cuda_stream))
+
             if lanes == 1:
-                ws = self._workspace(B, H, W)
-                _native.check(self.lib.lmv_forward_cls(self._plan, x.data_ptr(), _TORCH2LMV[x.dtype], B, H, W, ws.data_ptr(),
-                                                       ws.numel(), out.data_ptr(), _TORCH2LMV[out.dtype], cur.cuda_stream))
-                return out
+                ws = _ws[0] if _ws is not None else self._workspace(B, H, W)
+                launch(x, meta_tokens, features, out if want_logits else None, B, ws, cur)
+                return out if want_logits else None
             # independent sub-batches on concurrent streams: the images never interact (SURVEY.md §8e), so the tail / latency
             # bubbles of one lane's kernels are filled by the other lane's CTAs.  Fork / join through events (graph-capturable).
             nb = B // lanes
-            wss = self._lane_workspaces(nb, H, W, lanes)
+            wss = _ws if _ws is not None else self._lane_workspaces(nb, H, W, lanes)
             fork = torch.cuda.Event()
             fork.record(cur)
             for i, st in enumerate(self._lane_streams(lanes)):
                 st.wait_event(fork)
-                xi, oi = x[i * nb:(i + 1) * nb], out[i * nb:(i + 1) * nb]
-                _native.check(self.lib.lmv_forward_cls(self._plan, xi.data_ptr(), _TORCH2LMV[x.dtype], nb, H, W, wss[i].data_ptr(),
-                                                       wss[i].numel(), oi.data_ptr(), _TORCH2LMV[out.dtype], st.cuda_stream))
+                sl = slice(i * nb, (i + 1) * nb)
+                launch(x[sl], meta_tokens[sl] if meta_tokens is not None else None, features[sl] if features is not None else None,
+                       out[sl] if want_logits else None, nb, wss[i], st)
                 join = torch.cuda.Event()
                 join.record(st)
                 cur.wait_event(join)
-        return out
+        return out if want_logits else None
 
     def _lane_streams(self, lanes: int):
         if len(getattr(self, "_streams", [])) != lanes:
@@ -188,11 +242,12 @@ class Engine:
         return self._lane_ws
 
     def forward_features(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32,
-                         outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+                         outs: Optional[Sequence[torch.Tensor]] = None, _ws=None) -> List[torch.Tensor]:
+        self._check_open()
         x = self._prep_input(x)
         B, _, H, W = x.shape
         with torch.cuda.device(self.device):
-            ws = self._workspace(B, H, W)
+            ws = _ws[0] if _ws is not None else self._workspace(B, H, W)
             if outs is None:
                 outs = [torch.empty(s, dtype=out_dtype, device=self.device) for s in self.out_shapes(B, H, W)]
             ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
@@ -203,24 +258,48 @@ class Engine:
         return list(outs)
 
     # -- CUDA-graph replay of a fixed-shape forward ----------------------------------------------------
+    def _graph_workspaces(self, B: int, H: int, W: int) -> List[torch.Tensor]:
+        lanes = self._use_lanes(B)
+        need = int(self.lib.lmv_workspace_bytes(self._plan, B // lanes, H, W))
+        if need == 0:
+            raise RuntimeError(f"lemevit_b200: unsupported input shape {B}x{H}x{W}")
+        return [torch.empty(need, dtype=torch.uint8, device=self.device) for _ in range(lanes)]
+
     def graphed(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32):
-        """Capture the forward for x's shape once; returns (static_input, static_output(s), replay_fn)."""
+        """Capture the forward for x's shape once; returns (static_input, static_output(s), replay_fn).
+        The graph owns its workspace; at most ``max_graphs`` shapes stay captured (least recently used evicted).  replay_fn
+        raises once the engine was closed or the graph evicted — it never runs on memory that has been given back."""
+        self._check_open()
         x = self._prep_input(x)
         key = (tuple(x.shape), x.dtype, out_dtype)
         if key not in self._graphs:
+            B, _, H, W = x.shape
             static_x = x.clone()
             fwd = self.forward_features if self.backbone else self.forward_cls
             with torch.cuda.device(self.device):
+                wss = self._graph_workspaces(B, H, W)
                 side = torch.cuda.Stream(self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):
                     for _ in range(2):      # warm-up: builds the native schedule, sets kernel attributes
-                        static_out = fwd(static_x, out_dtype)
+                        static_out = fwd(static_x, out_dtype, _ws=wss)
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    static_out = fwd(static_x, out_dtype)
-            self._graphs[key] = (static_x, static_out, g)
-        static_x, static_out, g = self._graphs[key]
-        return static_x, static_out, g.replay
+                    static_out = fwd(static_x, out_dtype, _ws=wss)
+            while len(self._graphs) >= max(1, self.max_graphs):
+                torch.cuda.synchronize(self.device)
+                self._graphs.popitem(last=False)
+            self._graphs[key] = (static_x, static_out, g, wss, self.packed)
+        self._graphs.move_to_end(key)
+        static_x, static_out, g, _, _ = self._graphs[key]
+        gen = self._generation
+
+        def replay():
+            if self._closed or gen != self._generation or self._graphs.get(key, (None,) * 3)[2] is not g:
+                raise RuntimeError("lemevit_b200: this CUDA graph is stale (engine closed, options changed or graph evicted); "
+                                   "call graphed() again")
+            g.replay()
+
+        return static_x, static_out, replay

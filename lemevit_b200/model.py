@@ -9,6 +9,8 @@ as for the reference (569 tensors for Base, same names and shapes — SURVEY.md 
 """
 from __future__ import annotations
 
+import threading
+import warnings
 from typing import List, Optional, Sequence
 
 import torch
@@ -148,8 +150,11 @@ class LeMeViT(nn.Module):
         self.pre_logits = nn.Identity()
         self._build_head(num_classes)
         self.apply(self._init_weights)
-        self._engine: Optional[Engine] = None
-        self._engine_sig = None
+        # native engines, one per device: {str(device): (Engine, weight signature)}.  nn.DataParallel replicas (shallow copies
+        # of this module on other devices, reference validate.py:260-261) share this dict and its lock.
+        self._engines = {}
+        self._engines_lock = threading.Lock()
+        self._src_sig = None      # replicas: the weight signature of the module they were replicated from
         self.native_chunk = int(kwargs.pop("native_chunk", 0))
 
     # ---- reference surface -------------------------------------------------------------------------
@@ -181,38 +186,85 @@ class LeMeViT(nn.Module):
         self._drop_engine()
 
     # ---- native engine management ------------------------------------------------------------------
-    def _signature(self, device):
-        sig = [str(device), self.backbone_mode]
-        for t in list(self.parameters()) + list(self.buffers()):
-            sig.append((t.data_ptr(), t._version))
-        return tuple(sig)
+    def __setattr__(self, name, value):
+        # module surgery (model.head = ..., swapping a stage) changes the tensor set the signature walks
+        if isinstance(value, (nn.Module, nn.Parameter)) and "_sig_tensors" in self.__dict__:
+            self.__dict__["_sig_tensors"] = None
+        super().__setattr__(name, value)
+
+    def _signature(self):
+        """(storage address, version counter) of every parameter / buffer: changes on in-place edits (optimizer steps,
+        load_state_dict), on ``.to()`` and on re-assignment, which is when the packed weights must be rebuilt.  The tensor
+        list itself is cached (walking the module tree of ~570 tensors costs more than reading their versions).
+        A DataParallel replica answers with the signature of its source module: its own parameters are fresh broadcast
+        copies on every forward, their values are the source's."""
+        if self.__dict__.get("_src_sig") is not None:
+            return self.__dict__["_src_sig"]
+        ts = self.__dict__.get("_sig_tensors")
+        if ts is None:
+            ts = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_sig_tensors"] = ts
+        return (self.backbone_mode, len(ts), tuple([(t.data_ptr(), t._version) for t in ts]))
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__["_src_sig"] = self._signature()
+        replica.__dict__["_sig_tensors"] = None
+        return replica
 
     def _drop_engine(self):
-        if getattr(self, "_engine", None) is not None:
-            self._engine.close()
-        self._engine = None
-        self._engine_sig = None
+        """Close every native engine of this module (weights changed / module surgery)."""
+        engines = self.__dict__.get("_engines")
+        if engines:
+            with self._engines_lock:
+                for eng, _ in engines.values():
+                    eng.close()
+                engines.clear()
+        self.__dict__["_sig_tensors"] = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_sig_tensors"] = None      # .to() / .half() / .cuda() may replace Parameter objects
+        return super()._apply(fn, *args, **kwargs)
 
     def native_engine(self, device) -> Engine:
         """Pack the current weights (again, if they changed) and return the engine for `device`."""
-        sig = self._signature(device)
-        if self._engine is None or sig != self._engine_sig:
-            self._drop_engine()
-            self._engine = Engine(self.state_dict(), depth=self.depth, embed_dim=list(self.embed_dim),
-                                  mlp_ratios=self.mlp_ratios, attn_type=self.attn_type, head_dim=self.head_dim,
-                                  queries_len=self.queries_len, num_classes=self.num_classes, in_chans=self.in_chans,
-                                  backbone=self.backbone_mode, device=device, chunk=self.native_chunk)
-            self._engine_sig = sig
-        return self._engine
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key, sig = str(device), self._signature()
+        ent = self._engines.get(key)
+        if ent is not None and ent[1] == sig:
+            return ent[0]
+        with self._engines_lock:
+            ent = self._engines.get(key)
+            if ent is not None and ent[1] == sig:
+                return ent[0]
+            if ent is not None:
+                ent[0].close()
+                del self._engines[key]
+            if self.__dict__.get("_src_sig") is None:
+                # the weights of the source module changed: engines of other devices hold stale copies too
+                for k in [k for k, (e, sg) in self._engines.items() if sg != sig]:
+                    self._engines.pop(k)[0].close()
+            eng = Engine(self.state_dict(), depth=self.depth, embed_dim=list(self.embed_dim),
+                         mlp_ratios=self.mlp_ratios, attn_type=self.attn_type, head_dim=self.head_dim,
+                         queries_len=self.queries_len, num_classes=self.num_classes, in_chans=self.in_chans,
+                         backbone=self.backbone_mode, device=device, chunk=self.native_chunk)
+            self._engines[key] = (eng, sig)
+        return eng
 
     def __deepcopy__(self, memo):
-        # ModelEmaV2 deep-copies the model (reference main.py:316): copy parameters, never the native handle
+        # ModelEmaV2 deep-copies the model (reference main.py:316): copy parameters, never the native handles
         import copy
         cls = self.__class__
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engine", "_engine_sig"):
+            if k == "_engines":
+                new.__dict__[k] = {}
+            elif k == "_engines_lock":
+                new.__dict__[k] = threading.Lock()
+            elif k in ("_sig_tensors", "_src_sig"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
@@ -220,28 +272,57 @@ class LeMeViT(nn.Module):
 
     def __getstate__(self):
         d = dict(self.__dict__)
-        d["_engine"] = None
-        d["_engine_sig"] = None
+        d["_engines"] = {}
+        d["_engines_lock"] = None
+        d["_sig_tensors"] = None
+        d["_src_sig"] = None
         return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.__dict__["_engines_lock"] = threading.Lock()
 
     def _out_dtype(self, x):
         pd = self.meta_tokens.dtype
         return torch.bfloat16 if pd == torch.bfloat16 else torch.float32
 
+    _warned_grad = False
+
+    def _check_inference(self):
+        """The native path is the eval-mode forward (BatchNorm running statistics folded into the convolutions, DropPath and
+        dropout absent, no autograd graph).  In train mode the reference would use batch statistics, update the running
+        stats and apply stochastic depth (models/lemevit.py:531,700-703) — refusing is the only answer that cannot silently
+        give different numbers."""
+        if self.training:
+            raise RuntimeError("lemevit_b200 is inference-only: forward() implements the eval-mode LeMeViT forward on native sm_100a "
+                               "kernels (no BatchNorm batch statistics, no DropPath, no autograd). Call model.eval() first; "
+                               "train with the reference implementation and load the state_dict here.")
+        if torch.is_grad_enabled() and not LeMeViT._warned_grad and any(p.requires_grad for p in self.parameters()):
+            LeMeViT._warned_grad = True
+            warnings.warn("lemevit_b200: forward() runs outside autograd — the output carries no grad_fn even though gradients are "
+                          "enabled; wrap inference in torch.no_grad() (this warning is shown once).", stacklevel=3)
+
     # ---- forward -----------------------------------------------------------------------------------
     def forward_features(self, x, c=None):
-        """Pre-head features [B, C_last] (reference :809-829).  ``c`` is accepted for signature
-        compatibility; the native path always starts from ``meta_tokens`` like ``forward`` does (:833)."""
-        raise NotImplementedError("forward_features() of the classification model is fused into forward(); "
-                                  "use forward(x), or the backbone class for multi-scale feature maps")
+        """Pre-head features ``[B, embed_dim[-1]]`` = mean_HW(BN(x)) + mean_M(LN(c)) (reference :809-829).
+        ``c``: meta tokens ``[B, queries_len, embed_dim[0]]`` as the reference takes them (they go through
+        ``meta_token_downsample[0]`` first, :813); None = ``self.meta_tokens`` broadcast over the batch, which is what
+        ``forward`` passes (:833) and is constant-folded at weight-pack time."""
+        require_cuda(x)
+        self._check_inference()
+        eng = self.native_engine(x.device)
+        feat = torch.empty((x.shape[0], self.embed_dim[-1]), dtype=torch.bfloat16, device=x.device)
+        eng.forward_cls(x, meta_tokens=c, features=feat, want_logits=False)
+        dt = self._out_dtype(x)
+        return feat if dt == torch.bfloat16 else feat.to(dt)
 
     def forward(self, x):
         require_cuda(x)
+        self._check_inference()
         if self.num_classes <= 0:
-            raise NotImplementedError("num_classes == 0 is not implemented on the native path")
+            return self.forward_features(x)      # head = nn.Identity (reference :786, reset_classifier(0))
         eng = self.native_engine(x.device)
-        y = eng.forward_cls(x, out_dtype=torch.float32)
-        return y.to(self._out_dtype(x)) if self._out_dtype(x) != torch.float32 else y
+        return eng.forward_cls(x, out_dtype=self._out_dtype(x))      # the head GEMM writes bf16 / fp32 logits directly
 
 
 # ---- model variants (reference models/lemevit.py:845-932) --------------------------------------------

@@ -13,9 +13,9 @@ All folds are exact algebra done once in float64 on the host, then cast ONCE to 
 ORDER of the packed list (checked entry by entry by ``lmv_plan_create`` in csrc/api.cu):
 
   stem1_w bf16[C0/2, Kp0]  stem1_b f32[C0/2]  stem2_w bf16[C0, 9*C0/2]  stem2_b f32[C0]  c0_init bf16[M, C0]
-  for each stage i:
+  for each stage i (Cp = C(i-1), C0 for i = 0):
       if i > 0:  [ds_w bf16[Ci, 9*Cp], ds_b f32[Ci]]   (absent when stage i-1 is 'C': nn.Identity, :711-712)
-                 md_w0 bf16[4Cp,Cp] md_b0 f32 md_g1 f32 md_be1 f32 md_w3 bf16[Ci,4Cp] md_b3 f32 md_g4 f32 md_be4 f32
+      md_w0 bf16[4Cp,Cp] md_b0 f32 md_g1 f32 md_be1 f32 md_w3 bf16[Ci,4Cp] md_b3 f32 md_g4 f32 md_be4 f32
       for each block:  dw_w f32[9,C] dw_b f32[C]
           'C': q_w q_b q_cs kv_w kv_b kv_cs proj_w proj_b
           'D': qkv1_w qkv1_b qkv1_cs qkv2_w qkv2_b qkv2_cs proj_x_w proj_x_b proj_c_w proj_c_b
@@ -94,15 +94,15 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], *, depth: Sequence[int], embed_
     # ---- stages
     for i, kind in enumerate(attn_type):
         C = E[i]
-        if i > 0:
-            if attn_type[i - 1] != "C":
-                w, b = _fold_conv_bn(sd, f"downsample_layers.{i}.0", f"downsample_layers.{i}.1")
-                h(w.permute(0, 2, 3, 1).reshape(C, 9 * E[i - 1])); f(b)
-            p = f"meta_token_downsample.{i}."
-            h(_d(sd[p + "0.weight"])); f(_d(sd[p + "0.bias"]))
-            f(_d(sd[p + "1.weight"])); f(_d(sd[p + "1.bias"]))
-            h(_d(sd[p + "3.weight"])); f(_d(sd[p + "3.bias"]))
-            f(_d(sd[p + "4.weight"])); f(_d(sd[p + "4.bias"]))
+        if i > 0 and attn_type[i - 1] != "C":
+            w, b = _fold_conv_bn(sd, f"downsample_layers.{i}.0", f"downsample_layers.{i}.1")
+            h(w.permute(0, 2, 3, 1).reshape(C, 9 * E[i - 1])); f(b)
+        # meta_token_downsample[i]; [0] is only executed for caller-supplied meta tokens (forward_features(x, c))
+        p = f"meta_token_downsample.{i}."
+        h(_d(sd[p + "0.weight"])); f(_d(sd[p + "0.bias"]))
+        f(_d(sd[p + "1.weight"])); f(_d(sd[p + "1.bias"]))
+        h(_d(sd[p + "3.weight"])); f(_d(sd[p + "3.bias"]))
+        f(_d(sd[p + "4.weight"])); f(_d(sd[p + "4.bias"]))
         for j in range(depth[i]):
             p = f"stages.{i}.{j}."
             dw = _d(sd[p + "pos_embed.weight"]).reshape(C, 9).t().clone()   # [9, C], tap = ky*3 + kx

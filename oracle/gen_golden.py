@@ -32,7 +32,20 @@ CLS_CASES = [
 SEG_CASES = [
     ("lemevit_micro", 2, 64, 64, 0),
     ("lemevit_base", 1, 256, 256, 0),
+    ("lemevit_base", 1, 512, 512, 0),     # BASELINE configs[4] resolution: N = 16384 / 4096 / 1024 / 256 tokens
 ]
+# forward_features(x, c) of the classification model (models/lemevit.py:809-829), with the model's own meta tokens and with
+# caller-supplied ones
+FEAT_CASES = [
+    ("lemevit_micro", 2, 64, 64, 2),
+    ("lemevit_tiny", 2, 224, 224, 2),
+]
+
+
+def custom_meta_tokens(cfg: O.OracleConfig, B: int, seed: int) -> torch.Tensor:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(4242 + seed)
+    return torch.randn((B, cfg.queries_len, cfg.embed_dim[0]), generator=g)
 
 
 def _build_ref_cls(ref, cfg: O.OracleConfig):
@@ -80,6 +93,20 @@ def main():
         path = os.path.join(OUT, f"cls_{name}_b{B}_{H}x{W}_s{seed}.npz")
         np.savez_compressed(path, **payload)
         print("wrote", path, os.path.getsize(path) // 1024, "KiB", "max|logit|", float(logits.abs().max()))
+
+    for name, B, H, W, seed in FEAT_CASES:
+        cfg = O.VARIANTS[name]
+        sd = Wt.make_state_dict(cfg, seed)
+        model = _build_ref_cls(ref, cfg)
+        model.load_state_dict(sd)
+        x = Wt.make_input(B, H, W, seed)
+        c_own = model.meta_tokens.repeat(B, 1, 1)                 # what LeMeViT.forward passes (:833)
+        c_custom = custom_meta_tokens(cfg, B, seed)
+        path = os.path.join(OUT, f"feat_{name}_b{B}_{H}x{W}_s{seed}.npz")
+        np.savez_compressed(path, fingerprint=np.float64(Wt.fingerprint(sd)),
+                            features_own=model.forward_features(x, c_own).numpy(),
+                            features_custom=model.forward_features(x, c_custom).numpy())
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
     for name, B, H, W, seed in SEG_CASES:
         cfg = O.VARIANTS[name]

@@ -228,10 +228,12 @@ def meta_downsample(sd, i: int, c: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------------
 # whole model
 # --------------------------------------------------------------------------------------------
-def run_stages(sd, cfg: OracleConfig, x: Tensor, backbone: bool, taps: Optional[dict] = None):
-    """Stage loop of forward_features (:809-814).  Returns (x, c, [x after each stage])."""
+def run_stages(sd, cfg: OracleConfig, x: Tensor, backbone: bool, taps: Optional[dict] = None, c: Optional[Tensor] = None):
+    """Stage loop of forward_features(x, c) (:809-814).  Returns (x, c, [x after each stage]).
+    ``c`` None: the model's own meta tokens, as LeMeViT.forward supplies them (:833)."""
     B = x.shape[0]
-    c = sd["meta_tokens"].unsqueeze(0).expand(B, -1, -1)                  # :833 meta_tokens.repeat(B,1,1)
+    if c is None:
+        c = sd["meta_tokens"].unsqueeze(0).expand(B, -1, -1)              # :833 meta_tokens.repeat(B,1,1)
     outs = []
     for i, kind in enumerate(cfg.attn_type):
         x = downsample(sd, i, x, cfg.attn_type)
@@ -254,14 +256,20 @@ def run_stages(sd, cfg: OracleConfig, x: Tensor, backbone: bool, taps: Optional[
     return x, c, outs
 
 
-def forward_cls(sd, cfg: OracleConfig, x: Tensor, taps: Optional[dict] = None) -> Tensor:
-    """LeMeViT.forward (:831-836) + forward_features tail (:815-829) of the classification model."""
-    x, c, _ = run_stages(sd, cfg, x, backbone=False, taps=taps)
+def forward_features_cls(sd, cfg: OracleConfig, x: Tensor, c: Optional[Tensor] = None, taps: Optional[dict] = None) -> Tensor:
+    """LeMeViT.forward_features(x, c) of the classification model (:809-829): pre-head features [B, C_last]."""
+    x, c, _ = run_stages(sd, cfg, x, backbone=False, taps=taps, c=c)
     x = batch_norm_eval(x, sd["norm.weight"], sd["norm.bias"], sd["norm.running_mean"], sd["norm.running_var"])  # :815
     c = layer_norm(c, sd["norm_c.weight"], sd["norm_c.bias"], 1e-5)                                              # :818
     f = x.flatten(2).mean(-1) + c.transpose(-2, -1).mean(-1)                                                     # :825-827
     if taps is not None:
         taps["features"] = f
+    return f
+
+
+def forward_cls(sd, cfg: OracleConfig, x: Tensor, taps: Optional[dict] = None) -> Tensor:
+    """LeMeViT.forward (:831-836): forward_features on the model's own meta tokens, then the head."""
+    f = forward_features_cls(sd, cfg, x, None, taps)
     return linear(f, sd["head.weight"], sd["head.bias"])                                                         # :835
 
 

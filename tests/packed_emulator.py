@@ -55,7 +55,8 @@ def _posembed(x_tok, H, W, dw_w, dw_b):
     return y.flatten(2).transpose(1, 2)
 
 
-def forward(packed, x, *, depth, embed_dim, attn_type, head_dim, queries_len, num_classes, in_chans, backbone):
+def forward(packed, x, *, depth, embed_dim, attn_type, head_dim, queries_len, num_classes, in_chans, backbone,
+            c_in=None, features=False):
     it = iter([t.detach().cpu().double() for t in packed])
     nx = lambda: next(it)
     M = queries_len
@@ -67,16 +68,18 @@ def forward(packed, x, *, depth, embed_dim, attn_type, head_dim, queries_len, nu
     y = _gelu(F.conv2d(x, w4, stem1_b, stride=2, padding=1))
     H1, W1 = y.shape[2], y.shape[3]
     xt, H, W = _conv_tokens(y.flatten(2).transpose(1, 2), H1, W1, stem2_w, stem2_b)
-    c = c0.unsqueeze(0).expand(B, -1, -1)
+    c = c0.unsqueeze(0).expand(B, -1, -1)   # pack-time constant meta_ds_0(meta_tokens) unless the caller brings its own c
     outs = []
     for i, kind in enumerate(attn_type):
         C = embed_dim[i]
         heads = C // head_dim
-        if i > 0:
-            if attn_type[i - 1] != "C":
-                ds_w, ds_b = nx(), nx()
-                xt, H, W = _conv_tokens(xt, H, W, ds_w, ds_b)
-            w0, b0, g1, be1, w3, b3, g4, be4 = [nx() for _ in range(8)]
+        if i > 0 and attn_type[i - 1] != "C":
+            ds_w, ds_b = nx(), nx()
+            xt, H, W = _conv_tokens(xt, H, W, ds_w, ds_b)
+        w0, b0, g1, be1, w3, b3, g4, be4 = [nx() for _ in range(8)]
+        if i == 0 and c_in is not None:
+            c = c_in.double()
+        if i > 0 or c_in is not None:
             c = _gelu(_norm(c @ w0.t() + b0, 1e-5) * g1 + be1)
             c = _norm(c @ w3.t() + b3, 1e-5) * g4 + be4
         N = H * W
@@ -126,7 +129,10 @@ def forward(packed, x, *, depth, embed_dim, attn_type, head_dim, queries_len, nu
         return outs
     bn_s, bn_b, g, be = nx(), nx(), nx(), nx()
     feat = bn_s * xt.mean(1) + bn_b + (_norm(c, 1e-5) * g + be).mean(1)
-    hw, hb = nx(), nx()
+    if num_classes > 0:
+        hw, hb = nx(), nx()
     rest = list(it)
     assert not rest, f"{len(rest)} packed tensors were not consumed"
+    if features or num_classes <= 0:
+        return feat
     return feat @ hw.t() + hb

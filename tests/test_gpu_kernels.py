@@ -87,6 +87,32 @@ def test_linear_layernorm_fold(M, N, K, gelu, simt):
     assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999, G.describe_mismatch(out.float(), ref, TOL)
 
 
+@pytest.mark.parametrize("M,N,K,gelu", [(1000, 288, 96, False), (424, 1536, 384, True), (300, 576, 192, False)])
+@pytest.mark.parametrize("ratio", [30.0, 100.0, 300.0])
+def test_linear_layernorm_fold_large_row_offsets(M, N, K, gelu, ratio):
+    """Trained ViTs carry massive-activation channels / large per-row offsets: rows whose |mean| is `ratio` x their std.  The fold
+    computes var = E[y^2] - mu^2 and r (acc - mu colsum) in fp32 from the bf16 rows (gemm.cu), both cancellation-prone; checked
+    against fp64 LayerNorm of the same bf16-rounded rows (the information the reference's bf16 path sees, too)."""
+    std = 0.7
+    sign = torch.where(torch.rand(M, 1, device="cuda") < 0.5, -1.0, 1.0)
+    y = G.bf(torch.randn(M, K, device="cuda") * std + sign * ratio * std)
+    yd = y.double()
+    got_ratio = float((yd.mean(-1).abs() / yd.std(-1)).median())
+    assert got_ratio > 0.8 * ratio
+    W = _rand(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    stats = torch.stack([y.float().sum(-1), (y.float() ** 2).sum(-1)], dim=1).contiguous()
+    colsum = W.float().sum(-1).contiguous()
+    ln = torch.nn.functional.layer_norm(yd, (K,), eps=1e-6)
+    ref = ln @ W.double().t() + bias.double()
+    if gelu:
+        ref = 0.5 * ref * (1.0 + torch.erf(ref / math.sqrt(2.0)))
+    out = G.linear_fused(y, W, bias, gelu=gelu, ln_stats=stats, ln_colsum=colsum, ln_eps=1e-6)
+    err = G.rel_err(out, ref)
+    print(f"mean/std {got_ratio:.0f}: rel err {err:.5f}")
+    assert err < TOL and G.cosine(out, ref) > 0.9999, G.describe_mismatch(out.float(), ref.float(), TOL)
+
+
 MLP_SHAPES = [(1000, 96, 384), (777, 192, 768), (300, 64, 256), (260, 160, 640), (130, 128, 512), (129, 192, 1280),
               (40000, 96, 384), (25000, 192, 768)]
 

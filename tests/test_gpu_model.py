@@ -168,6 +168,157 @@ def test_full_size_batch_properties():
     assert G.rel_err(y[:4].float().cpu(), ref) <= TOL_MODEL
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "feat_*.npz"))), ids=os.path.basename)
+def test_forward_features_against_reference_golden(path):
+    """LeMeViT.forward_features(x, c) (models/lemevit.py:809-829): pre-head features with the model's own meta tokens and with
+    caller-supplied ones (run through meta_token_downsample[0] on the device), against outputs of the untouched reference."""
+    from oracle.gen_golden import custom_meta_tokens
+    name, B, H, W, seed = re.match(r"feat_(lemevit_\w+?)_b(\d+)_(\d+)x(\d+)_s(\d+)\.npz", os.path.basename(path)).groups()
+    B, H, W, seed = int(B), int(H), int(W), int(seed)
+    g = np.load(path)
+    cfg, sd, m = _build(name, seed)
+    x = Wt.make_input(B, H, W, seed).cuda().to(torch.bfloat16)
+    own = m.forward_features(x).float().cpu()
+    ref_own = torch.from_numpy(g["features_own"])
+    assert own.shape == ref_own.shape and G.rel_err(own, ref_own) <= TOL_MODEL and G.cosine(own, ref_own) > 0.9995
+    # passing meta_tokens.repeat(B, 1, 1) explicitly (what LeMeViT.forward does, :833) takes the run-time meta_ds_0 path
+    explicit = m.forward_features(x, m.meta_tokens.detach().unsqueeze(0).repeat(B, 1, 1)).float().cpu()
+    assert G.rel_err(explicit, ref_own) <= TOL_MODEL
+    c = custom_meta_tokens(cfg, B, seed).cuda()
+    custom = m.forward_features(x, c).float().cpu()
+    ref_custom = torch.from_numpy(g["features_custom"])
+    assert G.rel_err(custom, ref_custom) <= TOL_MODEL and G.cosine(custom, ref_custom) > 0.9995
+    # the head on top of forward_features is forward (:831-836)
+    y = m(x).float().cpu()
+    ref_y = O.linear(ref_own, sd["head.weight"], sd["head.bias"])
+    assert G.rel_err(y, ref_y) <= TOL_MODEL
+
+
+def test_num_classes_zero_and_reset_classifier():
+    """num_classes=0 / reset_classifier(0): head = nn.Identity, forward returns the features (models/lemevit.py:786,805-807)."""
+    cfg, sd, m = _build("lemevit_micro", 2, num_classes=0)
+    assert isinstance(m.head, torch.nn.Identity)
+    x = Wt.make_input(2, 64, 64, 2).cuda().to(torch.bfloat16)
+    f = m(x)
+    assert f.shape == (2, cfg.embed_dim[-1])
+    ref = O.forward_features_cls(sd, cfg, x.float().cpu())
+    assert G.rel_err(f.float().cpu(), ref) <= TOL_MODEL
+    cfg, sd, m2 = _build("lemevit_micro", 2)
+    y = m2(x)
+    m2.reset_classifier(0)
+    assert torch.equal(m2(x), f) and y.shape == (2, 1000)
+    m2.reset_classifier(10)
+    m2 = m2.to("cuda", torch.bfloat16)
+    assert m2(x).shape == (2, 10)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "cls_lemevit_micro_*.npz"))), ids=os.path.basename)
+def test_block_taps_against_reference_golden(path):
+    """Per-block parity: (x, c) after EVERY LeMeBlock against the reference's forward-hook taps stored in the micro goldens
+    (C block: x unchanged, c updated; D blocks: both; S blocks: both in the classification model)."""
+    name, B, H, W, seed = _parse(path)
+    g = np.load(path)
+    cfg, sd, m = _build(name, seed)
+    x = Wt.make_input(B, H, W, seed).cuda().to(torch.bfloat16)
+    eng = m.native_engine(x.device)
+    worst = 0.0
+    for i, depth in enumerate(cfg.depth):
+        for j in range(depth):
+            ref_x = torch.from_numpy(g[f"tap/stages.{i}.{j}.x"])          # [B, C, h, w]
+            ref_c = torch.from_numpy(g[f"tap/stages.{i}.{j}.c"])          # [B, M, C]
+            Bc, C, h, w = ref_x.shape
+            tx = torch.zeros(Bc, h * w, C, dtype=torch.bfloat16, device="cuda")
+            tc = torch.zeros(Bc, cfg.queries_len, C, dtype=torch.bfloat16, device="cuda")
+            eng.set_tap(i, j, tx, tc)
+            m(x)
+            torch.cuda.synchronize()
+            got_x = tx.float().cpu().transpose(1, 2).reshape(Bc, C, h, w)
+            ex, ec = G.rel_err(got_x, ref_x), G.rel_err(tc.float().cpu(), ref_c)
+            worst = max(worst, ex, ec)
+            assert ex <= 2e-2 and ec <= 2e-2, f"block ({i},{j}): x err {ex:.4f} c err {ec:.4f}"
+            assert G.cosine(got_x, ref_x) > 0.9995 and G.cosine(tc.float().cpu(), ref_c) > 0.9995
+    eng.set_tap(-1, -1)
+    print(f"worst block-tap rel err {worst:.4f}")
+
+
+def test_base_b256_two_lanes_against_oracle():
+    """The benched shape (Base, 224x224, batch 256 = two concurrent sub-batch lanes): four distinct images embedded at batch
+    positions that land in both lanes are compared with the fp32 oracle; the filler images are replicas."""
+    cfg, sd, m = _build("lemevit_base", 0)
+    base = Wt.make_input(4, 224, 224, 11)
+    pos = [0, 77, 128, 255]                      # lane 0: 0, 77; lane 1: 128, 255
+    x = Wt.make_input(1, 224, 224, 12).repeat(256, 1, 1, 1)
+    for k, p in enumerate(pos):
+        x[p] = base[k]
+    xg = x.cuda().to(torch.bfloat16)
+    eng = m.native_engine(xg.device)
+    y = m(xg)
+    assert eng.lanes == 2 and eng._use_lanes(256) == 2
+    ref = O.forward_cls(sd, cfg, base)
+    got = y[pos].float().cpu()
+    assert G.rel_err(got, ref) <= TOL_MODEL, f"rel err {G.rel_err(got, ref)}"
+    assert torch.equal(got.argmax(-1), ref.argmax(-1))
+    assert torch.equal(y[1], y[2]) and torch.equal(y[1], y[200])     # replicas agree bit for bit across lanes
+    assert torch.equal(m(xg[pos])[1], y[77])                         # and with a small single-lane batch
+
+
+def test_stale_graph_replay_raises_instead_of_touching_freed_memory():
+    """a captured graph owns its workspace and dies with the engine — replay callables must refuse afterwards."""
+    cfg, sd, m = _build("lemevit_micro", 6)
+    x = Wt.make_input(2, 64, 64, 6).cuda().to(torch.bfloat16)
+    eng = m.native_engine(x.device)
+    sx, sy, replay = eng.graphed(x)
+    replay()
+    y0 = sy.clone()
+    big = Wt.make_input(8, 128, 128, 6).cuda().to(torch.bfloat16)
+    m(big)                                   # a larger eager forward reallocates the shared workspace ...
+    replay()                                 # ... the graph has its own
+    assert torch.equal(sy, y0)
+    with torch.no_grad():
+        m.head.bias.add_(1.0)                # weights changed -> the engine is rebuilt on the next forward
+    m(x)
+    with pytest.raises(RuntimeError, match="stale"):
+        replay()
+    eng2 = m.native_engine(x.device)
+    eng2.max_graphs = 1
+    _, _, r1 = eng2.graphed(x)
+    _, _, r2 = eng2.graphed(big)             # evicts the first graph
+    r2()
+    with pytest.raises(RuntimeError, match="stale"):
+        r1()
+
+
+def test_unsupported_attention_shape_is_an_error_not_a_simt_fallback():
+    """No silent drop to the SIMT cross-check kernels: queries_len = 48 with 6 heads gives heads * Lq = 288 > 128
+    rows for the meta-token kernel and Lk = 3136 keys > the x-branch kernel's limit."""
+    m = L.LeMeViT(depth=[1, 1, 0, 0, 0], embed_dim=[192, 192, 192, 192, 192], head_dim=32, queries_len=48, attn_type=["C", "D", "D", "D", "D"])
+    m = m.to("cuda", torch.bfloat16)
+    m.train(False)
+    x = torch.randn(1, 3, 224, 224, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no tcgen05 kernel covers"):
+        m(x)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_data_parallel_two_devices_single_process():
+    """nn.DataParallel as reference validate.py:260-261: replicas on cuda:0 and cuda:1 in ONE process — kernel function attributes
+    and the SM count are per device, engines are per device and replicas reuse them across forwards."""
+    cfg, sd, m = _build("lemevit_tiny", 0)
+    x = Wt.make_input(8, 224, 224, 0).cuda().to(torch.bfloat16)
+    y_single = m(x)
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    y = dp(x)
+    assert y.device == x.device and torch.equal(y, y_single)
+    e1 = m._engines["cuda:1"][0]
+    y2 = dp(x)
+    assert torch.equal(y2, y_single) and m._engines["cuda:1"][0] is e1      # no re-pack on the second forward
+    m1 = getattr(L, "lemevit_tiny")().to("cuda:1", torch.bfloat16)
+    m1.load_state_dict(sd)
+    m1 = m1.to("cuda:1", torch.bfloat16)
+    m1.train(False)
+    assert torch.equal(m1(x.to("cuda:1")).cpu(), y_single.cpu())          # a model living on cuda:1 after cuda:0 was used
+
+
 def test_cpu_input_fails_loudly():
     cfg, sd, m = _build("lemevit_micro", 0)
     with pytest.raises(RuntimeError, match="CUDA"):

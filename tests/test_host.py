@@ -64,18 +64,61 @@ class _FakeRegistry:
 def test_backbone_registers_with_openmmlab_style_registries(monkeypatch):
     import types
     import lemevit_b200 as L
-    reg = _FakeRegistry()
+    regs = {}
     for pkg in ("mmseg", "mmdet"):
         root, models, builder = types.ModuleType(pkg), types.ModuleType(pkg + ".models"), types.ModuleType(pkg + ".models.builder")
-        builder.BACKBONES = reg
+        regs[pkg] = builder.BACKBONES = _FakeRegistry()
         monkeypatch.setitem(sys.modules, pkg, root)
         monkeypatch.setitem(sys.modules, pkg + ".models", models)
         monkeypatch.setitem(sys.modules, pkg + ".models.builder", builder)
     assert L.register_backbones() == ["mmseg", "mmdet"]
-    assert reg.modules["LeMeViT"] is L.LeMeViTBackbone
-    bb = reg.modules["LeMeViT"](depth=[1, 1, 1, 1, 1], embed_dim=[32, 32, 64, 96, 128], head_dim=32, queries_len=16, frozen_stages=-1)
+    assert regs["mmseg"].modules["LeMeViT"] is L.LeMeViTBackbone
+    kw = dict(depth=[1, 1, 1, 1, 1], embed_dim=[32, 32, 64, 96, 128], head_dim=32, queries_len=16)
+    bb = regs["mmseg"].modules["LeMeViT"](frozen_stages=-1, **kw)
     assert not any(k.startswith("head.") for k in bb.state_dict())               # backbone copies have no classifier
     assert bb.train(True) is None                                                 # the reference's train() returns None (:874-882)
+    assert all(m.training for m in bb.modules() if isinstance(m, torch.nn.BatchNorm2d))    # mmseg: freeze_bn = False (:875)
+    # mmdet copy (object_detection/mmdet/models/backbones/lemevit.py:827-842): frozen_stages is a list of stage indices, train()
+    # strips requires_grad from those stages and keeps every BatchNorm2d / LayerNorm in eval mode
+    det_cls = regs["mmdet"].modules["LeMeViT"]
+    assert issubclass(det_cls, L.LeMeViTBackbone) and det_cls.__name__ == "LeMeViT"
+    det = det_cls(frozen_stages=[0, 1], **kw)
+    assert det.train(True) is None and det.training
+    assert not any(m.training for m in det.modules() if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.LayerNorm)))
+    assert not any(p.requires_grad for i in (0, 1) for p in det.stages[i].parameters())
+    assert all(p.requires_grad for p in det.stages[2].parameters())
+
+
+def test_change_detection_entrypoints(tmp_path):
+    """change_detection/models/lemevit.py:874-963 + networks.py:365-368: lemevit_small(pretrained=path) builds the backbone
+    and loads the checkpoint inside the constructor ('model' / 'state_dict' / 'state_dict_ema' / bare, 'backbone.' prefix stripped)."""
+    from lemevit_b200 import change_detection as CD
+    import lemevit_b200 as L
+    src = CD.lemevit_tiny()
+    assert isinstance(src, L.LeMeViTBackbone) and src.frozen_stages == [-1]
+    sd = {"backbone." + k: torch.randn_like(v) if v.is_floating_point() else v for k, v in src.state_dict().items()}
+    path = str(tmp_path / "ckpt.pth")
+    torch.save({"state_dict": sd}, path)
+    m = CD.lemevit_tiny(pretrained=path)
+    got = m.state_dict()
+    assert all(torch.equal(got[k[9:]], v) for k, v in sd.items())
+    assert set(CD.__all__) == {"lemevit_tiny", "lemevit_small", "lemevit_base"}
+
+
+def test_training_mode_is_refused_not_silently_different():
+    """The native path is the eval-mode forward: in train mode the reference uses BatchNorm batch statistics and DropPath, so
+    forward() must refuse instead of returning eval numbers.  Checked before any device work."""
+    import lemevit_b200 as L
+    m = L.LeMeViT(depth=[1, 1, 1, 1, 1], embed_dim=[32, 32, 64, 96, 128], head_dim=32, queries_len=16)
+    assert m.training
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m._check_inference()
+    m.eval()
+    with torch.enable_grad(), pytest.warns(UserWarning, match="outside autograd"):
+        L.LeMeViT._warned_grad = False
+        m._check_inference()
+    with torch.no_grad():
+        m._check_inference()
 
 
 def _free_port():

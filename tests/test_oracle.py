@@ -72,6 +72,24 @@ def test_backbone_matches_reference_golden(path):
             assert np.abs(s - g[f"out{i}_sample"]).max() <= 2e-4 * np.abs(g[f"out{i}_sample"]).max()
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "feat_*.npz"))), ids=os.path.basename)
+def test_oracle_forward_features_against_reference_golden(path):
+    """forward_features(x, c) of the classification model (models/lemevit.py:809-829): own and caller-supplied meta tokens."""
+    from oracle.gen_golden import custom_meta_tokens
+    name, B, H, W, seed = re.match(r"feat_(lemevit_\w+?)_b(\d+)_(\d+)x(\d+)_s(\d+)\.npz", os.path.basename(path)).groups()
+    B, H, W, seed = int(B), int(H), int(W), int(seed)
+    g = np.load(path)
+    cfg = O.VARIANTS[name]
+    sd = Wt.make_state_dict(cfg, seed)
+    assert Wt.fingerprint(sd) == pytest.approx(float(g["fingerprint"]), rel=1e-12)
+    x = Wt.make_input(B, H, W, seed)
+    own = O.forward_features_cls(sd, cfg, x)
+    custom = O.forward_features_cls(sd, cfg, x, custom_meta_tokens(cfg, B, seed))
+    assert np.abs(own.numpy() - g["features_own"]).max() <= 2e-4 * np.abs(g["features_own"]).max()
+    assert np.abs(custom.numpy() - g["features_custom"]).max() <= 2e-4 * np.abs(g["features_custom"]).max()
+    assert np.abs(g["features_custom"] - g["features_own"]).max() > 1e-2      # the meta tokens do reach the features
+
+
 def test_flop_accounting_matches_survey():
     # SURVEY.md §8(d): 3.892 / 7.912 / 23.481 GFLOP per image at 224^2, 138.468 for base@512 backbone
     f = lambda n, s, b=False: O.algorithmic_flops_per_image(O.VARIANTS[n], s, s, backbone=b) / 1e9

@@ -44,6 +44,15 @@ def test_packed_forward_matches_oracle(name, H, W, backbone, monkeypatch):
     else:
         ref = O.forward_cls(sd64, cfg, x.double())
         assert (y - ref).abs().max() < 1e-9 * max(1.0, ref.abs().max())
+        # forward_features(x, c) (models/lemevit.py:809-829): pre-head features, with the model's own and with caller-supplied
+        # meta tokens (the latter run meta_token_downsample[0] at run time instead of the pack-time constant)
+        f = E.forward(packed, x, head_dim=cfg.head_dim, queries_len=cfg.queries_len, features=True, **kw)
+        ref_f = O.forward_features_cls(sd64, cfg, x.double())
+        assert (f - ref_f).abs().max() < 1e-9 * max(1.0, ref_f.abs().max())
+        c = torch.randn(x.shape[0], cfg.queries_len, cfg.embed_dim[0], dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+        f = E.forward(packed, x, head_dim=cfg.head_dim, queries_len=cfg.queries_len, features=True, c_in=c, **kw)
+        ref_f = O.forward_features_cls(sd64, cfg, x.double(), c)
+        assert (f - ref_f).abs().max() < 1e-9 * max(1.0, ref_f.abs().max())
 
 
 @pytest.mark.parametrize("name", ["lemevit_micro", "lemevit_tiny", "lemevit_small", "lemevit_base"])
