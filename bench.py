@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: images/sec of the LeMeViT-Base 224x224 bf16 forward (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model lemevit_base] [--batch 256]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload base256|tiny256|small512|base512seg]
 
 A *step* is one forward pass of the hot path over one synthetic batch (BASELINE.json configs[3]:
 256 images per GPU, weak scaling, batch sharded over ranks with no data-path collective).  One process
@@ -13,9 +13,12 @@ from the environment).  Rank 0 prints ONE JSON line.
                step uploads its batch (H2D) and reads the logits back (D2H) inside the timed region
   roofline     dominant kernel class (tcgen05 GEMM): algorithmic FLOPs / CUDA-event device time,
                measured live with the native per-launch event profile, against MEASURED_PEAKS.json
-  cpu_baseline the CPU port of the reference forward (oracle/, torch fp32, all host threads) on a
+  cpu_baseline the reference's own forward on the host cores (the UNMODIFIED reference module when its sources are
+               available — mount or baseline/_ref —, else the oracle port), torch fp32, all host threads, on a
                bounded sample of the same workload, rank 0 at N=1 only
-  --impl reference   times that CPU implementation as the reference arm (rank 0 only)
+  gpu_eager_reference   the UNMODIFIED reference module in PyTorch eager on the same GPU (bf16 and fp16-autocast +
+               channels_last), timed like its own benchmark.py — the real bar, rank 0 at N=1 only
+  --impl reference   times the CPU implementation as the reference arm (rank 0 only)
 
 The oracle is only ever the thing *beside* the measurement (cpu_baseline / reference arm); the product
 path is the native library and fails loudly without it.
@@ -37,6 +40,18 @@ if ROOT not in sys.path:
 
 METRIC = "images/sec LeMeViT-Base 224x224"
 UNIT = "img/s"
+# BASELINE.json configs[1..4] as per-GPU shards (configs[0] is the CPU plumbing run of tests/test_benchmark_driver.py).
+# The default (the configuration the metric is quoted on) is configs[3]: Base, 256 images per GPU.
+WORKLOADS = {
+    "base256": dict(model="lemevit_base", batch=256, res=224, backbone=False, config="BASELINE configs[3] per-GPU shard (2048 / 8)",
+                    metric=METRIC),
+    "tiny256": dict(model="lemevit_tiny", batch=256, res=224, backbone=False, config="BASELINE configs[1]",
+                    metric="images/sec LeMeViT-Tiny 224x224"),
+    "small512": dict(model="lemevit_small", batch=512, res=224, backbone=False, config="BASELINE configs[2]",
+                     metric="images/sec LeMeViT-Small 224x224"),
+    "base512seg": dict(model="lemevit_base", batch=16, res=512, backbone=True, config="BASELINE configs[4] per-GPU shard (128 / 8)",
+                       metric="images/sec LeMeViT-Base 512x512 4-stage backbone features (mmseg path)"),
+}
 FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
 
 
@@ -46,16 +61,26 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="lemevit_base")
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--res", type=int, default=224)
+    ap.add_argument("--workload", default="base256", choices=sorted(WORKLOADS), help="BASELINE.json configuration (per-GPU shard)")
+    ap.add_argument("--model", default=None, help="override the workload's model")
+    ap.add_argument("--batch", type=int, default=None, help="override: images per GPU per step")
+    ap.add_argument("--res", type=int, default=None, help="override: input resolution")
+    ap.add_argument("--no-eager-reference", action="store_true", help="skip the reference's PyTorch-eager GPU arm (gpu_eager_reference)")
     ap.add_argument("--chunk", type=int, default=-1, help="images per pass through the network (-1: library default)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel event profile (roofline object)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end loop (used for the ncu launch list)")
-    ap.add_argument("--cpu-batch", type=int, default=32)
-    return ap.parse_args()
+    ap.add_argument("--cpu-batch", type=int, default=None, help="images per step of the CPU arm (default 32; 4 at 512x512)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.model = args.model or wl["model"]
+    args.batch = args.batch or wl["batch"]
+    args.res = args.res or wl["res"]
+    args.backbone = wl["backbone"]
+    args.metric = wl["metric"] if (args.model, args.res) == (wl["model"], wl["res"]) else f"images/sec {args.model} {args.res}x{args.res}"
+    args.cpu_batch = args.cpu_batch or (4 if args.res >= 512 else 32)
+    return args
 
 
 # kernel class (native plan profile) -> kernel symbol in the ncu summaries under profiles/
@@ -188,49 +213,133 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU port of the reference forward (oracle) — cpu_baseline and the reference arm
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_throughput(model_name: str, res: int, batch: int, steps: int, warmup: int, budget_s: float):
+def _reference_modules():
+    """The UNMODIFIED reference model files (mount in the build container, verbatim git-ignored copy under baseline/_ref on the
+    GPU box — oracle/ref_copy.py), loaded through the import shims; None when neither exists."""
+    try:
+        from oracle import shims
+        if not shims.reference_available():
+            return None, None
+        return shims.load_reference_cls(), shims.load_reference_mmseg()
+    except Exception:
+        return None, None
+
+
+def _build_reference_model(model_name: str, backbone: bool, seed: int = 0):
+    """(kind, forward_fn(x) on CPU tensors, module or None): the untouched reference when available, else the oracle port."""
     import torch
     from oracle import lemevit_oracle as O
+    from oracle import weights as Wt
+    cfg = O.VARIANTS[model_name]
+    sd = Wt.make_state_dict(cfg, seed)
+    ref_cls, ref_seg = _reference_modules()
+    kw = dict(depth=list(cfg.depth), embed_dim=list(cfg.embed_dim), head_dim=cfg.head_dim, mlp_ratios=list(cfg.mlp_ratios),
+              attn_type=list(cfg.attn_type), queries_len=cfg.queries_len)
+    if backbone and ref_seg is not None:
+        m = ref_seg.LeMeViT(**kw)
+        m.train(False)
+        m.load_state_dict(sd, strict=False)
+        return "reference", m, m
+    if not backbone and ref_cls is not None:
+        m = ref_cls.LeMeViT(num_classes=cfg.num_classes, in_chans=cfg.in_chans, **kw).eval()
+        m.load_state_dict(sd)
+        return "reference", m, m
+    fn = (lambda x: O.forward_backbone(sd, cfg, x)) if backbone else (lambda x: O.forward_cls(sd, cfg, x))
+    return "port", fn, None
+
+
+def cpu_reference_throughput(model_name: str, res: int, batch: int, steps: int, warmup: int, budget_s: float, backbone: bool = False):
+    import torch
     from oracle import weights as Wt
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = O.VARIANTS[model_name]
-    sd = Wt.make_state_dict(cfg, 0)
+    kind, fwd, _ = _build_reference_model(model_name, backbone)
     x = Wt.make_input(batch, res, res, 0)
     times = []
     with torch.no_grad():
         t0 = time.perf_counter()
-        O.forward_cls(sd, cfg, x[: max(1, batch // 4)])          # page-in / thread-pool warm-up
+        fwd(x[: max(1, batch // 4)])          # page-in / thread-pool warm-up
         est = (time.perf_counter() - t0) * 4
         for _ in range(max(0, warmup)):
             if est * (len(times) + 2) > budget_s:
                 break
-            O.forward_cls(sd, cfg, x)
+            fwd(x)
         t_start = time.perf_counter()
         for i in range(steps):
             t0 = time.perf_counter()
-            O.forward_cls(sd, cfg, x)
+            fwd(x)
             times.append(time.perf_counter() - t0)
             if time.perf_counter() - t_start > budget_s and i + 1 >= 2:
                 break
     sec = sum(times) / len(times)
-    return {"img_s": batch / sec, "ms_per_step": sec * 1e3, "steps_run": len(times), "cores": torch.get_num_threads(),
-            "sample": f"{len(times)} forward passes of {batch} images ({model_name} {res}x{res}, torch fp32 eager CPU port of the reference forward)"}
+    what = ("the UNMODIFIED reference module (models/lemevit.py via import shims), torch fp32 eager on CPU" if kind == "reference"
+            else "torch fp32 eager CPU port of the reference forward (oracle/)")
+    return {"img_s": batch / sec, "ms_per_step": sec * 1e3, "steps_run": len(times), "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{len(times)} forward passes of {batch} images ({model_name} {res}x{res}{' backbone' if backbone else ''}, {what})"}
+
+
+def gpu_eager_reference(model_name: str, res: int, batch: int, backbone: bool, steps: int, warmup: int, device):
+    """The bar SURVEY.md §8(d) calls the real one: the reference's own PyTorch-eager GPU path on THIS GPU, timed the way
+    /root/reference/benchmark.py:481-519 does (warm-up, then a synchronize per step), in the two precision modes its callers select:
+    `--precision bfloat16` (model.to(bf16), benchmark.py:343-348,420-424) and `--amp --channels-last` (fp16 autocast,
+    scripts/benchmark.sh:10).  None when the reference sources are not available."""
+    import torch
+    kind, _, module = _build_reference_model(model_name, backbone)
+    if module is None:
+        return None
+    out = {"model": model_name, "batch": batch, "res": res, "steps": steps, "warmup": warmup,
+           "source": "unmodified reference module, same GPU, torch %s eager (F.scaled_dot_product_attention, cuBLAS, cuDNN)" % torch.__version__}
+    x32 = torch.randn(batch, 3, res, res, device=device)
+
+    def timed(fn):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+                torch.cuda.synchronize(device)
+            return (time.perf_counter() - t0) / steps
+
+    try:
+        m = module.to(device=device, dtype=torch.bfloat16)
+        xb = x32.to(torch.bfloat16)
+        sec = timed(lambda: m(xb))
+        out["bf16"] = {"value": batch / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "mode": "model.to(bfloat16), NCHW (benchmark.py --precision bfloat16)"}
+    except Exception as e:  # pragma: no cover
+        out["bf16"] = {"error": str(e)[:200]}
+    try:
+        m = module.to(device=device, dtype=torch.float32, memory_format=torch.channels_last)
+        xc = x32.contiguous(memory_format=torch.channels_last)
+
+        def amp():
+            with torch.autocast("cuda", dtype=torch.float16):
+                m(xc)
+        sec = timed(amp)
+        out["fp16_amp_channels_last"] = {"value": batch / sec, "unit": UNIT, "ms_per_step": sec * 1e3,
+                                         "mode": "fp32 weights, torch.autocast(float16), channels_last (scripts/benchmark.sh:10)"}
+    except Exception as e:  # pragma: no cover
+        out["fp16_amp_channels_last"] = {"error": str(e)[:200]}
+    module.to("cpu")
+    del x32
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_throughput(args.model, args.res, args.cpu_batch, args.steps, args.warmup, budget_s=200.0)
+    r = cpu_reference_throughput(args.model, args.res, args.cpu_batch, args.steps, args.warmup, budget_s=200.0, backbone=args.backbone)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["img_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_run"],
+        "impl": "reference", "metric": args.metric, "value": r["img_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps_run"],
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} {args.res}x{args.res} inference, bounded sample of {args.cpu_batch} images per step on host cores",
-                   "images_per_step": args.cpu_batch},
-        "cpu_baseline": {"value": r["img_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "config": {"workload": f"{args.model} {args.res}x{args.res}{' backbone' if args.backbone else ''} inference, bounded sample of "
+                               f"{args.cpu_batch} images per step on host cores", "images_per_step": args.cpu_batch},
+        "cpu_baseline": {"value": r["img_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["img_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -247,7 +356,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the lemevit_b200 forward has no CPU path (use --impl reference for the CPU arm)")
     import lemevit_b200 as L
-    from oracle import lemevit_oracle as O   # only for algorithmic_flops_per_image (a formula) and the cpu_baseline leg
+    from oracle import lemevit_oracle as O   # only for algorithmic_flops_per_image (a formula) and the reference legs
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -266,12 +375,20 @@ def run_ours(args):
     B, R, K, W = args.batch, args.res, args.steps, max(args.warmup, 3)
     torch.manual_seed(0)
     kw = {} if args.chunk < 0 else {"native_chunk": args.chunk}
-    model = getattr(L, args.model)(**kw).to(dev, torch.bfloat16)
+    cfg = O.VARIANTS[args.model]
+    if args.backbone:
+        model = L.LeMeViTBackbone(depth=list(cfg.depth), embed_dim=list(cfg.embed_dim), head_dim=cfg.head_dim, mlp_ratios=list(cfg.mlp_ratios),
+                                  attn_type=list(cfg.attn_type), queries_len=cfg.queries_len, **kw).to(dev, torch.bfloat16)
+        api = f"lemevit_b200.LeMeViTBackbone({args.model})(x)"
+    else:
+        model = getattr(L, args.model)(**kw).to(dev, torch.bfloat16)
+        api = f"lemevit_b200.{args.model}()(x)"
     model.train(False)
     eng = model.native_engine(dev)
-    gflop_img = O.algorithmic_flops_per_image(O.VARIANTS[args.model], R, R) / 1e9
+    gflop_img = O.algorithmic_flops_per_image(cfg, R, R, backbone=args.backbone) / 1e9
 
-    # two rotating device-resident batches (2 x 77 MB > L2) + a multi-GB activation workspace streamed every step
+    # two device-resident batches; every timed step copies the next one into the graph's static input (fresh values each step,
+    # 2 x the batch > L2 for the 224^2 workloads) and the forward streams a multi-GB activation workspace
     g = torch.Generator(device="cpu").manual_seed(shard_seed(rank))
     xs = [torch.randn(B, 3, R, R, generator=g).to(dev, torch.bfloat16) for _ in range(2)]
     with torch.no_grad():
@@ -279,18 +396,13 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         launches_per_step = eng.launch_count(B, R, R)
         use_graph = not args.no_graph
-        replays = None
         if use_graph:
-            replays = []
-            for x in xs:
-                sx, sy, replay = eng.graphed(x)
-                replays.append(replay)
-                if len(replays) == 1:      # one capture: both batches share the static input of the first graph
-                    break
+            sx, sy, replay = eng.graphed(xs[0], out_dtype=torch.bfloat16)
 
         def step(i):
             if use_graph:
-                replays[0]()
+                sx.copy_(xs[i & 1])
+                replay()
             else:
                 model(xs[i & 1])
 
@@ -312,9 +424,12 @@ def run_ours(args):
 
         # ---- end to end through the public API with pinned host buffers (double-buffered upload) ----
         e2e = None
+        y0 = model(xs[0])
+        outs0 = list(y0) if isinstance(y0, (list, tuple)) else [y0]
         hx = [torch.randn(B, 3, R, R, generator=g).to(torch.bfloat16).pin_memory() for _ in range(2)]
-        hy = [torch.empty(B, model.num_classes, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
+        hy = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs0] for _ in range(2)]
         dx = [torch.empty_like(xs[0]) for _ in range(2)]
+        del y0, outs0
         copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
         up_done = [torch.cuda.Event() for _ in range(2)]
         buf_free = [torch.cuda.Event() for _ in range(2)]
@@ -336,7 +451,8 @@ def run_ours(args):
                 comp_s.wait_event(up_done[cur])
                 out = model(dx[cur])
                 buf_free[cur].record(comp_s)
-                hy[cur].copy_(out, non_blocking=True)
+                for h, o in zip(hy[cur], out if isinstance(out, (list, tuple)) else [out]):
+                    h.copy_(o, non_blocking=True)
             torch.cuda.synchronize(dev)
 
         if not args.no_e2e:
@@ -349,55 +465,84 @@ def run_ours(args):
             e2e_ms = max_over_ranks(e2e_ms, world, dev)
             e2e = {"value": whole_job_rate(B, world, e2e_ms), "unit": UNIT, "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": world * hx[0].numel() * hx[0].element_size(),
-                   "d2h_bytes_per_step": world * hy[0].numel() * hy[0].element_size(),
-                   "api": "lemevit_b200.lemevit_base()(x): pinned host bf16 batch -> H2D -> native forward -> D2H logits, uploads double-buffered on a copy stream"}
+                   "d2h_bytes_per_step": world * sum(h.numel() * h.element_size() for h in hy[0]),
+                   "api": f"{api}: pinned host bf16 batch -> H2D -> native forward -> D2H of the result "
+                          f"({'4 NCHW feature maps' if args.backbone else 'logits'}), uploads double-buffered on a copy stream"}
+        del hx, hy, dx
 
-        # ---- per-kernel-class device time (CUDA events between consecutive launches on the launching stream)
+        # ---- per-kernel-class device time (CUDA events between consecutive launches on the launching stream), taken with ONE
+        # lane so that a launch's bracket holds that kernel alone (with two concurrent lanes every bracket would include the
+        # other lane's kernels: VERDICT r1)
         roof = None
         pk, pk_src = peaks()
         if not args.no_profile and rank == 0:
+            lanes_saved = eng.lanes
+            eng.lanes = 1
+            model(xs[0])
             eng.set_profile(True)
             for i in range(3):
                 model(xs[i & 1])
             prof = eng.get_profile()
             report = eng.profile_report()
             eng.set_profile(False)
+            eng.lanes = lanes_saved
             tot_ms = sum(p["device_ms"] for p in prof) or 1.0
             dom = max(prof, key=lambda p: p["device_ms"])
             ach = dom["flops"] / (dom["device_ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops_sustained"], "peak_source": f"bf16_tflops_sustained of {pk_src}",
                     "traffic": (ncu_traffic(dom["name"]) or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(dom["name"]),
-                    "kernel_share_of_step": dom["device_ms"] / tot_ms,
+                    "kernel_share_of_step": dom["device_ms"] / tot_ms, "profile_lanes": 1,
                     "launches_per_step": dom["launches"] // 3, "avg_launch_us": dom["device_ms"] / dom["launches"] * 1e3,
                     "flops_per_launch": dom["flops"] / dom["launches"],
                     "step_achieved": value / world * gflop_img / 1e3, "step_frac": value / world * gflop_img / 1e3 / pk["bf16_tflops_sustained"],
+                    "serial_step_ms": tot_ms / 3,
                     "classes": {p["name"]: {"ms_per_step": p["device_ms"] / 3, "launches": p["launches"] // 3,
                                             "tflops": p["flops"] / (p["device_ms"] * 1e-3) / 1e12 if p["device_ms"] else 0.0,
                                             "gbs": p["bytes"] / (p["device_ms"] * 1e-3) / 1e9 if p["device_ms"] else 0.0} for p in prof}}
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-            with open(os.path.join(ROOT, "gpurun_out", "bench_profile_report.txt"), "w") as f:
+            with open(os.path.join(ROOT, "gpurun_out", f"bench_profile_report_{args.workload}.txt"), "w") as f:
                 f.write(report)
+
+    # ---- the reference's PyTorch-eager GPU path on this very GPU (rank 0, N = 1 only)
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_reference:
+        del xs
+        torch.cuda.empty_cache()
+        try:
+            eager = gpu_eager_reference(args.model, R, B, args.backbone, steps=max(5, min(K, 20)), warmup=5, device=dev)
+        except Exception as e:  # pragma: no cover
+            eager = {"error": str(e)[:300]}
+        if eager:
+            best = max((v["value"] for v in eager.values() if isinstance(v, dict) and "value" in v), default=None)
+            if best:
+                eager["vs_eager"] = {"value_over_best_eager": value / best, "e2e_over_best_eager": (e2e["value"] / best) if e2e else None}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_throughput(args.model, R, args.cpu_batch, steps=5, warmup=1, budget_s=25.0)
-        cpu = {"value": r["img_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        r = cpu_reference_throughput(args.model, R, args.cpu_batch, steps=5, warmup=1, budget_s=25.0, backbone=args.backbone)
+        cpu = {"value": r["img_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
+        published = args.workload == "base256" and args.model == "lemevit_base" and R == 224
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": value / world / 1482.70, "dtype": "bf16", "data": "synthetic",
-            "vs_baseline_note": "per-GPU img/s / 1482.70 img/s per device published in the reference README.md:87 (hardware, batch and precision unstated)",
-            "config": {"workload": f"{args.model} {R}x{R} bf16 inference, {B} images per GPU per step (BASELINE configs[3] per-GPU shard), random-init weights",
-                       "global_batch": world * B, "parallelism": f"dp{world} (batch sharded, no collective)",
-                       "l2": "activation workspace streamed per step is >> 126 MB L2; device-timed loop replays a CUDA graph" if use_graph
-                       else "two rotating input batches (154 MB) + activation workspace >> 126 MB L2",
-                       "cuda_graph": bool(use_graph), "chunk": eng.chunk, "gflop_per_image": gflop_img},
+            "metric": args.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": (value / world / 1482.70) if published else None,
+            "dtype": "bf16", "data": "synthetic",
+            "vs_baseline_note": "per-GPU img/s / 1482.70 img/s per device published in the reference README.md:87 (hardware, batch and precision unstated)"
+            if published else "no published number for this configuration",
+            "config": {"workload": f"{args.model} {R}x{R} bf16 {'4-stage backbone features (mmseg path)' if args.backbone else 'inference'}, "
+                                   f"{B} images per GPU per step ({WORKLOADS[args.workload]['config']}), random-init weights",
+                       "name": args.workload, "global_batch": world * B, "parallelism": f"dp{world} (batch sharded, no collective)",
+                       "l2": ("every step copies a fresh batch (two rotate) into the graph's static input and streams a multi-GB activation "
+                              "workspace >> 126 MB L2; device-timed loop replays a CUDA graph") if use_graph
+                       else "two rotating input batches + activation workspace >> 126 MB L2",
+                       "cuda_graph": bool(use_graph), "chunk": eng.chunk, "lanes": eng._use_lanes(B), "gflop_per_image": gflop_img},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches_per_step * K,
-            "roofline": roof, "cpu_baseline": cpu,
-            "published_reference": {"value": 1482.70, "unit": UNIT, "hardware": "unstated (README.md:87)"},
+            "roofline": roof, "cpu_baseline": cpu, "gpu_eager_reference": eager,
         }
+        if published:
+            line["published_reference"] = {"value": 1482.70, "unit": UNIT, "hardware": "unstated (README.md:87)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -22,7 +22,10 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("LEMEVIT_REFERENCE_ROOT", "/root/reference")
+from . import ref_copy
+
+# /root/reference in the build container; on the GPU box the verbatim, git-ignored copy under baseline/_ref (oracle/ref_copy.py)
+REFERENCE_ROOT = ref_copy.root() or ref_copy.MOUNT
 
 
 class _Registry:

@@ -21,10 +21,13 @@ with torch.no_grad():
         if a.startswith("--opt="):          # e.g. --opt=fused_mlp=0
             k, v = a[6:].split("=")
             m.native_engine(x.device).set_option(k, int(v))
+    eng = m.native_engine(x.device)
+    for a in sys.argv:
+        if a.startswith("--lanes="):        # --lanes=1: kernels of a launch bracket run alone (per-op profile)
+            eng.lanes = int(a[8:])
     for _ in range(3):
         y = m(x)
     torch.cuda.synchronize()
-    eng = m.native_engine(x.device)
     fn = (lambda: m(x))
     if use_graph:
         sx, sy, replay = eng.graphed(x)
