@@ -75,7 +75,8 @@ int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
 /* schedule options (A/B switches; every schedule is rebuilt afterwards).  Known names:
  *   "fused_mlp" (default 1): run `x + mlp(norm2(x))` as ONE kernel (lmv_mlp_fused) where the shape allows it;
  *   "direct_stem" (default 1): first stem convolution as a direct kernel (lmv_stem_conv1) instead of im2col + GEMM;
- *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self). */
+ *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self);
+ *   "fused_dca" (default 1): 'C' / 'D' blocks through the fused cross-attention kernels (lmv_dca_block) where the shape allows it. */
 int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
 /* test hook (block-level parity against the reference's forward hooks): after block `block` of stage `stage` every forward
  * copies the block's outputs to x_tokens_out [B, N, C] bf16 (token-major) and c_out [B, queries_len, C] bf16 (either may be
@@ -183,6 +184,24 @@ size_t lmv_attention_meta_workspace(int B, int heads, int Lq, int Lk);
 int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, long long k_bs, int k_rs, const void* v,
                        long long v_bs, int v_rs, void* out, long long o_bs, int o_rs, int B, int heads, int Lq, int Lk,
                        float scale, void* workspace, size_t workspace_bytes, void* stream);
+/* Fused cross-attention block core: everything of LeMeBlock.forward_with_c ('C', models/lemevit.py:584-613 with CrossAttention
+ * :477-486) or forward_with_xc ('D', :542-582 with DualCrossAttention :252-302) between the positional embedding and the image-token
+ * MLP, in three launches (meta_pre -> dca_x -> meta_post; csrc/kernels.h describes the absorbed-projection formulation):
+ *   xt [B, N, C] bf16 = x + dwconv(x) (raw) with stats1 [B*N][parts1][2] = partial (sum, sum^2) of its rows (LayerNorm norm1 is
+ *   applied from the statistics; its affine is folded into the weights);
+ *   'D': xout [B, N, C] <- xt + proj_x(softmax(s_x q1 k2^T) v2) (may alias xt), stats2 [B*N][2] <- (sum, sum^2) of the stored rows;
+ *   c [B, 16, C] bf16 updated IN PLACE with the block's whole meta-token update: c += proj(softmax(s_c q k^T) v); c += mlp(norm2(c)).
+ * Weights as packed by lemevit_b200/pack.py (bf16 [out, in], LayerNorm affine folded, fp32 biases):
+ *   'D': wa = qkv1 [3C, C], wb = qkv2 [3C, C], wp1 = proj_x, wp2 = proj_c;   'C': wa = q [C, C], wb = kv [2C, C], wp1 = proj (wp2 unused);
+ *   w1 = mlp.0 [Hd, C] (norm2 folded), w2 = mlp.3 [C, Hd].
+ * scale_x / scale_c: softmax scales of the two branches (:235,255-256; 'C': scale_c = head_dim^-0.5, scale_x unused).
+ * Requires 16 meta tokens, C = heads * 32 <= 192.  workspace: lmv_dca_workspace_bytes(...) bytes, 256-byte aligned.
+ * flags bit 0: issue the c-branch accumulation per 64-channel block (test hook). */
+size_t lmv_dca_workspace_bytes(int B, int N, int C, int heads);
+int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, void* xout, float* stats2, void* c, const void* wa,
+                  const float* ba, const void* wb, const float* bb, const void* wp1, const float* bp1, const void* wp2, const float* bp2,
+                  const void* w1, const float* b1, const void* w2, const float* b2, int B, int N, int C, int heads, int Hd, float scale_x,
+                  float scale_c, void* workspace, size_t workspace_bytes, int flags, void* stream);
 /* patch gather for the first stem conv 3x3/s2/p1 (models/lemevit.py:699): x NCHW (f32|bf16) ->
  * out[B*Ho*Wo, Kp] bf16 with k = ci*9 + ky*3 + kx, zero padded to Kp = round_up(9*Cin, 8); the conv
  * itself (+ folded BN + GELU, :700-701) is then lmv_linear on the tcgen05 GEMM. */

@@ -109,9 +109,9 @@ struct StageW {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
-enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_SELF, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_STEM, OP_IM2COL, OP_MISC, OP_NUM_CLASSES };
+enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_SELF, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_STEM, OP_IM2COL, OP_MISC, OP_DCA, OP_META, OP_NUM_CLASSES };
 static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "mlp_fused_tcgen05", "attention_self_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
-                                                          "posembed_layernorm", "layernorm", "stem_conv_direct", "im2col", "misc"};
+                                                          "posembed_layernorm", "layernorm", "stem_conv_direct", "im2col", "misc", "dca_fused_tcgen05", "meta_branch"};
 struct OpRec {
   Launch fn;
   std::string desc;
@@ -155,6 +155,7 @@ struct lmv_plan {
   int debug_simt = 0;
   int fused_mlp = 1;
   int fused_self_attn = 1;
+  int fused_dca = 1;
   int direct_stem = 1;
   int profile = 0;
   int tap_stage = -1, tap_block = -1;       // test hook: copy (x, c) after this block to tap_x / tap_c
@@ -316,7 +317,7 @@ static int geometry(const lmv_config& c, int H, int W, Geo* g) {
 }
 
 struct WsLayout {
-  size_t patches, stem1, x0, x1, xn, qkv, hid, ca, cb, cn, cqkv, chid, ctmp, feat, stats1, stats2, cpart, cpart_bytes, total;
+  size_t patches, stem1, x0, x1, xn, qkv, hid, ca, cb, cn, cqkv, chid, ctmp, feat, stats1, stats2, cpart, cpart_bytes, dca, total;
 };
 
 static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
@@ -365,6 +366,12 @@ static void ws_layout(const lmv_config& c, const Geo& g, int B, WsLayout* L) {
     if (c.attn_type[i] == 'S') cpart = std::max(cpart, attention_self_workspace(B, c.embed_dim[i] / c.head_dim, g.T[i]));
   L->cpart_bytes = cpart;
   L->cpart = take((cpart + 1) / 2);
+  // scratch of the fused cross-attention blocks (per-image operands + c-branch softmax partials)
+  size_t dca = 0;
+  for (int i = 0; i < c.num_stages; ++i)
+    if (c.attn_type[i] != 'S' && dca_supported(g.N[i], c.embed_dim[i], c.embed_dim[i] / c.head_dim, M))
+      dca = std::max(dca, dca_workspace_bytes(dca_geometry(B, g.N[i], c.embed_dim[i], c.embed_dim[i] / c.head_dim)));
+  L->dca = take((dca + 1) / 2);
   L->total = off;
 }
 
@@ -501,6 +508,48 @@ struct Builder {
     if (rc) return;
     LnArgs a{in, out, g, b, R, C, eps, gelu, grp_rows, grp_stride, grp_off};
     sc->push([a](cudaStream_t s) { return layernorm_run(a, s); }, OP_LN, 0.0, 4.0 * R * C);
+  }
+  // Fused 'C' / 'D' block core (kernels.h): meta_pre -> dca_x -> meta_post.  xt = x + dw(x) with its LayerNorm statistics in stats1;
+  // 'D': x <- xt + proj_x(attention) written to xout (may alias xt) with the LN2 statistics in stats2; c updated in place (full
+  // meta-token update of the block including its MLP).
+  void dca_block(char kind, const bf16* xt, const float* stats1, int parts1, bf16* xout, float* stats2, bf16* cc, const BlockW& bw,
+                 int B, int N, int C, int heads, int Hd, float scale_x, float scale_c, void* dca_ws, int zsplit = 0) {
+    if (rc) return;
+    const DcaGeom g = dca_geometry(B, N, C, heads);
+    const DcaWs w = dca_workspace_carve(g, dca_ws);
+    const bool D = kind == 'D';
+    MetaPreArgs pre{};
+    pre.c = cc; pre.B = B; pre.C = C; pre.heads = heads; pre.eps = 1e-6f; pre.ws = w;
+    pre.scale_x = scale_x; pre.scale_c = scale_c;
+    MetaPostArgs post{};
+    post.c = cc; post.B = B; post.C = C; post.heads = heads; post.Hd = Hd; post.parts = g.parts; post.eps = 1e-6f; post.ws = w;
+    post.W1 = bw.w1; post.b1 = bw.b1; post.W2 = bw.w2; post.b2 = bw.b2;
+    if (D) {
+      pre.Wc = bw.wb; pre.bc = bw.bb; pre.nc = 3 * C; pre.q_off = 0; pre.k_off = C; pre.v_off = 2 * C;
+      pre.Wxq = bw.wa; pre.bxq = bw.ba; pre.Wxk = bw.wa + (size_t)C * C; pre.bxk = bw.ba + C; pre.Wpx = bw.wp1;
+      post.Wxv = bw.wa + (size_t)2 * C * C; post.bxv = bw.ba + 2 * C; post.Wp = bw.wp2; post.bp = bw.bp2;
+    } else {
+      pre.Wc = bw.wa; pre.bc = bw.ba; pre.nc = C; pre.q_off = 0; pre.k_off = -1; pre.v_off = -1;
+      pre.Wxk = bw.wb; pre.bxk = bw.bb;
+      post.Wxv = bw.wb + (size_t)C * C; post.bxv = bw.bb + C; post.Wp = bw.wp1; post.bp = bw.bp1;
+    }
+    DcaXArgs xa{};
+    xa.xt = xt; xa.stats1 = stats1; xa.parts1 = parts1; xa.eps = 1e-6f; xa.do_x = D ? 1 : 0;
+    xa.bpx = D ? bw.bp1 : nullptr; xa.xout = D ? xout : nullptr; xa.stats2 = D ? stats2 : nullptr;
+    xa.g = g; xa.ws = w; xa.zsplit = zsplit;
+    DcaXOp op;
+    rc = dca_x_prepare(xa, &op);
+    if (rc) return;
+    const double rows = (double)B * 16, R = g.R;
+    char d[160];
+    snprintf(d, sizeof(d), "meta_pre B=%d C=%d %c", B, C, kind);
+    sc->push([pre](cudaStream_t s) { return meta_pre_run(pre, s); }, OP_META, 2.0 * rows * C * (pre.nc + (D ? 3.0 : 1.0) * C), 0.0, d);
+    // algorithmic FLOPs of what the kernel replaces (SURVEY.md section 8d accounting): the image-side projections + both attentions
+    const double fl = 2.0 * B * N * ((D ? 4.0 : 2.0) * C * C + (D ? 2.0 : 1.0) * 2.0 * 16.0 * C);
+    snprintf(d, sizeof(d), "dca_x B=%d N=%d C=%d %c", B, N, C, kind);
+    sc->push([op](cudaStream_t s) { return dca_x_run(op, s); }, OP_DCA, fl, 2.0 * B * N * C * (D ? 2.0 : 1.0), d);
+    snprintf(d, sizeof(d), "meta_post B=%d C=%d %c", B, C, kind);
+    sc->push([post](cudaStream_t s) { return meta_post_run(post, s); }, OP_META, 2.0 * rows * C * (2.0 * C + 2.0 * Hd) + 2.0 * B * R * C * g.parts, 0.0, d);
   }
   void attn(const bf16* q, long long q_bs, int q_rs, const bf16* k, const bf16* v, long long kv_bs, int kv_rs, bf16* out,
             long long o_bs, int o_rs, int B, int heads, int Lq, int Lk, float scale) {
@@ -639,6 +688,9 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
       }
     }
     bf16* cc = cbuf[ccur];
+    // fused cross-attention blocks (dca_fused.cu + meta_branch.cu) wherever the shape allows; the unfused schedule otherwise
+    const bool fuse_dca = !b.simt && plan->fused_dca && kind != 'S' && !uni && dca_supported(N, C, heads, M);
+    void* dca_ws = ws + L.dca;
     // ---- blocks
     for (int j = 0; j < c.depth[i] && !b.rc; ++j) {
       const BlockW& bw = sw.blocks[j];
@@ -646,6 +698,10 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         // forward_with_c (models/lemevit.py:584-613) + CrossAttention (:477-486); x is returned unchanged
         // xn <- x + dw(x) (raw; norm1 is folded into the kv GEMM through stats1)
         const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xn, nullptr, B, g.H[i], g.W[i], T, C, stats1);
+        if (fuse_dca) {
+          b.dca_block('C', xn, stats1, sp, nullptr, nullptr, cc, bw, B, N, C, heads, Hd, 0.f, 1.0f / sqrtf((float)c.head_dim), dca_ws);
+          continue;
+        }
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.wa, bw.ba, B * M, C, C, cqkv, C);
         b.ln_linear(xn, stats1, sp, bw.wb, bw.bb, bw.csb, B * N, 2 * C, C, qkv);
@@ -660,11 +716,15 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
         cur ^= 1;
         bf16* x = xbuf[cur];
+        const double scale = 1.0 / std::sqrt((double)C);                       // :235 full channel dim
+        const double scale_x = std::log((double)M) / std::log((double)N) * scale;  // :255 math.log(M, N)
+        if (fuse_dca) {
+          b.dca_block('D', x, stats1, sp, x, stats2, cc, bw, B, N, C, heads, Hd, (float)scale_x, (float)scale, dca_ws);
+          b.mlp(x, stats2, 1, bw, B * N, C, Hd, hid);                                // norm2 folded, hidden stays on chip
+        } else {
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.ln_linear(x, stats1, sp, bw.wa, bw.ba, bw.csa, B * N, 3 * C, C, qkv);
         b.linear(cn, C, bw.wb, bw.bb, B * M, 3 * C, C, cqkv, 3 * C);
-        const double scale = 1.0 / std::sqrt((double)C);                       // :235 full channel dim
-        const double scale_x = std::log((double)M) / std::log((double)N) * scale;  // :255 math.log(M, N)
         b.attn(qkv, (long long)N * 3 * C, 3 * C, cqkv + C, cqkv + 2 * C, (long long)M * 3 * C, 3 * C, xn, (long long)N * C, C,
                B, heads, N, M, (float)scale_x);
         b.attn(cqkv, (long long)M * 3 * C, 3 * C, qkv + C, qkv + 2 * C, (long long)N * 3 * C, 3 * C, cn, (long long)M * C, C,
@@ -676,6 +736,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.w1, bw.b1, B * M, Hd, C, chid, Hd, 1);
         b.linear(chid, Hd, bw.w2, bw.b2, B * M, C, Hd, cc, C, 0, cc);
+        }
       } else {
         // forward_with_x (models/lemevit.py:615-650) + StandardAttention (:199-205); image and meta tokens
         // share norm1/attn/norm2/mlp, so they travel in one [B, N+M, C] buffer (classification model only)
@@ -945,6 +1006,7 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   if (n == "fused_mlp") plan->fused_mlp = value ? 1 : 0;
   else if (n == "fused_self_attn") plan->fused_self_attn = value ? 1 : 0;
   else if (n == "direct_stem") plan->direct_stem = value ? 1 : 0;
+  else if (n == "fused_dca") plan->fused_dca = value ? 1 : 0;
   else return fail(LMV_ERR_INVALID, "set_option: unknown option " + n);
   plan->cache.clear();   // schedules are rebuilt with the new setting
   return LMV_OK;
@@ -1143,6 +1205,39 @@ int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, l
   if (!q || !k || !v || !out) return fail(LMV_ERR_INVALID, "attention_meta: null pointer");
   AttnArgs a = make_attn_args(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, out, o_bs, o_rs, B, heads, Lq, Lk, scale);
   return attention_meta_run(a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+size_t lmv_dca_workspace_bytes(int B, int N, int C, int heads) {
+  if (B <= 0 || !dca_supported(N, C, heads, kDcaM)) return 0;
+  return dca_workspace_bytes(dca_geometry(B, N, C, heads));
+}
+
+int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, void* xout, float* stats2, void* c, const void* wa,
+                  const float* ba, const void* wb, const float* bb, const void* wp1, const float* bp1, const void* wp2, const float* bp2,
+                  const void* w1, const float* b1, const void* w2, const float* b2, int B, int N, int C, int heads, int Hd, float scale_x,
+                  float scale_c, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+  if (kind != 'C' && kind != 'D') return fail(LMV_ERR_INVALID, "dca_block: kind must be 'C' or 'D'");
+  if (!xt || !stats1 || !c || !wa || !ba || !wb || !bb || !wp1 || !bp1 || !w1 || !b1 || !w2 || !b2 || !workspace)
+    return fail(LMV_ERR_INVALID, "dca_block: null pointer");
+  if (kind == 'D' && (!xout || !stats2 || !wp2 || !bp2)) return fail(LMV_ERR_INVALID, "dca_block: null pointer ('D' block)");
+  if (!dca_supported(N, C, heads, kDcaM)) return fail(LMV_ERR_UNSUPPORTED, "dca_block: needs C = heads * 32 <= 192");
+  if (workspace_bytes < lmv_dca_workspace_bytes(B, N, C, heads) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return fail(LMV_ERR_INVALID, "dca_block: workspace too small or not 256-byte aligned");
+  BlockW bw;
+  memset(&bw, 0, sizeof(bw));
+  bw.wa = static_cast<const bf16*>(wa); bw.ba = ba; bw.wb = static_cast<const bf16*>(wb); bw.bb = bb;
+  bw.wp1 = static_cast<const bf16*>(wp1); bw.bp1 = bp1; bw.wp2 = static_cast<const bf16*>(wp2); bw.bp2 = bp2;
+  bw.w1 = static_cast<const bf16*>(w1); bw.b1 = b1; bw.w2 = static_cast<const bf16*>(w2); bw.b2 = b2;
+  Schedule sc;
+  Builder b{nullptr, &sc, LMV_OK, false};
+  b.dca_block((char)kind, static_cast<const bf16*>(xt), stats1, parts1, static_cast<bf16*>(xout), stats2, static_cast<bf16*>(c), bw, B, N, C,
+              heads, Hd, scale_x, scale_c, workspace, flags & 1);
+  if (b.rc) return b.rc;
+  for (auto& op : sc.ops) {
+    int rc = op.fn(static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+  }
+  return LMV_OK;
 }
 
 int lmv_stem_im2col(const void* x, int x_dtype, void* out, int B, int Cin, int H, int W, void* stream) {

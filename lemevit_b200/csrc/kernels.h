@@ -142,4 +142,112 @@ bool mlp_fused_supported(int C, int Hd);
 int mlp_fused_prepare(const MlpArgs& a, MlpOp* op);
 int mlp_fused_run(const MlpOp& op, cudaStream_t s);
 
+// ------------------------------------------------------------------------------------------------
+// Fused cross-attention blocks (dca_fused.cu + meta_branch.cu): CrossAttention 'C' blocks (models/lemevit.py:477-486,584-613)
+// and DualCrossAttention 'D' blocks (:252-302,542-582) with the image-side projections ABSORBED into per-image operands:
+//
+//   x-branch   dx[n]   = proj_x( concat_h softmax_m( s_x q1_h[n] . k2_h[m] ) v2_h )         q1 = Wq xn[n] + bq
+//                      = sum_(h,m) P[n,(h,m)] Vt[(h,m)] + b_px        S[n,(h,m)] = xn[n] . Kt[(h,m)] + kappa[(h,m)]
+//              with  Kt[(h,m)] = s_x Wq_h^T k2_h[m]   kappa = s_x bq_h . k2_h[m]   Vt[(h,m)] = Wpx[:, h] v2_h[m]     (all [R = heads*M, C])
+//   c-branch   attn_c[(h,m)] = softmax_n( s_c q2_h[m] . k1_h[n] ) v1_h[n]                     k1 = Wk xn + bk, v1 = Wv xn + bv
+//                            = Wv_h Zbar[(h,m)] + bv_h,  Zbar = sum_n softmax_n(Sc) xn[n]     Sc[(h,m),n] = Qt[(h,m)] . xn[n] + beta[(h,m)]
+//              with  Qt[(h,m)] = s_c Wk_h^T q2_h[m]   beta = s_c bk_h . q2_h[m]
+//
+// so the N x 3C projection qkv1 (and q1/k1/v1 themselves) never exists: the image-token kernel only contracts the token tile
+// with the [R, C] operands of its image.  xn = LayerNorm_noaffine(xt) is applied AFTER the contraction from the per-row
+// statistics (xn = r (xt - mu)): S = r (xt.Kt - mu sum(Kt)) + kappa, Zbar = sum p r (xt - mu).
+// ------------------------------------------------------------------------------------------------
+constexpr int kDcaM = 16;        // meta tokens per image (queries_len of every published variant); other values use the unfused schedule
+constexpr int kDcaTile = 128;    // image tokens per tile
+
+struct DcaGeom {
+  int B, N, C, heads, R;         // R = heads * kDcaM <= 128
+  int tiles, seg_tiles, segs;    // 128-token tiles per image, cut into `segs` segments of seg_tiles tiles (one softmax partial each)
+  int dup, ncopy;                // R <= 64: the (h,m) rows are duplicated at lanes 64.., each copy takes half of a tile's tokens
+  int parts;                     // segs * ncopy partials per image
+};
+bool dca_supported(int N, int C, int heads, int M);
+DcaGeom dca_geometry(int B, int N, int C, int heads);
+
+// device scratch of ONE fused block (carved from the caller's workspace; byte offsets from dca_workspace_layout)
+struct DcaWs {
+  bf16* kt;          // [B][R][C]   x-branch keys in token space (scaled by s_x log2 e)                   ('D' only)
+  bf16* qt;          // [B][R][C]   c-branch queries in token space (scaled by s_c log2 e)
+  bf16* vt;          // [B][C][R]   x-branch values pushed through proj_x, transposed                      ('D' only)
+  float* cst;        // [B][4][R]   (sum_c Kt, kappa, sum_c Qt, beta): sums of the bf16-ROUNDED rows, kappa/beta in the log2 domain
+  float4* part_ml;   // [B][parts][R]      (running max, sum p, sum p' mu, -) of a segment, log2 domain
+  float* part_z;     // [B][parts][R][C]   sum_n p'_n xt[n]  (p' = bf16(p r_n))
+};
+size_t dca_workspace_bytes(const DcaGeom& g);
+DcaWs dca_workspace_carve(const DcaGeom& g, void* base);
+
+struct MetaPreArgs {
+  const bf16* c;             // [B, M, C] meta tokens (block input)
+  const bf16* Wc;            // projection applied to LN1(c): 'D' qkv2 [3C, C] (q2 | k2 | v2 rows), 'C' q [C, C]; LN1 affine folded
+  const float* bc;
+  int nc;                    // rows of Wc (3C or C)
+  int q_off, k_off, v_off;   // first row of q2 / k2 / v2 inside that projection (k_off, v_off < 0: absent, 'C' blocks)
+  const bf16* Wxq;           // image-side query rows  [C, C] (LN1-folded) + bias: 'D' only
+  const float* bxq;
+  const bf16* Wxk;           // image-side key rows    [C, C] (LN1-folded) + bias
+  const float* bxk;
+  const bf16* Wpx;           // proj_x [C, C] ('D' only)
+  float scale_x, scale_c;    // softmax scales of the two branches (natural-log domain)
+  int B, C, heads;
+  float eps;
+  DcaWs ws;
+};
+int meta_pre_run(const MetaPreArgs& a, cudaStream_t s);
+
+struct MetaPostArgs {
+  bf16* c;                   // [B, M, C] meta tokens, updated in place: c += proj(attn_c); c += mlp(LN2(c))
+  const bf16* Wxv;           // image-side value rows [C, C] (LN1-folded) + bias
+  const float* bxv;
+  const bf16* Wp;            // proj_c ('D') / proj ('C')  [C, C]
+  const float* bp;
+  const bf16* W1;            // mlp.0 with LN2 folded [Hd, C]
+  const float* b1;
+  const bf16* W2;            // mlp.3 [C, Hd]
+  const float* b2;
+  int B, C, heads, Hd, parts;
+  float eps;
+  DcaWs ws;
+};
+int meta_post_run(const MetaPostArgs& a, cudaStream_t s);
+
+struct DcaXArgs {
+  const bf16* xt;            // [B, N, C] image tokens after x + dwconv(x) (raw; LayerNorm through stats1)
+  const float* stats1;       // [B*N][parts1][2] partial (sum, sum^2) of the xt rows
+  int parts1;
+  float eps;
+  int do_x;                  // 1: 'D' block (x-branch + c-branch); 0: 'C' block (c-branch only, x untouched)
+  const float* bpx;          // proj_x bias [C]                                  (do_x)
+  bf16* xout;                // [B, N, C]: xt + dx   (may alias xt)              (do_x)
+  float* stats2;             // [B*N][2]: (sum, sum^2) of the stored xout rows   (do_x)
+  DcaGeom g;
+  DcaWs ws;
+  int zsplit;                // test hook: issue the Z accumulation per 64-channel block instead of one MN-major operand spanning C
+};
+struct DcaXParams {
+  DcaGeom g;
+  int do_x, kb, kbr, nx, rq, zsplit, parts1;
+  float eps, inv_c;
+  const float* stats1;
+  const float* cst;
+  const float* bpx;
+  const bf16* xres;
+  bf16* xout;
+  float* stats2;
+  float4* part_ml;
+  float* part_z;
+  int smem_x, smem_kt, smem_qt, smem_vt, smem_p, smem_pc;   // byte offsets of the shared-memory regions
+};
+struct DcaXOp {
+  CUtensorMap tmX, tmKt, tmQt, tmVt;
+  DcaXParams p;
+  int grid = 0, smem_bytes = 0;
+};
+int dca_x_prepare(const DcaXArgs& a, DcaXOp* op);
+int dca_x_run(const DcaXOp& op, cudaStream_t s);
+
 }  // namespace lmv

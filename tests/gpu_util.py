@@ -165,3 +165,54 @@ def ref_attention(q, k, v, scale):
     p = torch.softmax(qf @ kf.transpose(-1, -2) * scale, dim=-1)
     o = (p @ vf).permute(0, 2, 1, 3)
     return o.reshape(o.shape[0], o.shape[1], -1)
+
+
+def dca_block(kind, xt, c, W, heads, scale_x, scale_c, flags=0, stats_parts=1):
+    """Fused 'C' / 'D' block core (lmv_dca_block).  xt [B, N, C] bf16, c [B, 16, C] bf16, W: dict of bf16 weights / fp32 biases
+    (wa, ba, wb, bb, wp1, bp1, wp2, bp2, w1, b1, w2, b2).  Returns (xout, stats2, c_out, workspace)."""
+    B, N, Cc = xt.shape
+    Hd = W["w1"].shape[0]
+    st = torch.stack([xt.float().sum(-1), (xt.float() ** 2).sum(-1)], dim=-1).reshape(B * N, 1, 2)
+    if stats_parts > 1:
+        st = (st / stats_parts).repeat(1, stats_parts, 1)
+    st = st.contiguous()
+    need = int(lib().lmv_dca_workspace_bytes(B, N, Cc, heads))
+    assert need > 0
+    ws = torch.zeros(need, dtype=torch.uint8, device=xt.device)
+    c_out = c.clone()
+    xout = torch.empty_like(xt) if kind == "D" else None
+    stats2 = torch.zeros(B * N, 2, device=xt.device) if kind == "D" else None
+    ok(lib().lmv_dca_block(ord(kind), ptr(xt), ptr(st), stats_parts, ptr(xout), ptr(stats2), ptr(c_out), ptr(W["wa"]), ptr(W["ba"]), ptr(W["wb"]),
+                           ptr(W["bb"]), ptr(W["wp1"]), ptr(W["bp1"]), ptr(W.get("wp2")), ptr(W.get("bp2")), ptr(W["w1"]), ptr(W["b1"]),
+                           ptr(W["w2"]), ptr(W["b2"]), B, N, Cc, heads, Hd, float(scale_x), float(scale_c), ptr(ws), ws.numel(), int(flags), stream()))
+    return xout, stats2, c_out, ws
+
+
+def ref_dca_block(kind, xt, c, W, heads, scale_x, scale_c):
+    """The reference's op order in fp32 (models/lemevit.py:288-302 / :477-486 + :561-564 / :600-601): separate q/k/v projections of
+    the LayerNorm-ed tokens, two scaled_dot_product_attentions, output projections, residuals and the meta-token MLP."""
+    f = lambda k: W[k].float()
+    B, N, Cc = xt.shape
+    ln = lambda t: torch.nn.functional.layer_norm(t, (Cc,), eps=1e-6)
+    xn, cn = ln(xt.float()), ln(c.float())
+    hd = lambda t: t.reshape(t.shape[0], t.shape[1], heads, Cc // heads)
+    if kind == "D":
+        qkv1 = xn @ f("wa").t() + f("ba")
+        qkv2 = cn @ f("wb").t() + f("bb")
+        q1, k1, v1 = qkv1.split(Cc, dim=-1)
+        q2, k2, v2 = qkv2.split(Cc, dim=-1)
+        ax = ref_attention(hd(q1), hd(k2), hd(v2), scale_x)
+        ac = ref_attention(hd(q2), hd(k1), hd(v1), scale_c)
+        xout = xt.float() + ax @ f("wp1").t() + f("bp1")
+        c1 = c.float() + ac @ f("wp2").t() + f("bp2")
+    else:
+        q = cn @ f("wa").t() + f("ba")
+        kv = xn @ f("wb").t() + f("bb")
+        k, v = kv.split(Cc, dim=-1)
+        ac = ref_attention(hd(q), hd(k), hd(v), scale_c)
+        xout = None
+        c1 = c.float() + ac @ f("wp1").t() + f("bp1")
+    h = ln(c1) @ f("w1").t() + f("b1")
+    h = 0.5 * h * (1.0 + torch.erf(h / math.sqrt(2.0)))
+    c2 = c1 + h @ f("w2").t() + f("b2")
+    return xout, c2

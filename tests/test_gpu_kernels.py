@@ -113,6 +113,76 @@ def test_linear_layernorm_fold_large_row_offsets(M, N, K, gelu, ratio):
     assert err < TOL and G.cosine(out, ref) > 0.9999, G.describe_mismatch(out.float(), ref.float(), TOL)
 
 
+def _dca_weights(kind, C, Hd, gain=1.5):
+    W = {}
+    lin = lambda o, i, g=1.0: _rand(o, i, scale=g * i ** -0.5)
+    if kind == "D":
+        W["wa"], W["wb"], W["wp1"], W["wp2"] = lin(3 * C, C, gain), lin(3 * C, C, gain), lin(C, C, 0.6), lin(C, C, 0.6)
+        W["ba"], W["bb"] = torch.randn(3 * C, device="cuda") * 0.2, torch.randn(3 * C, device="cuda") * 0.2
+        W["bp2"] = torch.randn(C, device="cuda") * 0.1
+    else:
+        W["wa"], W["wb"], W["wp1"] = lin(C, C, gain), lin(2 * C, C, gain), lin(C, C, 0.6)
+        W["ba"], W["bb"] = torch.randn(C, device="cuda") * 0.2, torch.randn(2 * C, device="cuda") * 0.2
+    W["bp1"] = torch.randn(C, device="cuda") * 0.1
+    W["w1"], W["w2"] = lin(Hd, C, 0.8), lin(C, Hd, 0.8)
+    W["b1"], W["b2"] = torch.randn(Hd, device="cuda") * 0.2, torch.randn(C, device="cuda") * 0.1
+    return W
+
+
+DCA_SHAPES = [(3, 300, 96, 3), (2, 3136, 96, 3), (2, 784, 192, 6), (5, 784, 192, 6), (2, 200, 64, 2), (2, 1000, 128, 4), (3, 128, 32, 1),
+              (2, 4096, 160, 5), (40, 3136, 96, 3), (160, 784, 192, 6)]
+
+
+@pytest.mark.parametrize("B,N,C,heads", DCA_SHAPES)
+@pytest.mark.parametrize("kind", ["D", "C"])
+def test_dca_block_fused(kind, B, N, C, heads):
+    """Fused cross-attention block core (meta_pre -> dca_x -> meta_post, absorbed projections) against the reference's op order in
+    fp32: DualCrossAttention (models/lemevit.py:252-302) with both residual updates and the meta-token MLP (:561-564), and the
+    CrossAttention variant (:477-486, :600-601).  Partial last tiles (N % 128 != 0), duplicated-row (R <= 64) and full-row
+    layouts, several segments per image, several segments per CTA."""
+    torch.manual_seed(B * 7 + N + C)
+    xt = G.bf(torch.randn(B, N, C, device="cuda") * 1.3 + torch.randn(B, N, 1, device="cuda") * 1.5)
+    c = G.bf(torch.randn(B, 16, C, device="cuda"))
+    W = _dca_weights(kind, C, 4 * C)
+    scale_c = C ** -0.5 if kind == "D" else 32 ** -0.5
+    scale_x = math.log(16) / math.log(N) * C ** -0.5
+    ref_x, ref_c = G.ref_dca_block(kind, xt, c, W, heads, scale_x, scale_c)
+    xout, stats2, c_out, _ = G.dca_block(kind, xt, c, W, heads, scale_x, scale_c, stats_parts=2 if B % 2 else 1)
+    torch.cuda.synchronize()
+    ec = G.rel_err(c_out, ref_c)
+    assert ec < TOL and G.cosine(c_out, ref_c) > 0.9999, f"c: rel err {ec}\n" + G.describe_mismatch(c_out.float().reshape(-1, C), ref_c.reshape(-1, C), TOL)
+    if kind == "D":
+        ex = G.rel_err(xout, ref_x)
+        assert ex < TOL and G.cosine(xout, ref_x) > 0.9999, f"x: rel err {ex}\n" + G.describe_mismatch(xout.float().reshape(-1, C), ref_x.reshape(-1, C), TOL)
+        st = torch.stack([xout.float().sum(-1), (xout.float() ** 2).sum(-1)], dim=-1).reshape(-1, 2)
+        assert torch.allclose(stats2, st, rtol=2e-3, atol=2e-2)
+        # the x-branch update must be visible above the rounding floor (otherwise the check above is vacuous)
+        assert (ref_x - xt.float()).abs().max() > 0.05 * ref_x.abs().max()
+    assert (ref_c - c.float()).abs().max() > 0.05 * ref_c.abs().max()
+    # deterministic, and bit-identical with the per-64-channel issue of the c-branch accumulation
+    x2, _, c2, _ = G.dca_block(kind, xt, c, W, heads, scale_x, scale_c, stats_parts=2 if B % 2 else 1)
+    assert torch.equal(c2, c_out) and (kind == "C" or torch.equal(x2, xout))
+    x3, _, c3, _ = G.dca_block(kind, xt, c, W, heads, scale_x, scale_c, flags=1, stats_parts=2 if B % 2 else 1)
+    assert G.rel_err(c3, ref_c) < TOL
+
+
+def test_dca_block_batch_invariance_and_peaked_softmax():
+    """An image's result does not depend on the batch around it (fixed segments, fixed merge order), and a c-branch softmax that is
+    nearly one-hot with a late maximum (forces the lazy rescale of the TMEM accumulator) stays exact."""
+    B, N, C, heads = 9, 3136, 96, 3
+    torch.manual_seed(5)
+    xt = G.bf(torch.randn(B, N, C, device="cuda"))
+    xt[:, 3000:3010] *= 6.0                       # a few late tokens with large norms -> large scores late in the image
+    c = G.bf(torch.randn(B, 16, C, device="cuda"))
+    W = _dca_weights("D", C, 4 * C, gain=4.0)
+    sc, sx = C ** -0.5, math.log(16) / math.log(N) * C ** -0.5
+    ref_x, ref_c = G.ref_dca_block("D", xt, c, W, heads, sx, sc)
+    xout, _, c_out, _ = G.dca_block("D", xt, c, W, heads, sx, sc)
+    assert G.rel_err(c_out, ref_c) < TOL and G.rel_err(xout, ref_x) < TOL
+    x1, _, c1, _ = G.dca_block("D", xt[4:5].contiguous(), c[4:5].contiguous(), W, heads, sx, sc)
+    assert torch.equal(x1[0], xout[4]) and torch.equal(c1[0], c_out[4])
+
+
 MLP_SHAPES = [(1000, 96, 384), (777, 192, 768), (300, 64, 256), (260, 160, 640), (130, 128, 512), (129, 192, 1280),
               (40000, 96, 384), (25000, 192, 768)]
 

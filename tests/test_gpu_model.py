@@ -80,7 +80,11 @@ def test_backbone_against_reference_golden(path):
             assert tuple(o.shape) == tuple(g[f"out{i}_shape"])
             ref = torch.from_numpy(g[f"out{i}_sample"])
             got = o[:, ::8, ::4, ::4].float().cpu()
-            assert G.rel_err(got, ref) <= 4e-2 and G.cosine(got, ref) > 0.999
+            # raw residual streams after up to 32 bf16 blocks: the max-abs metric grows with the number of elements it is taken
+            # over (16x more tokens at 512^2 than at 256^2), so the large maps get a wider max bound next to an RMS bound
+            rms = float(((got - ref).double().pow(2).mean() / ref.double().pow(2).mean()).sqrt())
+            print(f"{os.path.basename(path)} out{i}: rel-max-err {G.rel_err(got, ref):.4f} rel-rms-err {rms:.4f} cosine {G.cosine(got, ref):.6f}")
+            assert G.rel_err(got, ref) <= (6e-2 if H * W >= 512 * 512 else 4e-2) and rms <= 1.5e-2 and G.cosine(got, ref) > 0.999
 
 
 @pytest.mark.parametrize("name,B,H,W", [("lemevit_micro", 3, 64, 96), ("lemevit_tiny", 4, 224, 224), ("lemevit_small", 2, 160, 160)])
@@ -119,6 +123,27 @@ def test_fused_mlp_schedule_agrees_with_unfused_gemm_schedule():
     eng.set_option("fused_mlp", 1)
     assert n_fused < n_unfused            # one launch instead of two for every fusable MLP
     assert G.rel_err(y, y_unfused) < 1e-2
+    assert torch.equal(m(x).float(), y)
+
+
+@pytest.mark.parametrize("name,B,res", [("lemevit_tiny", 3, 224), ("lemevit_small", 2, 224), ("lemevit_base", 2, 224), ("lemevit_micro", 3, 96)])
+def test_fused_dca_schedule_agrees_with_unfused_schedule(name, B, res):
+    """'C' / 'D' blocks through the fused cross-attention kernels (absorbed projections, 3 launches) against the unfused schedule
+    (~14 launches per 'D' block) and the fp32 oracle; the fused path must not lose accuracy."""
+    cfg, sd, m = _build(name, 2)
+    x = Wt.make_input(B, res, res, 2).cuda().to(torch.bfloat16)
+    eng = m.native_engine(x.device)
+    y = m(x).float()
+    n_fused = eng.launch_count(B, res, res)
+    eng.set_option("fused_dca", 0)
+    y_unfused = m(x).float()
+    n_unfused = eng.launch_count(B, res, res)
+    eng.set_option("fused_dca", 1)
+    assert n_fused < n_unfused
+    ref = O.forward_cls(sd, cfg, x.float().cpu())
+    e_f, e_u = G.rel_err(y.cpu(), ref), G.rel_err(y_unfused.cpu(), ref)
+    print(f"{name}: launches {n_unfused} -> {n_fused}; rel err vs oracle fused {e_f:.4f} unfused {e_u:.4f}")
+    assert e_f <= TOL_MODEL and e_f <= max(1.5 * e_u, 0.012)
     assert torch.equal(m(x).float(), y)
 
 

@@ -28,7 +28,7 @@ has ops && TAILN=90 run ops_base256 200 python tools/quick_bench.py lemevit_base
 if has ncu_metrics; then
   # per-launch device time, DRAM traffic and tensor-pipe work (UTCHMMA math ops: a per-launch counter, unlike the *_realtime ones)
   run ncu_launches 900 ncu --metrics $NCU_METRICS --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-graph --no-e2e --no-eager-reference
+      python tools/ncu_target.py lemevit_base 256 2
 fi
 if has ncu_full; then
   for k in ${NCU_KERNELS:-gemm_bf16}; do
