@@ -193,15 +193,16 @@ int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, l
  *   c [B, 16, C] bf16 updated IN PLACE with the block's whole meta-token update: c += proj(softmax(s_c q k^T) v); c += mlp(norm2(c)).
  * Weights as packed by lemevit_b200/pack.py (bf16 [out, in], LayerNorm affine folded, fp32 biases):
  *   'D': wa = qkv1 [3C, C], wb = qkv2 [3C, C], wp1 = proj_x, wp2 = proj_c;   'C': wa = q [C, C], wb = kv [2C, C], wp1 = proj (wp2 unused);
- *   w1 = mlp.0 [Hd, C] (norm2 folded), w2 = mlp.3 [C, Hd].
+ *   w1 = mlp.0 [Hd, C] (norm2 folded), w2 = mlp.3 [C, Hd];
+ *   wxt = transposed copies of the image-side projections that get absorbed: 'D' [2][C][C] = (wa[0:C]^T, wa[C:2C]^T), 'C' [C][C] = wb[0:C]^T.
  * scale_x / scale_c: softmax scales of the two branches (:235,255-256; 'C': scale_c = head_dim^-0.5, scale_x unused).
  * Requires 16 meta tokens, C = heads * 32 <= 192.  workspace: lmv_dca_workspace_bytes(...) bytes, 256-byte aligned.
  * flags bit 0: issue the c-branch accumulation per 64-channel block (test hook). */
 size_t lmv_dca_workspace_bytes(int B, int N, int C, int heads);
 int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, void* xout, float* stats2, void* c, const void* wa,
-                  const float* ba, const void* wb, const float* bb, const void* wp1, const float* bp1, const void* wp2, const float* bp2,
-                  const void* w1, const float* b1, const void* w2, const float* b2, int B, int N, int C, int heads, int Hd, float scale_x,
-                  float scale_c, void* workspace, size_t workspace_bytes, int flags, void* stream);
+                  const float* ba, const void* wb, const float* bb, const void* wxt, const void* wp1, const float* bp1, const void* wp2,
+                  const float* bp2, const void* w1, const float* b1, const void* w2, const float* b2, int B, int N, int C, int heads, int Hd,
+                  float scale_x, float scale_c, void* workspace, size_t workspace_bytes, int flags, void* stream);
 /* patch gather for the first stem conv 3x3/s2/p1 (models/lemevit.py:699): x NCHW (f32|bf16) ->
  * out[B*Ho*Wo, Kp] bf16 with k = ci*9 + ky*3 + kx, zero padded to Kp = round_up(9*Cin, 8); the conv
  * itself (+ folded BN + GELU, :700-701) is then lmv_linear on the tcgen05 GEMM. */

@@ -75,7 +75,7 @@ SIGNATURES = {
     "lmv_attention_meta_workspace": (_sz, [_i, _i, _i, _i]),
     "lmv_attention_meta": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "lmv_dca_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "lmv_dca_block": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f,
+    "lmv_dca_block": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f,
                            _vp, _sz, _i, _vp]),
     "lmv_stem_im2col": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "lmv_stem_conv1": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

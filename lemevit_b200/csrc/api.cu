@@ -98,6 +98,7 @@ struct BlockW {
   const bf16 *w1, *w2;
   const float *b1, *b2;
   const float *csa, *csb, *cs1;   // column sums of the LayerNorm-folded weights wa, wb, w1 (gemm.cu LN fold)
+  const bf16 *wxqT, *wxkT;        // transposed image-side query ('D') / key ('C', 'D') projections, [C, C] each (fused cross-attention blocks)
 };
 struct StageW {
   const bf16* ds_w = nullptr;
@@ -256,10 +257,12 @@ static void walk(const lmv_config& c, PackWalker& w, lmv_plan* plan) {
         case 'C':
           b.wa = w.h((int64_t)C * C, "q_w"); b.ba = w.f(C, "q_b"); b.csa = w.f(C, "q_colsum");
           b.wb = w.h((int64_t)2 * C * C, "kv_w"); b.bb = w.f(2 * C, "kv_b"); b.csb = w.f(2 * C, "kv_colsum");
+          b.wxkT = w.h((int64_t)C * C, "kv_kT");
           b.wp1 = w.h((int64_t)C * C, "proj_w"); b.bp1 = w.f(C, "proj_b");
           break;
         case 'D':
           b.wa = w.h((int64_t)3 * C * C, "qkv1_w"); b.ba = w.f(3 * C, "qkv1_b"); b.csa = w.f(3 * C, "qkv1_colsum");
+          b.wxqT = w.h((int64_t)C * C, "qkv1_qT"); b.wxkT = w.h((int64_t)C * C, "qkv1_kT");
           b.wb = w.h((int64_t)3 * C * C, "qkv2_w"); b.bb = w.f(3 * C, "qkv2_b"); b.csb = w.f(3 * C, "qkv2_colsum");
           b.wp1 = w.h((int64_t)C * C, "proj_x_w"); b.bp1 = w.f(C, "proj_x_b");
           b.wp2 = w.h((int64_t)C * C, "proj_c_w"); b.bp2 = w.f(C, "proj_c_b");
@@ -526,11 +529,11 @@ struct Builder {
     post.W1 = bw.w1; post.b1 = bw.b1; post.W2 = bw.w2; post.b2 = bw.b2;
     if (D) {
       pre.Wc = bw.wb; pre.bc = bw.bb; pre.nc = 3 * C; pre.q_off = 0; pre.k_off = C; pre.v_off = 2 * C;
-      pre.Wxq = bw.wa; pre.bxq = bw.ba; pre.Wxk = bw.wa + (size_t)C * C; pre.bxk = bw.ba + C; pre.Wpx = bw.wp1;
+      pre.WxqT = bw.wxqT; pre.bxq = bw.ba; pre.WxkT = bw.wxkT; pre.bxk = bw.ba + C; pre.Wpx = bw.wp1;
       post.Wxv = bw.wa + (size_t)2 * C * C; post.bxv = bw.ba + 2 * C; post.Wp = bw.wp2; post.bp = bw.bp2;
     } else {
       pre.Wc = bw.wa; pre.bc = bw.ba; pre.nc = C; pre.q_off = 0; pre.k_off = -1; pre.v_off = -1;
-      pre.Wxk = bw.wb; pre.bxk = bw.bb;
+      pre.WxkT = bw.wxkT; pre.bxk = bw.bb;
       post.Wxv = bw.wb + (size_t)C * C; post.bxv = bw.bb + C; post.Wp = bw.wp1; post.bp = bw.bp1;
     }
     DcaXArgs xa{};
@@ -700,8 +703,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xn, nullptr, B, g.H[i], g.W[i], T, C, stats1);
         if (fuse_dca) {
           b.dca_block('C', xn, stats1, sp, nullptr, nullptr, cc, bw, B, N, C, heads, Hd, 0.f, 1.0f / sqrtf((float)c.head_dim), dca_ws);
-          continue;
-        }
+        } else {
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.wa, bw.ba, B * M, C, C, cqkv, C);
         b.ln_linear(xn, stats1, sp, bw.wb, bw.bb, bw.csb, B * N, 2 * C, C, qkv);
@@ -711,6 +713,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.w1, bw.b1, B * M, Hd, C, chid, Hd, 1);
         b.linear(chid, Hd, bw.w2, bw.b2, B * M, C, Hd, cc, C, 0, cc);
+        }
       } else if (kind == 'D') {
         // forward_with_xc (models/lemevit.py:542-582) + DualCrossAttention (:252-256,288-302)
         const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xbuf[cur ^ 1], nullptr, B, g.H[i], g.W[i], T, C, stats1);
@@ -1213,11 +1216,11 @@ size_t lmv_dca_workspace_bytes(int B, int N, int C, int heads) {
 }
 
 int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, void* xout, float* stats2, void* c, const void* wa,
-                  const float* ba, const void* wb, const float* bb, const void* wp1, const float* bp1, const void* wp2, const float* bp2,
-                  const void* w1, const float* b1, const void* w2, const float* b2, int B, int N, int C, int heads, int Hd, float scale_x,
-                  float scale_c, void* workspace, size_t workspace_bytes, int flags, void* stream) {
+                  const float* ba, const void* wb, const float* bb, const void* wxt, const void* wp1, const float* bp1, const void* wp2,
+                  const float* bp2, const void* w1, const float* b1, const void* w2, const float* b2, int B, int N, int C, int heads, int Hd,
+                  float scale_x, float scale_c, void* workspace, size_t workspace_bytes, int flags, void* stream) {
   if (kind != 'C' && kind != 'D') return fail(LMV_ERR_INVALID, "dca_block: kind must be 'C' or 'D'");
-  if (!xt || !stats1 || !c || !wa || !ba || !wb || !bb || !wp1 || !bp1 || !w1 || !b1 || !w2 || !b2 || !workspace)
+  if (!xt || !stats1 || !c || !wa || !ba || !wb || !bb || !wxt || !wp1 || !bp1 || !w1 || !b1 || !w2 || !b2 || !workspace)
     return fail(LMV_ERR_INVALID, "dca_block: null pointer");
   if (kind == 'D' && (!xout || !stats2 || !wp2 || !bp2)) return fail(LMV_ERR_INVALID, "dca_block: null pointer ('D' block)");
   if (!dca_supported(N, C, heads, kDcaM)) return fail(LMV_ERR_UNSUPPORTED, "dca_block: needs C = heads * 32 <= 192");
@@ -1228,6 +1231,8 @@ int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, voi
   bw.wa = static_cast<const bf16*>(wa); bw.ba = ba; bw.wb = static_cast<const bf16*>(wb); bw.bb = bb;
   bw.wp1 = static_cast<const bf16*>(wp1); bw.bp1 = bp1; bw.wp2 = static_cast<const bf16*>(wp2); bw.bp2 = bp2;
   bw.w1 = static_cast<const bf16*>(w1); bw.b1 = b1; bw.w2 = static_cast<const bf16*>(w2); bw.b2 = b2;
+  if (kind == 'D') { bw.wxqT = static_cast<const bf16*>(wxt); bw.wxkT = bw.wxqT + (size_t)C * C; }
+  else bw.wxkT = static_cast<const bf16*>(wxt);
   Schedule sc;
   Builder b{nullptr, &sc, LMV_OK, false};
   b.dca_block((char)kind, static_cast<const bf16*>(xt), stats1, parts1, static_cast<bf16*>(xout), stats2, static_cast<bf16*>(c), bw, B, N, C,

@@ -187,9 +187,9 @@ struct MetaPreArgs {
   const float* bc;
   int nc;                    // rows of Wc (3C or C)
   int q_off, k_off, v_off;   // first row of q2 / k2 / v2 inside that projection (k_off, v_off < 0: absent, 'C' blocks)
-  const bf16* Wxq;           // image-side query rows  [C, C] (LN1-folded) + bias: 'D' only
+  const bf16* WxqT;          // image-side query projection (LN1-folded) TRANSPOSED: WxqT[j][i] = Wq[i][j], [C, C] + bias [C]: 'D' only
   const float* bxq;
-  const bf16* Wxk;           // image-side key rows    [C, C] (LN1-folded) + bias
+  const bf16* WxkT;          // image-side key projection (LN1-folded) transposed [C, C] + bias [C]
   const float* bxk;
   const bf16* Wpx;           // proj_x [C, C] ('D' only)
   float scale_x, scale_c;    // softmax scales of the two branches (natural-log domain)

@@ -7,9 +7,12 @@
 //   meta_post  merges the c-branch softmax partials of the image-token kernel into Zbar = sum_n softmax_n(Sc) xn[n], then
 //              attn_c = Wv_h Zbar + bv;  c += proj_c(attn_c);  c += mlp(LN2(c))          (:563-564 / :600-601).
 //
-// 16 rows per image are far below a tensor-core tile, so these are CUDA-core kernels: one CTA per image, the 16 rows held in
-// shared memory as fp32, one thread per output column (16 accumulators), weights streamed from L2 with 16-byte loads.  The
-// work is ~6 (pre) + ~10 (post) C^2 MACs per row — 1-6 MFLOP per image.
+// One CTA per image.  16 rows are one eighth of a tcgen05 tile (M = 128) but exactly one warp-level tensor-core tile, so every
+// contraction here is `mma.sync.m16n8k16` (bf16 in, fp32 accumulate): the 16 x K activation sits in shared memory as bf16 (the A
+// fragments of a warp are two 16-byte loads per 32 k), the weights are never staged — each lane reads its B fragment straight from
+// L2 with one 16-byte load per (8 columns x 32 k), by pairing the k indices of the two fragments in the order they lie in memory
+// (a consistent permutation of k on both operands leaves the dot product unchanged).  Per image: ~1.2 MB of weights from L2 and
+// ~19 MFLOP at C = 192, 0.3 MB / 5 MFLOP at C = 96.
 #include <algorithm>
 #include <cmath>
 
@@ -21,7 +24,11 @@ namespace lmv {
 namespace {
 
 constexpr int M = kDcaM;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+// row pitch (bf16 elements) of a 16 x K activation tile in shared memory: pitch bytes = 64 (mod 128), so that the eight lanes of
+// a quarter warp (two rows x four 16-byte chunks) hit 128 distinct bytes when they load their A fragments
+__host__ __device__ inline int pitch(int K) { return K + ((K % 64 == 0) ? 32 : 0); }
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -30,42 +37,65 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// out[m][n] = sum_k in[m][k] W[n][k]  for the 16 rows in shared memory; one thread per output column n, fn(n, acc[16]) consumes
-// the result.  W rows are read with 16-byte loads (K % 8 == 0), `in` rows with broadcast float4 loads (ld = row pitch in floats).
-template <typename Fn>
-__device__ __forceinline__ void rows16_linear(const float* __restrict__ in, int ld, int K, const bf16* __restrict__ W, int ldw,
-                                               int n_begin, int n_end, Fn fn) {
-  for (int n = n_begin + (int)threadIdx.x; n < n_end; n += kThreads) {
-    float acc[M];
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// out[m][n] = sum_k A[m][k] W[n][k] for the 16 rows of an image.  A: bf16 in shared memory, row pitch lda (pitch(K), 16-byte
+// aligned rows); W: bf16 in global memory, K contiguous, row pitch ldw; K % 32 == 0, N % 8 == 0.  Each warp takes groups of four
+// 8-column tiles; epi(n, m, v0, v1) receives out[m][n], out[m][n + 1] (fp32) for the lane's two rows m = g and g + 8.
+// a_group_stride: the A tile used for the 32-column group starting at column n is A0 + (n / 32) * a_group_stride (one A tile per
+// head in the value contraction of meta_post; 0 everywhere else).
+template <typename Epi>
+__device__ __forceinline__ void rows16_mma(const bf16* __restrict__ A0, int lda, const bf16* __restrict__ W, int ldw, int N, int K, Epi epi,
+                                            int a_group_stride = 0) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const int ntiles = N >> 3;
+  for (int tile0 = warp * 4; tile0 < ntiles; tile0 += kWarps * 4) {
+    const int nt = min(4, ntiles - tile0);
+    const bf16* A = A0 + (size_t)(tile0 >> 2) * a_group_stride;
+    float acc[4][4];
 #pragma unroll
-    for (int m = 0; m < M; ++m) acc[m] = 0.f;
-    const uint4* wrow = reinterpret_cast<const uint4*>(W + (size_t)n * ldw);
-    for (int k8 = 0; k8 < K / 8; ++k8) {
-      const uint4 u = __ldg(wrow + k8);
-      const float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
+    for (int t = 0; t < 4; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; acc[t][2] = 0.f; acc[t][3] = 0.f; }
+    const bf16* wrow[4];
 #pragma unroll
-      for (int m = 0; m < M; ++m) {
-        const float4 a = *reinterpret_cast<const float4*>(in + m * ld + k8 * 8);
-        const float4 b = *reinterpret_cast<const float4*>(in + m * ld + k8 * 8 + 4);
-        acc[m] = fmaf(a.x, w0.x, fmaf(a.y, w0.y, fmaf(a.z, w1.x, fmaf(a.w, w1.y, acc[m]))));
-        acc[m] = fmaf(b.x, w2.x, fmaf(b.y, w2.y, fmaf(b.z, w3.x, fmaf(b.w, w3.y, acc[m]))));
+    for (int t = 0; t < 4; ++t) wrow[t] = W + (size_t)((tile0 + min(t, nt - 1)) * 8 + g) * ldw + tq * 8;
+#pragma unroll 2
+    for (int kc = 0; kc < K; kc += 32) {
+      uint4 b[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) b[t] = __ldg(reinterpret_cast<const uint4*>(wrow[t] + kc));
+      const uint4 alo = *reinterpret_cast<const uint4*>(A + (size_t)g * lda + kc + tq * 8);
+      const uint4 ahi = *reinterpret_cast<const uint4*>(A + (size_t)(g + 8) * lda + kc + tq * 8);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        mma_bf16_16816(acc[t], alo.x, ahi.x, alo.y, ahi.y, b[t].x, b[t].y);
+        mma_bf16_16816(acc[t], alo.z, ahi.z, alo.w, ahi.w, b[t].z, b[t].w);
       }
     }
-    fn(n, acc);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (t < nt) {
+        const int n = (tile0 + t) * 8 + tq * 2;
+        epi(n, g, acc[t][0], acc[t][1]);
+        epi(n, g + 8, acc[t][2], acc[t][3]);
+      }
   }
 }
 
-// LayerNorm without affine over the 16 rows (one warp per two rows): out[m][:] = (in[m][:] - mu) rsqrt(var + eps)
-__device__ __forceinline__ void rows16_layernorm(const float* in, float* out, int ld, int C, float eps) {
+// LayerNorm without affine of the 16 fp32 rows -> bf16 rows (A operand of the next contraction); one warp per row
+__device__ __forceinline__ void rows16_layernorm(const float* in, int ld, bf16* out, int ldo, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int m = warp; m < M; m += kThreads / 32) {
+  for (int m = warp; m < M; m += kWarps) {
     float s1 = 0.f;
     for (int k = lane; k < C; k += 32) s1 += in[m * ld + k];
     const float mu = warp_sum(s1) / (float)C;
     float s2 = 0.f;
     for (int k = lane; k < C; k += 32) { const float d = in[m * ld + k] - mu; s2 = fmaf(d, d, s2); }
     const float r = rsqrtf(warp_sum(s2) / (float)C + eps);
-    for (int k = lane; k < C; k += 32) out[m * ld + k] = (in[m * ld + k] - mu) * r;
+    for (int k = lane; k < C; k += 32) out[m * ldo + k] = __float2bfloat16((in[m * ld + k] - mu) * r);
   }
 }
 
@@ -76,54 +106,39 @@ __global__ void __launch_bounds__(kThreads)
 meta_pre_kernel(MetaPreArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int C = a.C, R = a.heads * M, nc = a.nc, b = blockIdx.x;
-  float* s_c = reinterpret_cast<float*>(smem_raw);         // [M][C]   raw, then normalised meta tokens
-  float* s_p = s_c + M * C;                                 // [M][nc]  projection of LN1(c)
-  bf16* s_t = reinterpret_cast<bf16*>(s_p + M * nc);        // [R][C]   staging of Kt / Qt (bf16, as stored)
+  const int lda = pitch(C), ldp = pitch(nc);
+  float* s_c = reinterpret_cast<float*>(smem_raw);                 // [M][C]        raw meta tokens (fp32)
+  bf16* s_n = reinterpret_cast<bf16*>(s_c + M * C);                // [M][C + pad]  LN1(c)
+  bf16* s_p = s_n + M * lda;                                       // [M][nc + pad] projection of LN1(c): q2 | k2 | v2
+  bf16* s_t = s_p + M * ldp;                                       // [R][C] staging of Kt / Qt, [C][R] staging of Vt^T
   pdl_launch_dependents();
   pdl_wait();
   const bf16* cb = a.c + (size_t)b * M * C;
   for (int i = threadIdx.x; i < M * C; i += kThreads) s_c[i] = __bfloat162float(cb[i]);
   __syncthreads();
-  rows16_layernorm(s_c, s_c, C, C, a.eps);     // in place: every element is read and written by the same lane
+  rows16_layernorm(s_c, C, s_n, lda, C, a.eps);
   __syncthreads();
-  rows16_linear(s_c, C, C, a.Wc, C, 0, nc, [&](int n, const float (&acc)[M]) {
-    const float bias = __ldg(a.bc + n);
-#pragma unroll
-    for (int m = 0; m < M; ++m) s_p[m * nc + n] = acc[m] + bias;
+  rows16_mma(s_n, lda, a.Wc, C, nc, C, [&](int n, int m, float v0, float v1) {
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(a.bc + n));
+    *reinterpret_cast<uint32_t*>(s_p + m * ldp + n) = pack_bf16x2(v0 + bias.x, v1 + bias.y);
   });
   __syncthreads();
 
-  // T[(h,m)][j] = scale * sum_d vec[m][32h + d] Wx[32h + d][j]   (Wx: image-side projection rows, [C, C] row-major, j contiguous)
-  // + its row sums (of the bf16-rounded values) and the bias constant scale * sum_d bx[32h + d] vec[m][32h + d]
-  auto absorb = [&](const float* vec /* s_p + offset */, const bf16* Wx, const float* bx, float scale, bf16* out_g, float* sum_g,
-                    float* cst_g) {
-    for (int j2 = threadIdx.x; j2 < C / 2; j2 += kThreads) {
-      for (int h = 0; h < a.heads; ++h) {
-        float2 acc[M];
-#pragma unroll
-        for (int m = 0; m < M; ++m) acc[m] = make_float2(0.f, 0.f);
-        for (int d = 0; d < 32; ++d) {
-          const float2 w = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(Wx + (size_t)(32 * h + d) * C) + j2));
-#pragma unroll
-          for (int m = 0; m < M; ++m) {
-            const float v = vec[m * nc + 32 * h + d];
-            acc[m].x = fmaf(v, w.x, acc[m].x);
-            acc[m].y = fmaf(v, w.y, acc[m].y);
-          }
-        }
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-          *reinterpret_cast<uint32_t*>(s_t + (size_t)(h * M + m) * C + 2 * j2) = pack_bf16x2(acc[m].x * scale, acc[m].y * scale);
-      }
-    }
+  // T[(h,m)][j] = scale * sum_d vec[m][32h + d] Wx[32h + d][j], through the transposed copy WxT[j][i] (K contiguous);
+  // then the row sums of the bf16-rounded T and the bias constant scale * sum_d bx[32h + d] vec[m][32h + d]
+  auto absorb = [&](int off, const bf16* WxT, const float* bx, float scale, bf16* out_g, float* sum_g, float* cst_g) {
+    for (int h = 0; h < a.heads; ++h)
+      rows16_mma(s_p + off + 32 * h, ldp, WxT + 32 * h, C, C, 32, [&](int n, int m, float v0, float v1) {
+        *reinterpret_cast<uint32_t*>(s_t + (size_t)(h * M + m) * C + n) = pack_bf16x2(v0 * scale, v1 * scale);
+      });
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < R; r += kThreads / 32) {
+    for (int r = warp; r < R; r += kWarps) {
       float s = 0.f;
       for (int k = lane; k < C; k += 32) s += __bfloat162float(s_t[(size_t)r * C + k]);
       s = warp_sum(s);
       const int h = r / M, m = r - h * M;
-      const float kc = vec[m * nc + 32 * h + lane] * __ldg(bx + 32 * h + lane);
+      const float kc = __bfloat162float(s_p[m * ldp + off + 32 * h + lane]) * __ldg(bx + 32 * h + lane);
       const float k2 = warp_sum(kc) * scale;
       if (lane == 0) { sum_g[r] = s; cst_g[r] = k2; }
     }
@@ -133,40 +148,20 @@ meta_pre_kernel(MetaPreArgs a) {
     __syncthreads();
   };
   float* cst = a.ws.cst + (size_t)b * 4 * R;
-  if (a.Wxq)   // 'D': x-branch keys in token space
-    absorb(s_p + a.k_off, a.Wxq, a.bxq, a.scale_x * kLog2e, a.ws.kt + (size_t)b * R * C, cst, cst + R);
-  absorb(s_p + a.q_off, a.Wxk, a.bxk, a.scale_c * kLog2e, a.ws.qt + (size_t)b * R * C, cst + 2 * R, cst + 3 * R);
+  if (a.WxqT)   // 'D': x-branch keys in token space
+    absorb(a.k_off, a.WxqT, a.bxq, a.scale_x * kLog2e, a.ws.kt + (size_t)b * R * C, cst, cst + R);
+  absorb(a.q_off, a.WxkT, a.bxk, a.scale_c * kLog2e, a.ws.qt + (size_t)b * R * C, cst + 2 * R, cst + 3 * R);
   if (a.Wpx) {
-    // Vt^T[j][(h,m)] = sum_d Wpx[j][32h + d] v2[m][32h + d]: one thread per output channel j, its row of Vt^T is contiguous
-    const float* v2 = s_p + a.v_off;
-    bf16* vt = a.ws.vt + (size_t)b * C * R;
-    for (int j = threadIdx.x; j < C; j += kThreads) {
-      for (int h = 0; h < a.heads; ++h) {
-        float w[32];
-        const uint4* wr = reinterpret_cast<const uint4*>(a.Wpx + (size_t)j * C + 32 * h);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 u = __ldg(wr + q);
-          const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-          w[8 * q + 0] = f0.x; w[8 * q + 1] = f0.y; w[8 * q + 2] = f1.x; w[8 * q + 3] = f1.y;
-          w[8 * q + 4] = f2.x; w[8 * q + 5] = f2.y; w[8 * q + 6] = f3.x; w[8 * q + 7] = f3.y;
-        }
-        uint32_t pk[M / 2];
-#pragma unroll
-        for (int m = 0; m < M; m += 2) {
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int d = 0; d < 32; ++d) {
-            s0 = fmaf(w[d], v2[m * nc + 32 * h + d], s0);
-            s1 = fmaf(w[d], v2[(m + 1) * nc + 32 * h + d], s1);
-          }
-          pk[m / 2] = pack_bf16x2(s0, s1);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(vt + (size_t)j * R + h * M);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-    }
+    // Vt^T[j][(h,m)] = sum_d Wpx[j][32h + d] v2[m][32h + d]
+    for (int h = 0; h < a.heads; ++h)
+      rows16_mma(s_p + a.v_off + 32 * h, ldp, a.Wpx + 32 * h, C, C, 32, [&](int n, int m, float v0, float v1) {
+        s_t[(size_t)n * R + h * M + m] = __float2bfloat16(v0);
+        s_t[(size_t)(n + 1) * R + h * M + m] = __float2bfloat16(v1);
+      });
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(s_t);
+    uint4* dst = reinterpret_cast<uint4*>(a.ws.vt + (size_t)b * C * R);
+    for (int i = threadIdx.x; i < R * C / 8; i += kThreads) dst[i] = src[i];
   }
 }
 
@@ -177,10 +172,11 @@ __global__ void __launch_bounds__(kThreads)
 meta_post_kernel(MetaPostArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int C = a.C, R = a.heads * M, Hd = a.Hd, b = blockIdx.x, P = a.parts;
-  float* s_c = reinterpret_cast<float*>(smem_raw);   // [M][C]  meta tokens (residual stream, fp32)
-  float* s_a = s_c + M * C;                           // [M][C]  attn_c, later LN2(c)
-  float* s_w = s_a + M * C;                           // [P][R]  merge weights, [R] 1 / l
-  float* s_z = s_w + (P + 1) * R;                     // [R][C]  Zbar; reused as the MLP hidden activation [M][Hd]
+  const int lda = pitch(C), ldh = pitch(Hd);
+  float* s_c = reinterpret_cast<float*>(smem_raw);       // [M][C]   meta tokens (residual stream, fp32)
+  float* s_w = s_c + M * C;                               // [P + 1][R]  merge weights, 1 / l
+  bf16* s_a = reinterpret_cast<bf16*>(s_w + (P + 1) * R); // [M][C + pad]   attn_c, later LN2(c)
+  bf16* s_z = s_a + M * lda;                              // [R][C + pad]   Zbar (bf16); reused as the MLP hidden activation [M][Hd + pad]
   pdl_launch_dependents();
   pdl_wait();
   bf16* cb = a.c + (size_t)b * M * C;
@@ -202,7 +198,7 @@ meta_post_kernel(MetaPostArgs a) {
   __syncthreads();
   const float* pz = a.ws.part_z + (size_t)b * P * R * C;
   for (int i = threadIdx.x; i < R * C / 4; i += kThreads) {
-    const int r = (i * 4) / C;
+    const int r = (i * 4) / C, col = i * 4 - r * C;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p = 0; p < P; ++p) {
       const float w = s_w[p * R + r];
@@ -213,54 +209,37 @@ meta_post_kernel(MetaPostArgs a) {
       acc.z = fmaf(w, z.z - t, acc.z); acc.w = fmaf(w, z.w - t, acc.w);
     }
     const float il = s_w[P * R + r];
-    reinterpret_cast<float4*>(s_z)[i] = make_float4(acc.x * il, acc.y * il, acc.z * il, acc.w * il);
+    uint2 pk;
+    pk.x = pack_bf16x2(acc.x * il, acc.y * il);
+    pk.y = pack_bf16x2(acc.z * il, acc.w * il);
+    *reinterpret_cast<uint2*>(s_z + (size_t)r * lda + col) = pk;
   }
   __syncthreads();
-  // ---- attn_c[m][32h + d] = Wv[32h + d][:] . Zbar[(h,m)][:] + bv   (a warp's 32 output channels share the head: broadcast reads)
-  for (int n = threadIdx.x; n < C; n += kThreads) {
-    const int h = n >> 5;
-    float acc[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) acc[m] = 0.f;
-    const uint4* wrow = reinterpret_cast<const uint4*>(a.Wxv + (size_t)n * C);
-    const float* z = s_z + (size_t)h * M * C;
-    for (int k8 = 0; k8 < C / 8; ++k8) {
-      const uint4 u = __ldg(wrow + k8);
-      const float2 w0 = unpack_bf16x2(u.x), w1 = unpack_bf16x2(u.y), w2 = unpack_bf16x2(u.z), w3 = unpack_bf16x2(u.w);
-#pragma unroll
-      for (int m = 0; m < M; ++m) {
-        const float4 p = *reinterpret_cast<const float4*>(z + m * C + k8 * 8);
-        const float4 q = *reinterpret_cast<const float4*>(z + m * C + k8 * 8 + 4);
-        acc[m] = fmaf(p.x, w0.x, fmaf(p.y, w0.y, fmaf(p.z, w1.x, fmaf(p.w, w1.y, acc[m]))));
-        acc[m] = fmaf(q.x, w2.x, fmaf(q.y, w2.y, fmaf(q.z, w3.x, fmaf(q.w, w3.y, acc[m]))));
-      }
-    }
-    const float bias = __ldg(a.bxv + n);
-#pragma unroll
-    for (int m = 0; m < M; ++m) s_a[m * C + n] = acc[m] + bias;
-  }
+  // ---- attn_c[m][32h + d] = Wv[32h + d][:] . Zbar[(h,m)][:] + bv
+  rows16_mma(s_z, lda, a.Wxv, C, C, C, [&](int n, int m, float v0, float v1) {
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(a.bxv + n));
+    *reinterpret_cast<uint32_t*>(s_a + m * lda + n) = pack_bf16x2(v0 + bias.x, v1 + bias.y);
+  }, M * lda);
   __syncthreads();
   // ---- c += proj(attn_c)
-  rows16_linear(s_a, C, C, a.Wp, C, 0, C, [&](int n, const float (&acc)[M]) {
-    const float bias = __ldg(a.bp + n);
-#pragma unroll
-    for (int m = 0; m < M; ++m) s_c[m * C + n] += acc[m] + bias;
+  rows16_mma(s_a, lda, a.Wp, C, C, C, [&](int n, int m, float v0, float v1) {
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(a.bp + n));
+    s_c[m * C + n] += v0 + bias.x;
+    s_c[m * C + n + 1] += v1 + bias.y;
   });
   __syncthreads();
   // ---- c += mlp(LN2(c))   (LN2 affine folded into W1 / b1)
-  rows16_layernorm(s_c, s_a, C, C, a.eps);
+  rows16_layernorm(s_c, C, s_a, lda, C, a.eps);
   __syncthreads();
-  float* s_h = s_z;
-  rows16_linear(s_a, C, C, a.W1, C, 0, Hd, [&](int n, const float (&acc)[M]) {
-    const float bias = __ldg(a.b1 + n);
-#pragma unroll
-    for (int m = 0; m < M; ++m) s_h[m * Hd + n] = gelu_erf(acc[m] + bias);
+  bf16* s_h = s_z;
+  rows16_mma(s_a, lda, a.W1, C, Hd, C, [&](int n, int m, float v0, float v1) {
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(a.b1 + n));
+    *reinterpret_cast<uint32_t*>(s_h + (size_t)m * ldh + n) = pack_bf16x2(gelu_erf(v0 + bias.x), gelu_erf(v1 + bias.y));
   });
   __syncthreads();
-  rows16_linear(s_h, Hd, Hd, a.W2, Hd, 0, C, [&](int n, const float (&acc)[M]) {
-    const float bias = __ldg(a.b2 + n);
-#pragma unroll
-    for (int m = 0; m < M; ++m) cb[m * C + n] = __float2bfloat16(s_c[m * C + n] + acc[m] + bias);
+  rows16_mma(s_h, ldh, a.W2, Hd, C, Hd, [&](int n, int m, float v0, float v1) {
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(a.b2 + n));
+    *reinterpret_cast<uint32_t*>(cb + m * C + n) = pack_bf16x2(s_c[m * C + n] + v0 + bias.x, s_c[m * C + n + 1] + v1 + bias.y);
   });
 }
 
@@ -307,11 +286,11 @@ DcaWs dca_workspace_carve(const DcaGeom& g, void* base) {
 }
 
 int meta_pre_run(const MetaPreArgs& a, cudaStream_t s) {
-  LMV_REQUIRE(a.c && a.Wc && a.bc && a.Wxk && a.bxk && a.ws.qt && a.ws.cst, "meta_pre: null pointer");
-  LMV_REQUIRE((a.Wxq == nullptr) == (a.Wpx == nullptr), "meta_pre: Wxq and Wpx go together (x-branch)");
+  LMV_REQUIRE(a.c && a.Wc && a.bc && a.WxkT && a.bxk && a.ws.qt && a.ws.cst, "meta_pre: null pointer");
+  LMV_REQUIRE((a.WxqT == nullptr) == (a.Wpx == nullptr), "meta_pre: WxqT and Wpx go together (x-branch)");
   LMV_REQUIRE(a.C % 32 == 0 && a.heads * 32 == a.C && a.nc % 8 == 0, "meta_pre: C must be heads * 32");
   const int R = a.heads * M;
-  const size_t smem = (size_t)M * a.C * 4 + (size_t)M * a.nc * 4 + (size_t)R * a.C * 2;
+  const size_t smem = (size_t)M * a.C * 4 + (size_t)M * pitch(a.C) * 2 + (size_t)M * pitch(a.nc) * 2 + (size_t)R * a.C * 2;
   LMV_REQUIRE(smem <= (size_t)kMetaSmemMax, "meta_pre: shared memory budget");
   LMV_CUDA_OK(g_pre_once.run([] { return cudaFuncSetAttribute(meta_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetaSmemMax); }));
   LMV_CUDA_OK(launch_kernel(meta_pre_kernel, dim3(a.B), dim3(kThreads), smem, s, a));
@@ -321,10 +300,10 @@ int meta_pre_run(const MetaPreArgs& a, cudaStream_t s) {
 
 int meta_post_run(const MetaPostArgs& a, cudaStream_t s) {
   LMV_REQUIRE(a.c && a.Wxv && a.bxv && a.Wp && a.bp && a.W1 && a.b1 && a.W2 && a.b2 && a.ws.part_ml && a.ws.part_z, "meta_post: null pointer");
-  LMV_REQUIRE(a.C % 32 == 0 && a.heads * 32 == a.C && a.Hd % 8 == 0 && a.parts >= 1, "meta_post: shape");
+  LMV_REQUIRE(a.C % 32 == 0 && a.heads * 32 == a.C && a.Hd % 32 == 0 && a.parts >= 1, "meta_post: shape");
   const int R = a.heads * M;
-  const size_t zbytes = std::max((size_t)R * a.C, (size_t)M * a.Hd) * 4;
-  const size_t smem = (size_t)2 * M * a.C * 4 + (size_t)(a.parts + 1) * R * 4 + zbytes;
+  const size_t zbytes = std::max((size_t)R * pitch(a.C), (size_t)M * pitch(a.Hd)) * 2;
+  const size_t smem = (size_t)M * a.C * 4 + (size_t)(a.parts + 1) * R * 4 + (size_t)M * pitch(a.C) * 2 + zbytes;
   LMV_REQUIRE(smem <= (size_t)kMetaSmemMax, "meta_post: shared memory budget");
   LMV_CUDA_OK(g_post_once.run([] { return cudaFuncSetAttribute(meta_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetaSmemMax); }));
   LMV_CUDA_OK(launch_kernel(meta_post_kernel, dim3(a.B), dim3(kThreads), smem, s, a));

@@ -27,7 +27,7 @@ struct PosTileParams {
   const float* dw_b;   // [C]
   bf16* out;           // [B, T, C]
   float* stats;        // [B*T][2] or null
-  int H, W, T, C;
+  int B, H, W, T, C;
   int TW, TH, tiles_x, tiles_y;
   int cbox, ncb;       // channel box of one TMA load, number of boxes per CTA (CS = cbox * ncb)
   int CS, parts;       // channels per CTA (blockIdx.z selects the slice) and slices per row; C = CS * parts
@@ -41,133 +41,170 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 
+// Persistent CTAs (grid.x strides over the (image, tile) items of one channel slice) with a double-buffered input tile: the TMA
+// load of item i+1 is in flight while item i is computed, and the depthwise taps are fetched once per CTA instead of once per tile.
+// Thread = (column tx of the tile, 8-channel vector v); it streams the TH + 2 input rows of its column ONCE: every input row
+// (3 x LDS.128, unpacked once) feeds the three output rows it touches through three rotating accumulators, so an output element
+// costs 3 shared loads + 36 packed FMAs instead of 9 loads + 9 unpacks + 72 FMAs (the one-shot version was issue-bound at 57 %).
 __global__ void __launch_bounds__(kThreads)
 posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (128u - (smem_u32(smem_raw) & 127u)) & 127u;
   uint8_t* smem = smem_raw + pad;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  const int C = p.C, V = p.CS >> 3, HW = p.H * p.W;   // V: 16-byte channel vectors of this CTA's slice
-  const int b = blockIdx.y, slice = blockIdx.z, c_off = slice * p.CS;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);           // full[2]
+  const int C = p.C, V = p.CS >> 3, HW = p.H * p.W;            // V: 16-byte channel vectors of this CTA's slice
+  const int slice = blockIdx.z, c_off = slice * p.CS;
   const int ntiles = p.tiles_x * p.tiles_y;
   pdl_launch_dependents();
   pdl_wait();
 
-  if ((int)blockIdx.x >= ntiles) {
+  if (blockIdx.y == 1) {
     // ---- meta-token rows of a unified buffer: copy + statistics, one warp per row ----
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;          // blockDim need not be a multiple of 32: use the full warps only
     if (warp >= nwarps || slice != 0) return;   // slice 0 copies the whole row; the other partials of the row are zero
-    for (int t = HW + warp; t < p.T; t += nwarps) {
-      const long long row = (long long)b * p.T + t;
-      float s1 = 0.f, s2 = 0.f;
-      for (int v = lane; v < (C >> 3); v += 32) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.tokens + row * C) + v);
-        float f[8];
-        unpack8(u, f);
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x)
+      for (int t = HW + warp; t < p.T; t += nwarps) {
+        const long long row = (long long)b * p.T + t;
+        float s1 = 0.f, s2 = 0.f;
+        for (int v = lane; v < (C >> 3); v += 32) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.tokens + row * C) + v);
+          float f[8];
+          unpack8(u, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
-        reinterpret_cast<uint4*>(p.out + row * C)[v] = u;
-      }
+          for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+          reinterpret_cast<uint4*>(p.out + row * C)[v] = u;
+        }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane < p.parts && p.stats)
+          *reinterpret_cast<float2*>(p.stats + 2 * (row * p.parts + lane)) = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
       }
-      if (lane < p.parts && p.stats)
-        *reinterpret_cast<float2*>(p.stats + 2 * (row * p.parts + lane)) = lane == 0 ? make_float2(s1, s2) : make_float2(0.f, 0.f);
-    }
     return;
   }
 
-  const int tile_y = blockIdx.x / p.tiles_x, tile_x = blockIdx.x % p.tiles_x;
-  const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
   const int IW = p.TW + 2, IH = p.TH + 2;
-  const int sub_bytes = p.sub_bytes;                             // one channel box of the input tile
-  uint8_t* s_tile = smem + 128;
-  float2* s_part = reinterpret_cast<float2*>(s_tile + (size_t)p.ncb * sub_bytes);   // [TH*TW][V] partial statistics
-  (void)IH;
-
+  const int in_bytes = p.ncb * p.sub_bytes;                              // one input tile (all channel boxes of the slice)
+  uint8_t* s_in = smem + 128;                                            // [2][in_bytes]
+  float2* s_part = reinterpret_cast<float2*>(s_in + 2 * (size_t)in_bytes);   // [2][TH*TW][V] partial statistics
+  const int part_elems = p.TH * p.TW * V;
+  const int n_items = ntiles * p.B;
+  auto issue = [&](int item, int buf) {
+    const int b = item / ntiles, t = item - b * ntiles;
+    const int tile_y = t / p.tiles_x, tile_x = t - tile_y * p.tiles_x;
+    mbar_expect_tx(&bar[buf], (uint32_t)(p.ncb * IH * IW * p.cbox * 2));
+    for (int cb = 0; cb < p.ncb; ++cb)
+      tma_load_4d(s_in + (size_t)buf * in_bytes + (size_t)cb * p.sub_bytes, &tm, &bar[buf], c_off + cb * p.cbox, tile_x * p.TW - 1, tile_y * p.TH - 1, b);
+  };
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     fence_mbar_init();
-    mbar_expect_tx(bar, (uint32_t)(p.ncb * IH * IW * p.cbox * 2));
-    for (int cb = 0; cb < p.ncb; ++cb) tma_load_4d(s_tile + (size_t)cb * sub_bytes, &tm, bar, c_off + cb * p.cbox, x0 - 1, y0 - 1, b);
+    if ((int)blockIdx.x < n_items) issue(blockIdx.x, 0);
   }
-  // blockDim is a multiple of V, so every thread keeps ONE channel vector for all its items: its 9 x 8 depthwise taps
-  // and 8 biases live in registers (shared-memory bandwidth is spent on activations only)
-  const int v = threadIdx.x % V;
-  float w[9][8], bias[8];
+  // one (column, channel vector) per thread: its 9 x 8 depthwise taps and 8 biases live in registers as packed pairs
+  const bool active = (int)threadIdx.x < p.TW * V;
+  const int tx = active ? (int)threadIdx.x / V : 0, v = active ? (int)threadIdx.x - tx * V : 0;
+  float2 w[9][4], bias[4];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.dw_w + tap * C + c_off + v * 8));
     const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.dw_w + tap * C + c_off + v * 8) + 1);
-    w[tap][0] = w0.x; w[tap][1] = w0.y; w[tap][2] = w0.z; w[tap][3] = w0.w;
-    w[tap][4] = w1.x; w[tap][5] = w1.y; w[tap][6] = w1.z; w[tap][7] = w1.w;
+    w[tap][0] = make_float2(w0.x, w0.y); w[tap][1] = make_float2(w0.z, w0.w);
+    w[tap][2] = make_float2(w1.x, w1.y); w[tap][3] = make_float2(w1.z, w1.w);
   }
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.dw_b + c_off + v * 8));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.dw_b + c_off + v * 8) + 1);
-    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w; bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    bias[0] = make_float2(b0.x, b0.y); bias[1] = make_float2(b0.z, b0.w); bias[2] = make_float2(b1.x, b1.y); bias[3] = make_float2(b1.z, b1.w);
   }
+  const int vpb = p.cbox >> 3;                     // 16-byte vectors per channel box
+  const int cb = v / vpb, vv = v - cb * vpb;
+  const int row_pitch = IW * p.cbox * 2, col_pitch = p.cbox * 2;
   __syncthreads();          // barrier init visible to every waiter
-  mbar_wait(bar, 0, 20);
 
-  const int vpb = p.cbox >> 3;   // 16-byte vectors per channel box
-  const int items = p.TW * p.TH * V;
-  // blockDim is a multiple of V: a thread's token index advances by blockDim / V per trip, so (tx, ty) are stepped
-  // instead of divided out of the item index
-  const int tok_step = blockDim.x / V;
-  int tx = (threadIdx.x / V) % p.TW, ty = (threadIdx.x / V) / p.TW;
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int x = x0 + tx, y = y0 + ty;
-    float2 part = make_float2(0.f, 0.f);
-    if (x < p.W && y < p.H) {
-      const int cb = v / vpb, vv = v - cb * vpb;
-      const uint8_t* base = s_tile + (size_t)cb * sub_bytes + (size_t)vv * 16;
-      float acc[8];
+  int it = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    // prefetch the next item into the other buffer: its previous reader (item it - 1) finished before the trailing __syncthreads
+    if (threadIdx.x == 0 && item + (int)gridDim.x < n_items) issue(item + gridDim.x, buf ^ 1);
+    const int b = item / ntiles, t = item - b * ntiles;
+    const int tile_y = t / p.tiles_x, tile_x = t - tile_y * p.tiles_x;
+    const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
+    mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u, 20);
+    float2* part = s_part + (size_t)buf * part_elems;
+    if (active) {
+      const int x = x0 + tx;
+      const bool xok = x < p.W;
+      const uint8_t* base = s_in + (size_t)buf * in_bytes + (size_t)cb * p.sub_bytes + (size_t)tx * col_pitch + (size_t)vv * 16;
+      const long long row0 = (long long)b * p.T + (long long)y0 * p.W + x;
+      float2 a0[4], a1[4], a2[4];    // accumulators of output rows (ir), (ir - 1), (ir - 2), rotated by the 3x unrolled loop
+      // one input row: three 16-byte vectors (kx = 0..2) feed NEW (ky = 0), MID (ky = 1) and OLD (ky = 2); OLD is then complete
+      auto step = [&](int ir, float2 (&NEW)[4], float2 (&MID)[4], float2 (&OLD)[4]) {
+        float2 in[3][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = bias[j];
-      uint4 u[9];
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)ir * row_pitch + (size_t)kx * col_pitch);
+          in[kx][0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+          in[kx][1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+          in[kx][2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+          in[kx][3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+        }
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+        for (int j = 0; j < 4; ++j) {
+          NEW[j] = ffma2(in[0][j], w[0][j], bias[j]);
+          NEW[j] = ffma2(in[1][j], w[1][j], NEW[j]);
+          NEW[j] = ffma2(in[2][j], w[2][j], NEW[j]);
+          MID[j] = ffma2(in[0][j], w[3][j], MID[j]);
+          MID[j] = ffma2(in[1][j], w[4][j], MID[j]);
+          MID[j] = ffma2(in[2][j], w[5][j], MID[j]);
+          OLD[j] = ffma2(in[0][j], w[6][j], OLD[j]);
+          OLD[j] = ffma2(in[1][j], w[7][j], OLD[j]);
+          OLD[j] = ffma2(in[2][j], w[8][j], OLD[j]);
+        }
+        const int ty = ir - 2;                      // the output row that is complete now
+        if (ty >= 0) {
+          float2 st = make_float2(0.f, 0.f);
+          if (xok && y0 + ty < p.H) {
+            uint4 pk;
+            pk.x = pack_bf16x2(OLD[0].x, OLD[0].y); pk.y = pack_bf16x2(OLD[1].x, OLD[1].y);
+            pk.z = pack_bf16x2(OLD[2].x, OLD[2].y); pk.w = pack_bf16x2(OLD[3].x, OLD[3].y);
+            reinterpret_cast<uint4*>(p.out + (row0 + (long long)ty * p.W) * C + c_off)[v] = pk;
+            // statistics of the STORED (bf16-rounded) values: exactly what the consuming GEMM reads
+            float f[8];
+            unpack8(pk, f);
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-          u[ky * 3 + kx] = *reinterpret_cast<const uint4*>(base + (size_t)((ty + ky) * IW + tx + kx) * (p.cbox * 2));
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        float f[8];
-        unpack8(u[tap], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[tap][j], acc[j]);
+            for (int j = 0; j < 8; ++j) { st.x += f[j]; st.y = fmaf(f[j], f[j], st.y); }
+          }
+          if (p.stats) part[(ty * p.TW + tx) * V + v] = st;
+        }
+      };
+      int ir = 0;
+      for (; ir + 2 < IH; ir += 3) {
+        step(ir, a0, a1, a2);
+        step(ir + 1, a2, a0, a1);
+        step(ir + 2, a1, a2, a0);
       }
-      uint4 pk;
-      pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
-      pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
-      const long long row = (long long)b * p.T + (long long)y * p.W + x;
-      reinterpret_cast<uint4*>(p.out + row * C + c_off)[v] = pk;
-      // statistics of the STORED (bf16-rounded) values: exactly what the consuming GEMM reads
-      unpack8(pk, acc);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { part.x += acc[j]; part.y = fmaf(acc[j], acc[j], part.y); }
+      if (ir < IH) { step(ir, a0, a1, a2); ++ir; }
+      if (ir < IH) { step(ir, a2, a0, a1); }
     }
-    if (p.stats) s_part[i] = part;
-    tx += tok_step;
-    while (tx >= p.TW) { tx -= p.TW; ++ty; }
-  }
-  if (p.stats) {
     __syncthreads();
-    for (int tok = threadIdx.x; tok < p.TW * p.TH; tok += blockDim.x) {
-      const int tx = tok % p.TW, ty = tok / p.TW;
-      const int x = x0 + tx, y = y0 + ty;
-      if (x >= p.W || y >= p.H) continue;
-      float s1 = 0.f, s2 = 0.f;
-      for (int vv = 0; vv < V; ++vv) {
-        const float2 q = s_part[tok * V + vv];
-        s1 += q.x; s2 += q.y;
+    if (p.stats) {
+      for (int tok = threadIdx.x; tok < p.TW * p.TH; tok += blockDim.x) {
+        const int ty = tok / p.TW, txx = tok - ty * p.TW;
+        const int x = x0 + txx, y = y0 + ty;
+        if (x >= p.W || y >= p.H) continue;
+        float s1 = 0.f, s2 = 0.f;
+        for (int q = 0; q < V; ++q) {
+          const float2 pq = part[tok * V + q];
+          s1 += pq.x; s2 += pq.y;
+        }
+        const long long row = (long long)b * p.T + (long long)y * p.W + x;
+        *reinterpret_cast<float2*>(p.stats + 2 * (row * p.parts + slice)) = make_float2(s1, s2);
       }
-      const long long row = (long long)b * p.T + (long long)y * p.W + x;
-      *reinterpret_cast<float2*>(p.stats + 2 * (row * p.parts + slice)) = make_float2(s1, s2);
     }
   }
 }
@@ -207,8 +244,9 @@ int posembed_tile_prepare(const PosLnArgs& a, PosEmbedOp* op) {
   op->tiles_x = (a.W + TW - 1) / TW;
   op->tiles_y = (a.H + TH - 1) / TH;
   op->sub_bytes = (((TH + 2) * (TW + 2) * op->cbox * 2 + 127) / 128) * 128;
-  op->threads = (CS / 8) * (kThreads / (CS / 8));     // multiple of V = CS/8, <= 256
-  op->smem = 128 + 128 + op->ncb * op->sub_bytes + TH * TW * (CS / 8) * 8;
+  LMV_REQUIRE(TW * (CS / 8) <= kThreads, "posembed: one thread per (tile column, channel vector) must fit the CTA");
+  op->threads = ((TW * (CS / 8) + 31) / 32) * 32;     // one thread per (tile column, 8-channel vector)
+  op->smem = 128 + 128 + 2 * op->ncb * op->sub_bytes + 2 * TH * TW * (CS / 8) * 8;
   LMV_REQUIRE(op->smem <= 200 * 1024, "posembed: tile does not fit in shared memory");
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
   uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)a.W * C * 2, (uint64_t)a.T * C * 2};
@@ -225,8 +263,12 @@ int posembed_tile_run(const PosEmbedOp& op, cudaStream_t s) {
   p.tokens = a.tokens; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.out = a.resid_out; p.stats = a.stats_out;
   p.H = a.H; p.W = a.W; p.T = a.T; p.C = a.C;
   p.TW = op.TW; p.TH = op.TH; p.tiles_x = op.tiles_x; p.tiles_y = op.tiles_y; p.cbox = op.cbox; p.ncb = op.ncb;
-  p.sub_bytes = op.sub_bytes; p.parts = op.parts; p.CS = a.C / op.parts;
-  dim3 grid(op.tiles_x * op.tiles_y + (a.T > a.H * a.W ? 1 : 0), a.B, op.parts);
+  p.sub_bytes = op.sub_bytes; p.parts = op.parts; p.CS = a.C / op.parts; p.B = a.B;
+  // persistent CTAs: as many as can be resident (shared memory / registers allow 2-3 per SM), striding over the (image, tile) items;
+  // blockIdx.y == 1: the CTAs that pass the meta-token rows of a unified buffer through
+  const int n_items = op.tiles_x * op.tiles_y * a.B;
+  const int per_sm = std::max(1, std::min(3, (200 * 1024) / std::max(op.smem, 1)));
+  dim3 grid(std::min(n_items, per_sm * device_sm_count()), a.T > a.H * a.W ? 2 : 1, op.parts);
   LMV_CUDA_OK(launch_kernel(posembed_tile_kernel, dim3(grid), dim3(op.threads), (size_t)(op.smem), s, op.tm, p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;

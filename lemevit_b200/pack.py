@@ -17,8 +17,9 @@ ORDER of the packed list (checked entry by entry by ``lmv_plan_create`` in csrc/
       if i > 0:  [ds_w bf16[Ci, 9*Cp], ds_b f32[Ci]]   (absent when stage i-1 is 'C': nn.Identity, :711-712)
       md_w0 bf16[4Cp,Cp] md_b0 f32 md_g1 f32 md_be1 f32 md_w3 bf16[Ci,4Cp] md_b3 f32 md_g4 f32 md_be4 f32
       for each block:  dw_w f32[9,C] dw_b f32[C]
-          'C': q_w q_b q_cs kv_w kv_b kv_cs proj_w proj_b
-          'D': qkv1_w qkv1_b qkv1_cs qkv2_w qkv2_b qkv2_cs proj_x_w proj_x_b proj_c_w proj_c_b
+          'C': q_w q_b q_cs kv_w kv_b kv_cs kv_kT proj_w proj_b
+          'D': qkv1_w qkv1_b qkv1_cs qkv1_qT qkv1_kT qkv2_w qkv2_b qkv2_cs proj_x_w proj_x_b proj_c_w proj_c_b
+               (*_qT / *_kT: bf16 [C, C] transposes of the query / key rows, for the fused cross-attention blocks)
           'S': qkv_w qkv_b qkv_cs proj_w proj_b          then: mlp0_w mlp0_b mlp0_cs mlp3_w mlp3_b
           (weights bf16 [out,in], biases f32, *_cs = f32[out] column sums of the bf16 LayerNorm-folded weight)
   classification only:  bn_scale bn_shift norm_c_g norm_c_b (f32[CL])  [head_w bf16[ncls, CL], head_b f32[ncls]]
@@ -127,6 +128,12 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], *, depth: Sequence[int], embed_
                     h(w); f(b)
                     # column sums of the weights AS STORED (bf16): LN(y) W^T = r (y W^T - mu colsum), csrc/gemm.cu
                     f(w.to(torch.bfloat16).to(torch.float64).sum(dim=1))
+                    # transposed copies of the image-side query / key projections for the fused cross-attention blocks, which absorb
+                    # them into per-image operands (csrc/kernels.h): T[(h,m)][j] = sum_i vec[m][i] W[i][j] needs W^T with i contiguous
+                    if lin == "attn.qkv1":
+                        h(w[:C].t()); h(w[C:2 * C].t())
+                    elif lin == "attn.kv":
+                        h(w[:C].t())
     # ---- tail
     if not backbone:
         s = _d(sd["norm.weight"]) / torch.sqrt(_d(sd["norm.running_var"]) + BN_EPS)

@@ -182,8 +182,12 @@ def dca_block(kind, xt, c, W, heads, scale_x, scale_c, flags=0, stats_parts=1):
     c_out = c.clone()
     xout = torch.empty_like(xt) if kind == "D" else None
     stats2 = torch.zeros(B * N, 2, device=xt.device) if kind == "D" else None
+    if kind == "D":   # transposed copies of the absorbed image-side projections (pack.py emits them next to qkv1 / kv)
+        wxt = torch.stack([W["wa"][:Cc].t(), W["wa"][Cc:2 * Cc].t()]).contiguous()
+    else:
+        wxt = W["wb"][:Cc].t().contiguous()
     ok(lib().lmv_dca_block(ord(kind), ptr(xt), ptr(st), stats_parts, ptr(xout), ptr(stats2), ptr(c_out), ptr(W["wa"]), ptr(W["ba"]), ptr(W["wb"]),
-                           ptr(W["bb"]), ptr(W["wp1"]), ptr(W["bp1"]), ptr(W.get("wp2")), ptr(W.get("bp2")), ptr(W["w1"]), ptr(W["b1"]),
+                           ptr(W["bb"]), ptr(wxt), ptr(W["wp1"]), ptr(W["bp1"]), ptr(W.get("wp2")), ptr(W.get("bp2")), ptr(W["w1"]), ptr(W["b1"]),
                            ptr(W["w2"]), ptr(W["b2"]), B, N, Cc, heads, Hd, float(scale_x), float(scale_c), ptr(ws), ws.numel(), int(flags), stream()))
     return xout, stats2, c_out, ws
 

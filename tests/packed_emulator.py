@@ -86,9 +86,11 @@ def forward(packed, x, *, depth, embed_dim, attn_type, head_dim, queries_len, nu
         for j in range(depth[i]):
             dw_w, dw_b = nx(), nx()
             if kind == "C":
-                wq, bq, csq, wkv, bkv, cskv, wp, bp = [nx() for _ in range(8)]
+                wq, bq, csq, wkv, bkv, cskv, wkT, wp, bp = [nx() for _ in range(9)]
+                assert torch.equal(wkT, wkv[:C].t())       # transposed key rows for the fused cross-attention kernels
             elif kind == "D":
-                wa, ba, csa, wb, bb, csb, wpx, bpx, wpc, bpc = [nx() for _ in range(10)]
+                wa, ba, csa, wqT, wkT, wb, bb, csb, wpx, bpx, wpc, bpc = [nx() for _ in range(12)]
+                assert torch.equal(wqT, wa[:C].t()) and torch.equal(wkT, wa[C:2 * C].t())
             else:
                 wqkv, bqkv, csqkv, wp, bp = [nx() for _ in range(5)]
             w1, b1, cs1, w2, b2 = [nx() for _ in range(5)]
