@@ -388,6 +388,33 @@ struct Builder {
   bool simt;
   void* cpart = nullptr;      // split-softmax partials of the meta-token attention
   size_t cpart_bytes = 0;
+  // meta-token update of the last fused cross-attention block, not launched yet: it is chained with the operand build (meta_pre) of
+  // the next block of the stage into ONE launch (meta_chain_run); flushed on its own at the end of a stage
+  bool has_post = false;
+  MetaPostArgs pending_post;
+  double pending_post_flops = 0;
+
+  void flush_meta(const MetaPreArgs* pre = nullptr, double pre_flops = 0) {
+    if (rc || (!has_post && !pre)) return;
+    const MetaPostArgs post = pending_post;
+    const bool chain = has_post && pre && post.c == pre->c && post.C == pre->C && post.B == pre->B;
+    char d[160];
+    if (has_post && !chain) {
+      snprintf(d, sizeof(d), "meta_post B=%d C=%d", post.B, post.C);
+      sc->push([post](cudaStream_t s) { return meta_chain_run(&post, nullptr, s); }, OP_META, pending_post_flops, 0.0, d);
+    }
+    if (pre) {
+      const MetaPreArgs p2 = *pre;
+      if (chain) {
+        snprintf(d, sizeof(d), "meta_post+pre B=%d C=%d", post.B, post.C);
+        sc->push([post, p2](cudaStream_t s) { return meta_chain_run(&post, &p2, s); }, OP_META, pending_post_flops + pre_flops, 0.0, d);
+      } else {
+        snprintf(d, sizeof(d), "meta_pre B=%d C=%d", p2.B, p2.C);
+        sc->push([p2](cudaStream_t s) { return meta_chain_run(nullptr, &p2, s); }, OP_META, pre_flops, 0.0, d);
+      }
+    }
+    has_post = false;
+  }
 
   void gemm(GemmArgs a) {
     if (rc) return;
@@ -545,14 +572,14 @@ struct Builder {
     if (rc) return;
     const double rows = (double)B * 16, R = g.R;
     char d[160];
-    snprintf(d, sizeof(d), "meta_pre B=%d C=%d %c", B, C, kind);
-    sc->push([pre](cudaStream_t s) { return meta_pre_run(pre, s); }, OP_META, 2.0 * rows * C * (pre.nc + (D ? 3.0 : 1.0) * C), 0.0, d);
+    flush_meta(&pre, 2.0 * rows * C * (pre.nc + (D ? 3.0 : 1.0) * C));
     // algorithmic FLOPs of what the kernel replaces (SURVEY.md section 8d accounting): the image-side projections + both attentions
     const double fl = 2.0 * B * N * ((D ? 4.0 : 2.0) * C * C + (D ? 2.0 : 1.0) * 2.0 * 16.0 * C);
     snprintf(d, sizeof(d), "dca_x B=%d N=%d C=%d %c", B, N, C, kind);
     sc->push([op](cudaStream_t s) { return dca_x_run(op, s); }, OP_DCA, fl, 2.0 * B * N * C * (D ? 2.0 : 1.0), d);
-    snprintf(d, sizeof(d), "meta_post B=%d C=%d %c", B, C, kind);
-    sc->push([post](cudaStream_t s) { return meta_post_run(post, s); }, OP_META, 2.0 * rows * C * (2.0 * C + 2.0 * Hd) + 2.0 * B * R * C * g.parts, 0.0, d);
+    pending_post = post;
+    pending_post_flops = 2.0 * rows * C * (2.0 * C + 2.0 * Hd) + 2.0 * B * R * C * g.parts;
+    has_post = true;
   }
   void attn(const bf16* q, long long q_bs, int q_rs, const bf16* k, const bf16* v, long long kv_bs, int kv_rs, bf16* out,
             long long o_bs, int o_rs, int B, int heads, int Lq, int Lk, float scale) {
@@ -677,6 +704,19 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
             return LMV_OK;
           });
         }
+        if (!b.simt && M == kDcaM && meta_downsample_supported(Cp, C)) {
+          // one kernel per stage transition (meta_branch.cu) instead of gather + linear + LN/GELU + linear + LN
+          MetaDsArgs da{};
+          if (c_prev_unified) { da.in = c_prev_unified + (size_t)g.N[i - 1] * Cp; da.in_bs = (long long)g.T[i - 1] * Cp; }
+          else { da.in = cbuf[ccur]; da.in_bs = (long long)M * Cp; }
+          if (uni) { da.out = xbuf[cur] + (size_t)N * C; da.out_bs = (long long)T * C; }
+          else { da.out = cbuf[ccur ^ 1]; da.out_bs = (long long)M * C; ccur ^= 1; }
+          da.W0 = sw.md_w0; da.b0 = sw.md_b0; da.g1 = sw.md_g1; da.be1 = sw.md_be1; da.W3 = sw.md_w3; da.b3 = sw.md_b3; da.g4 = sw.md_g4; da.be4 = sw.md_be4;
+          da.B = B; da.Cp = Cp; da.C = C; da.eps = 1e-5f;
+          char d[120];
+          snprintf(d, sizeof(d), "meta_downsample B=%d %d->%d", B, Cp, C);
+          sc->push([da](cudaStream_t s) { return meta_downsample_run(da, s); }, OP_META, 2.0 * B * M * 4.0 * Cp * (Cp + C), 0.0, d);
+        } else {
         if (c_prev_unified) {
           const bf16* src = c_prev_unified;
           bf16* dst = cbuf[ccur];
@@ -688,6 +728,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         b.linear(chid, 4 * Cp, sw.md_w3, sw.md_b3, B * M, C, 4 * Cp, ctmp, C);
         if (uni) b.ln(ctmp, xbuf[cur], sw.md_g4, sw.md_be4, B * M, C, 1e-5f, 0, M, T, N);
         else { b.ln(ctmp, cbuf[ccur ^ 1], sw.md_g4, sw.md_be4, B * M, C, 1e-5f); ccur ^= 1; }
+        }
       }
     }
     bf16* cc = cbuf[ccur];
@@ -752,6 +793,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         b.linear_res_stats(xn, bw.wp1, bw.bp1, B * T, C, C, x, stats2, &parts2);
         b.mlp(x, stats2, parts2, bw, B * T, C, Hd, hid);
       }
+      if (j + 1 == c.depth[i] || (i == plan->tap_stage && j == plan->tap_block)) b.flush_meta();   // end of the stage / tap reads c
       if (i == plan->tap_stage && j == plan->tap_block) {
         // test hook (lmv_plan_set_tap): dense copies of the block's outputs, x as tokens [B, N, C], c as [B, M, C]
         const bf16* xs = xbuf[cur];
@@ -1237,6 +1279,7 @@ int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, voi
   Builder b{nullptr, &sc, LMV_OK, false};
   b.dca_block((char)kind, static_cast<const bf16*>(xt), stats1, parts1, static_cast<bf16*>(xout), stats2, static_cast<bf16*>(c), bw, B, N, C,
               heads, Hd, scale_x, scale_c, workspace, flags & 1);
+  b.flush_meta();
   if (b.rc) return b.rc;
   for (auto& op : sc.ops) {
     int rc = op.fn(static_cast<cudaStream_t>(stream));

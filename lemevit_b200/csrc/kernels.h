@@ -21,7 +21,7 @@ int posembed_ln_run(const PosLnArgs& a, cudaStream_t s);
 struct PosEmbedOp {
   CUtensorMap tm;
   PosLnArgs a;
-  int TW, TH, tiles_x, tiles_y, cbox, ncb, smem, sub_bytes, threads;
+  int TW, TH, tiles_x, tiles_y, cbox, ncb, smem, sub_bytes, threads, col_threads;
   int parts;   // channel slices == statistics partials per row (stats_out is [B*T][parts][2])
 };
 bool posembed_tile_supported(const PosLnArgs& a);
@@ -126,7 +126,7 @@ struct MlpArgs {
   int R = 0, C = 0, Hd = 0;
 };
 struct MlpParams {
-  int R, C, Hd, tiles, kb1, chunks, nparts2, n2, nx, nh, n1slots, n2slots, slot2_bytes, const_bytes;
+  int R, C, Hd, tiles, kb1, chunks, nparts2, n2, nx, nh, n1slots, n2slots, slot2_bytes, const_bytes, res_smem;
   const float *b1, *cs1, *b2, *ln_stats;
   int ln_parts;
   float ln_eps, ln_inv_k;
@@ -214,6 +214,24 @@ struct MetaPostArgs {
   DcaWs ws;
 };
 int meta_post_run(const MetaPostArgs& a, cudaStream_t s);
+// [post of block j] -> [pre of block j + 1] of the same stage in ONE launch (either may be null)
+int meta_chain_run(const MetaPostArgs* post, const MetaPreArgs* pre, cudaStream_t s);
+
+// meta_token_downsample[i] (models/lemevit.py:729-745) in one launch: Linear(Cp, 4Cp) -> LayerNorm -> GELU -> Linear(4Cp, C) -> LayerNorm
+struct MetaDsArgs {
+  const bf16* in;            // rows of image b: in + b * in_bs, [16, Cp] dense
+  long long in_bs;
+  bf16* out;                 // rows of image b: out + b * out_bs, [16, C] dense
+  long long out_bs;
+  const bf16* W0;            // [4Cp, Cp]
+  const float *b0, *g1, *be1;
+  const bf16* W3;            // [C, 4Cp]
+  const float *b3, *g4, *be4;
+  int B, Cp, C;
+  float eps;
+};
+bool meta_downsample_supported(int Cp, int C);
+int meta_downsample_run(const MetaDsArgs& a, cudaStream_t s);
 
 struct DcaXArgs {
   const bf16* xt;            // [B, N, C] image tokens after x + dwconv(x) (raw; LayerNorm through stats1)

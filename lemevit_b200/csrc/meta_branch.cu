@@ -48,41 +48,52 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
 // 8-column tiles; epi(n, m, v0, v1) receives out[m][n], out[m][n + 1] (fp32) for the lane's two rows m = g and g + 8.
 // a_group_stride: the A tile used for the 32-column group starting at column n is A0 + (n / 32) * a_group_stride (one A tile per
 // head in the value contraction of meta_post; 0 everywhere else).
-template <typename Epi>
-__device__ __forceinline__ void rows16_mma(const bf16* __restrict__ A0, int lda, const bf16* __restrict__ W, int ldw, int N, int K, Epi epi,
-                                            int a_group_stride = 0) {
+// NT: 8-column tiles per warp trip (4, 2 or 1): chosen by rows16_mma so that all 16 warps have work even when N is small
+// (N = 192 has only 24 tiles), at the price of re-loading the A fragments more often.
+template <int NT, typename Epi>
+__device__ __forceinline__ void rows16_mma_nt(const bf16* __restrict__ A0, int lda, const bf16* __restrict__ W, int ldw, int N, int K, Epi& epi,
+                                               int a_group_stride) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
   const int ntiles = N >> 3;
-  for (int tile0 = warp * 4; tile0 < ntiles; tile0 += kWarps * 4) {
-    const int nt = min(4, ntiles - tile0);
+  for (int tile0 = warp * NT; tile0 < ntiles; tile0 += kWarps * NT) {
+    const int nt = min(NT, ntiles - tile0);
     const bf16* A = A0 + (size_t)(tile0 >> 2) * a_group_stride;
-    float acc[4][4];
+    float acc[NT][4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; acc[t][2] = 0.f; acc[t][3] = 0.f; }
-    const bf16* wrow[4];
+    for (int t = 0; t < NT; ++t) { acc[t][0] = 0.f; acc[t][1] = 0.f; acc[t][2] = 0.f; acc[t][3] = 0.f; }
+    const bf16* wrow[NT];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) wrow[t] = W + (size_t)((tile0 + min(t, nt - 1)) * 8 + g) * ldw + tq * 8;
-#pragma unroll 2
+    for (int t = 0; t < NT; ++t) wrow[t] = W + (size_t)((tile0 + min(t, nt - 1)) * 8 + g) * ldw + tq * 8;
+#pragma unroll(NT == 4 ? 2 : 4)
     for (int kc = 0; kc < K; kc += 32) {
-      uint4 b[4];
+      uint4 b[NT];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) b[t] = __ldg(reinterpret_cast<const uint4*>(wrow[t] + kc));
+      for (int t = 0; t < NT; ++t) b[t] = __ldg(reinterpret_cast<const uint4*>(wrow[t] + kc));
       const uint4 alo = *reinterpret_cast<const uint4*>(A + (size_t)g * lda + kc + tq * 8);
       const uint4 ahi = *reinterpret_cast<const uint4*>(A + (size_t)(g + 8) * lda + kc + tq * 8);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < NT; ++t) {
         mma_bf16_16816(acc[t], alo.x, ahi.x, alo.y, ahi.y, b[t].x, b[t].y);
         mma_bf16_16816(acc[t], alo.z, ahi.z, alo.w, ahi.w, b[t].z, b[t].w);
       }
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t)
+    for (int t = 0; t < NT; ++t)
       if (t < nt) {
         const int n = (tile0 + t) * 8 + tq * 2;
         epi(n, g, acc[t][0], acc[t][1]);
         epi(n, g + 8, acc[t][2], acc[t][3]);
       }
   }
+}
+
+template <typename Epi>
+__device__ __forceinline__ void rows16_mma(const bf16* __restrict__ A0, int lda, const bf16* __restrict__ W, int ldw, int N, int K, Epi epi,
+                                            int a_group_stride = 0) {
+  const int ntiles = N >> 3;
+  if (ntiles >= 4 * kWarps) rows16_mma_nt<4>(A0, lda, W, ldw, N, K, epi, a_group_stride);
+  else if (ntiles >= 2 * kWarps) rows16_mma_nt<2>(A0, lda, W, ldw, N, K, epi, a_group_stride);
+  else rows16_mma_nt<1>(A0, lda, W, ldw, N, K, epi, a_group_stride);
 }
 
 // LayerNorm without affine of the 16 fp32 rows -> bf16 rows (A operand of the next contraction); one warp per row
@@ -102,19 +113,18 @@ __device__ __forceinline__ void rows16_layernorm(const float* in, int ld, bf16* 
 // ------------------------------------------------------------------------------------------------
 // meta_pre
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-meta_pre_kernel(MetaPreArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int C = a.C, R = a.heads * M, nc = a.nc, b = blockIdx.x;
+// s_c: [M][C] fp32 meta tokens at the front of shared memory (loaded here unless `have_c`: the post body of the same launch
+// left the block's output there); `scratch`: the rest of the dynamic shared memory.
+__device__ __forceinline__ void meta_pre_body(const MetaPreArgs& a, float* s_c, uint8_t* scratch, int b, bool have_c) {
+  const int C = a.C, R = a.heads * M, nc = a.nc;
   const int lda = pitch(C), ldp = pitch(nc);
-  float* s_c = reinterpret_cast<float*>(smem_raw);                 // [M][C]        raw meta tokens (fp32)
-  bf16* s_n = reinterpret_cast<bf16*>(s_c + M * C);                // [M][C + pad]  LN1(c)
+  bf16* s_n = reinterpret_cast<bf16*>(scratch);                    // [M][C + pad]  LN1(c)
   bf16* s_p = s_n + M * lda;                                       // [M][nc + pad] projection of LN1(c): q2 | k2 | v2
   bf16* s_t = s_p + M * ldp;                                       // [R][C] staging of Kt / Qt, [C][R] staging of Vt^T
-  pdl_launch_dependents();
-  pdl_wait();
-  const bf16* cb = a.c + (size_t)b * M * C;
-  for (int i = threadIdx.x; i < M * C; i += kThreads) s_c[i] = __bfloat162float(cb[i]);
+  if (!have_c) {
+    const bf16* cb = a.c + (size_t)b * M * C;
+    for (int i = threadIdx.x; i < M * C; i += kThreads) s_c[i] = __bfloat162float(cb[i]);
+  }
   __syncthreads();
   rows16_layernorm(s_c, C, s_n, lda, C, a.eps);
   __syncthreads();
@@ -168,17 +178,13 @@ meta_pre_kernel(MetaPreArgs a) {
 // ------------------------------------------------------------------------------------------------
 // meta_post
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
-meta_post_kernel(MetaPostArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int C = a.C, R = a.heads * M, Hd = a.Hd, b = blockIdx.x, P = a.parts;
+// Leaves the block's output meta tokens (the bf16-rounded values that were stored) in s_c for a following pre body.
+__device__ __forceinline__ void meta_post_body(const MetaPostArgs& a, float* s_c, uint8_t* scratch, int b) {
+  const int C = a.C, R = a.heads * M, Hd = a.Hd, P = a.parts;
   const int lda = pitch(C), ldh = pitch(Hd);
-  float* s_c = reinterpret_cast<float*>(smem_raw);       // [M][C]   meta tokens (residual stream, fp32)
-  float* s_w = s_c + M * C;                               // [P + 1][R]  merge weights, 1 / l
+  float* s_w = reinterpret_cast<float*>(scratch);         // [P + 1][R]  merge weights, 1 / l
   bf16* s_a = reinterpret_cast<bf16*>(s_w + (P + 1) * R); // [M][C + pad]   attn_c, later LN2(c)
   bf16* s_z = s_a + M * lda;                              // [R][C + pad]   Zbar (bf16); reused as the MLP hidden activation [M][Hd + pad]
-  pdl_launch_dependents();
-  pdl_wait();
   bf16* cb = a.c + (size_t)b * M * C;
   for (int i = threadIdx.x; i < M * C; i += kThreads) s_c[i] = __bfloat162float(cb[i]);
   // ---- merge the segment partials (fixed order: deterministic, independent of batch size and position)
@@ -200,13 +206,22 @@ meta_post_kernel(MetaPostArgs a) {
   for (int i = threadIdx.x; i < R * C / 4; i += kThreads) {
     const int r = (i * 4) / C, col = i * 4 - r * C;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < P; ++p) {
-      const float w = s_w[p * R + r];
-      if (w == 0.f) continue;      // an empty partial (no valid token in that copy's columns) may hold anything
-      const float4 z = __ldg(reinterpret_cast<const float4*>(pz + (size_t)p * R * C) + i);
-      const float t = ml[p * R + r].z;    // sum_n p'_n mu_n: Zbar = sum p' (xt - mu)
-      acc.x = fmaf(w, z.x - t, acc.x); acc.y = fmaf(w, z.y - t, acc.y);
-      acc.z = fmaf(w, z.z - t, acc.z); acc.w = fmaf(w, z.w - t, acc.w);
+    for (int p0 = 0; p0 < P; p0 += 4) {      // four partials in flight
+      float4 z[4];
+      float w[4], t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = min(p0 + q, P - 1);
+        w[q] = (p0 + q < P) ? s_w[p * R + r] : 0.f;
+        z[q] = __ldg(reinterpret_cast<const float4*>(pz + (size_t)p * R * C) + i);
+        t[q] = ml[p * R + r].z;     // sum_n p'_n mu_n: Zbar = sum p' (xt - mu)
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (w[q] != 0.f) {          // an empty partial (no valid token in that copy's columns) may hold anything
+          acc.x = fmaf(w[q], z[q].x - t[q], acc.x); acc.y = fmaf(w[q], z[q].y - t[q], acc.y);
+          acc.z = fmaf(w[q], z[q].z - t[q], acc.z); acc.w = fmaf(w[q], z[q].w - t[q], acc.w);
+        }
     }
     const float il = s_w[P * R + r];
     uint2 pk;
@@ -239,11 +254,87 @@ meta_post_kernel(MetaPostArgs a) {
   __syncthreads();
   rows16_mma(s_h, ldh, a.W2, Hd, C, Hd, [&](int n, int m, float v0, float v1) {
     const float2 bias = __ldg(reinterpret_cast<const float2*>(a.b2 + n));
-    *reinterpret_cast<uint32_t*>(cb + m * C + n) = pack_bf16x2(s_c[m * C + n] + v0 + bias.x, s_c[m * C + n + 1] + v1 + bias.y);
+    const uint32_t pk = pack_bf16x2(s_c[m * C + n] + v0 + bias.x, s_c[m * C + n + 1] + v1 + bias.y);
+    *reinterpret_cast<uint32_t*>(cb + m * C + n) = pk;
+    const float2 f = unpack_bf16x2(pk);
+    s_c[m * C + n] = f.x;
+    s_c[m * C + n + 1] = f.y;
   });
 }
 
-PerDeviceOnce g_pre_once, g_post_once;
+// One launch = [post of block j] -> [pre of block j + 1] of the same stage (either may be absent): one meta-token kernel per block.
+__global__ void __launch_bounds__(kThreads)
+meta_chain_kernel(MetaPostArgs post, MetaPreArgs pre, int do_post, int do_pre, int C) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* s_c = reinterpret_cast<float*>(smem_raw);
+  uint8_t* scratch = smem_raw + (size_t)M * C * 4;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (do_post) {
+    meta_post_body(post, s_c, scratch, blockIdx.x);
+    __syncthreads();
+  }
+  if (do_pre) meta_pre_body(pre, s_c, scratch, blockIdx.x, do_post != 0);
+}
+
+// meta_token_downsample[i] (models/lemevit.py:729-745): Linear(Cp, 4Cp) -> LayerNorm(eps 1e-5) -> GELU -> Linear(4Cp, C) -> LayerNorm,
+// one CTA per image instead of five launches.  in / out rows of image b start at in + b * in_bs / out + b * out_bs (the meta tokens may
+// live behind the image tokens of a unified [B, N + M, C] buffer).
+__global__ void __launch_bounds__(kThreads)
+meta_downsample_kernel(MetaDsArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int Cp = a.Cp, C = a.C, H4 = 4 * a.Cp, b = blockIdx.x;
+  const int ldi = pitch(Cp), ldh = pitch(H4);
+  float* s_f = reinterpret_cast<float*>(smem_raw);                 // [M][max(4Cp, C)] fp32 pre-LayerNorm rows
+  const int ldf = max(H4, C);
+  bf16* s_i = reinterpret_cast<bf16*>(s_f + M * ldf);              // [M][Cp + pad]  input rows
+  bf16* s_h = s_i + M * ldi;                                       // [M][4Cp + pad] hidden rows
+  pdl_launch_dependents();
+  pdl_wait();
+  const bf16* in = a.in + (size_t)b * a.in_bs;
+  for (int i = threadIdx.x; i < M * Cp / 8; i += kThreads) {
+    const int m = (i * 8) / Cp, k = i * 8 - m * Cp;
+    *reinterpret_cast<uint4*>(s_i + m * ldi + k) = *reinterpret_cast<const uint4*>(in + (size_t)m * Cp + k);
+  }
+  __syncthreads();
+  rows16_mma(s_i, ldi, a.W0, Cp, H4, Cp, [&](int n, int m, float v0, float v1) {
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(a.b0 + n));
+    // the reference's bf16 pipeline stores the Linear output before the LayerNorm: round like it
+    const float2 f = unpack_bf16x2(pack_bf16x2(v0 + bias.x, v1 + bias.y));
+    s_f[m * ldf + n] = f.x;
+    s_f[m * ldf + n + 1] = f.y;
+  });
+  __syncthreads();
+  // LayerNorm(4Cp, affine, eps) -> GELU -> bf16 hidden rows; one warp per row
+  auto ln_rows = [&](int width, const float* gamma, const float* beta, bool gelu, bf16* out, int ldo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int m = warp; m < M; m += kWarps) {
+      float s1 = 0.f;
+      for (int k = lane; k < width; k += 32) s1 += s_f[m * ldf + k];
+      const float mu = warp_sum(s1) / (float)width;
+      float s2 = 0.f;
+      for (int k = lane; k < width; k += 32) { const float d = s_f[m * ldf + k] - mu; s2 = fmaf(d, d, s2); }
+      const float r = rsqrtf(warp_sum(s2) / (float)width + a.eps);
+      for (int k = lane; k < width; k += 32) {
+        float v = (s_f[m * ldf + k] - mu) * r * __ldg(gamma + k) + __ldg(beta + k);
+        if (gelu) v = gelu_erf(v);
+        out[(size_t)m * ldo + k] = __float2bfloat16(v);
+      }
+    }
+  };
+  ln_rows(H4, a.g1, a.be1, true, s_h, ldh);
+  __syncthreads();
+  rows16_mma(s_h, ldh, a.W3, H4, C, H4, [&](int n, int m, float v0, float v1) {
+    const float2 bias = __ldg(reinterpret_cast<const float2*>(a.b3 + n));
+    const float2 f = unpack_bf16x2(pack_bf16x2(v0 + bias.x, v1 + bias.y));
+    s_f[m * ldf + n] = f.x;
+    s_f[m * ldf + n + 1] = f.y;
+  });
+  __syncthreads();
+  ln_rows(C, a.g4, a.be4, false, a.out + (size_t)b * a.out_bs, C);
+}
+
+PerDeviceOnce g_chain_once, g_ds_once;
 constexpr int kMetaSmemMax = 200 * 1024;
 
 }  // namespace
@@ -285,28 +376,60 @@ DcaWs dca_workspace_carve(const DcaGeom& g, void* base) {
   return w;
 }
 
-int meta_pre_run(const MetaPreArgs& a, cudaStream_t s) {
+static size_t pre_scratch_bytes(const MetaPreArgs& a) {
+  const int R = a.heads * M;
+  return (size_t)M * pitch(a.C) * 2 + (size_t)M * pitch(a.nc) * 2 + (size_t)R * a.C * 2;
+}
+static size_t post_scratch_bytes(const MetaPostArgs& a) {
+  const int R = a.heads * M;
+  const size_t zbytes = std::max((size_t)R * pitch(a.C), (size_t)M * pitch(a.Hd)) * 2;
+  return (size_t)(a.parts + 1) * R * 4 + (size_t)M * pitch(a.C) * 2 + zbytes;
+}
+static int check_pre(const MetaPreArgs& a) {
   LMV_REQUIRE(a.c && a.Wc && a.bc && a.WxkT && a.bxk && a.ws.qt && a.ws.cst, "meta_pre: null pointer");
   LMV_REQUIRE((a.WxqT == nullptr) == (a.Wpx == nullptr), "meta_pre: WxqT and Wpx go together (x-branch)");
   LMV_REQUIRE(a.C % 32 == 0 && a.heads * 32 == a.C && a.nc % 8 == 0, "meta_pre: C must be heads * 32");
-  const int R = a.heads * M;
-  const size_t smem = (size_t)M * a.C * 4 + (size_t)M * pitch(a.C) * 2 + (size_t)M * pitch(a.nc) * 2 + (size_t)R * a.C * 2;
-  LMV_REQUIRE(smem <= (size_t)kMetaSmemMax, "meta_pre: shared memory budget");
-  LMV_CUDA_OK(g_pre_once.run([] { return cudaFuncSetAttribute(meta_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetaSmemMax); }));
-  LMV_CUDA_OK(launch_kernel(meta_pre_kernel, dim3(a.B), dim3(kThreads), smem, s, a));
+  return LMV_OK;
+}
+static int check_post(const MetaPostArgs& a) {
+  LMV_REQUIRE(a.c && a.Wxv && a.bxv && a.Wp && a.bp && a.W1 && a.b1 && a.W2 && a.b2 && a.ws.part_ml && a.ws.part_z, "meta_post: null pointer");
+  LMV_REQUIRE(a.C % 32 == 0 && a.heads * 32 == a.C && a.Hd % 32 == 0 && a.parts >= 1, "meta_post: shape");
+  return LMV_OK;
+}
+
+// [post of block j] -> [pre of block j + 1] in one launch; either pointer may be null.  Both must belong to the same stage (same
+// B, C and meta-token buffer): the pre body continues on the tokens the post body leaves in shared memory.
+int meta_chain_run(const MetaPostArgs* post, const MetaPreArgs* pre, cudaStream_t s) {
+  LMV_REQUIRE(post || pre, "meta_chain: nothing to run");
+  int rc;
+  if (post && (rc = check_post(*post))) return rc;
+  if (pre && (rc = check_pre(*pre))) return rc;
+  if (post && pre) LMV_REQUIRE(post->C == pre->C && post->B == pre->B && post->c == pre->c, "meta_chain: post and pre of different stages");
+  const int C = post ? post->C : pre->C, B = post ? post->B : pre->B;
+  const size_t smem = (size_t)M * C * 4 + std::max(post ? post_scratch_bytes(*post) : 0, pre ? pre_scratch_bytes(*pre) : 0);
+  LMV_REQUIRE(smem <= (size_t)kMetaSmemMax, "meta_chain: shared memory budget");
+  LMV_CUDA_OK(g_chain_once.run([] { return cudaFuncSetAttribute(meta_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetaSmemMax); }));
+  const MetaPostArgs pa = post ? *post : MetaPostArgs{};
+  const MetaPreArgs ra = pre ? *pre : MetaPreArgs{};
+  LMV_CUDA_OK(launch_kernel(meta_chain_kernel, dim3(B), dim3(kThreads), smem, s, pa, ra, post ? 1 : 0, pre ? 1 : 0, C));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
 
-int meta_post_run(const MetaPostArgs& a, cudaStream_t s) {
-  LMV_REQUIRE(a.c && a.Wxv && a.bxv && a.Wp && a.bp && a.W1 && a.b1 && a.W2 && a.b2 && a.ws.part_ml && a.ws.part_z, "meta_post: null pointer");
-  LMV_REQUIRE(a.C % 32 == 0 && a.heads * 32 == a.C && a.Hd % 32 == 0 && a.parts >= 1, "meta_post: shape");
-  const int R = a.heads * M;
-  const size_t zbytes = std::max((size_t)R * pitch(a.C), (size_t)M * pitch(a.Hd)) * 2;
-  const size_t smem = (size_t)M * a.C * 4 + (size_t)(a.parts + 1) * R * 4 + (size_t)M * pitch(a.C) * 2 + zbytes;
-  LMV_REQUIRE(smem <= (size_t)kMetaSmemMax, "meta_post: shared memory budget");
-  LMV_CUDA_OK(g_post_once.run([] { return cudaFuncSetAttribute(meta_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetaSmemMax); }));
-  LMV_CUDA_OK(launch_kernel(meta_post_kernel, dim3(a.B), dim3(kThreads), smem, s, a));
+int meta_pre_run(const MetaPreArgs& a, cudaStream_t s) { return meta_chain_run(nullptr, &a, s); }
+int meta_post_run(const MetaPostArgs& a, cudaStream_t s) { return meta_chain_run(&a, nullptr, s); }
+
+bool meta_downsample_supported(int Cp, int C) { return Cp % 32 == 0 && C % 8 == 0 && Cp >= 32 && Cp <= 512 && C <= 2048; }
+
+int meta_downsample_run(const MetaDsArgs& a, cudaStream_t s) {
+  LMV_REQUIRE(a.in && a.out && a.W0 && a.b0 && a.g1 && a.be1 && a.W3 && a.b3 && a.g4 && a.be4, "meta_downsample: null pointer");
+  if (!meta_downsample_supported(a.Cp, a.C)) return fail(LMV_ERR_UNSUPPORTED, "meta_downsample: needs Cp % 32 == 0, C % 8 == 0");
+  LMV_REQUIRE((reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && a.in_bs % 8 == 0, "meta_downsample: input rows must be 16-byte aligned");
+  const int H4 = 4 * a.Cp;
+  const size_t smem = (size_t)M * std::max(H4, a.C) * 4 + (size_t)M * pitch(a.Cp) * 2 + (size_t)M * pitch(H4) * 2;
+  LMV_REQUIRE(smem <= (size_t)kMetaSmemMax, "meta_downsample: shared memory budget");
+  LMV_CUDA_OK(g_ds_once.run([] { return cudaFuncSetAttribute(meta_downsample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMetaSmemMax); }));
+  LMV_CUDA_OK(launch_kernel(meta_downsample_kernel, dim3(a.B), dim3(kThreads), smem, s, a));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

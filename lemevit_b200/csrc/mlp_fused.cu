@@ -77,7 +77,7 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctrl->x_full[i], 1);
-      mbar_init(&ctrl->x_empty[i], 1);
+      mbar_init(&ctrl->x_empty[i], p.res_smem ? 1 + kEpiWarps : 1);   // + the output epilogue when it reads the residual from the X tile
       mbar_init(&ctrl->acc1_full[i], 1);
       mbar_init(&ctrl->acc1_empty[i], kEpiWarps);
       mbar_init(&ctrl->hid_full[i], kEpiWarps);
@@ -242,9 +242,18 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int row = (blockIdx.x + oit * gridDim.x) * BM + rloc;
       const bool rok = row < p.R;
         bool waited = false;
+        const int xb_o = oit & 1;      // res_smem implies two X buffers: tile `oit` sits in buffer oit & 1
+        if (p.res_smem) mbar_wait(&ctrl->x_full[xb_o], (uint32_t)(oit >> 1) & 1u, 63);   // (completed long ago: acquire of the TMA writes)
         for (int c0 = e * 32; c0 < p.C; c0 += 128) {
           uint4 res[4];
-          if (rok) {
+          if (p.res_smem) {
+            // the residual IS the X tile that fed fc1 (resid == x): read it back from shared memory (128B-swizzled K-blocks)
+            // instead of a second, latency-exposed trip to global memory
+            const uint8_t* xr = sX + (size_t)xb_o * x_bytes + (size_t)(c0 >> 6) * kXBlockBytes + (size_t)rloc * 128;
+            const int ch0 = (c0 & 63) >> 3;
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) res[i] = *reinterpret_cast<const uint4*>(xr + (((ch0 + i) ^ (rloc & 7)) << 4));
+          } else if (rok) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (long long)row * p.C + c0);
   #pragma unroll
             for (int i = 0; i < 4; ++i) res[i] = rp[i];   // plain loads: resid may alias out
@@ -281,7 +290,10 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->acc2_empty);
+        if (lane == 0) {
+          mbar_arrive(&ctrl->acc2_empty);
+          if (p.res_smem) mbar_arrive(&ctrl->x_empty[xb_o]);   // the X tile may be refilled (tile oit + 2)
+        }
     };
     for (int it = 0; it < my_tiles; ++it) {
       const int t = blockIdx.x + it * gridDim.x;
@@ -388,6 +400,7 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
   p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1; p.ln_eps = a.ln_eps; p.ln_inv_k = 1.0f / (float)a.C;
   p.resid = a.resid ? a.resid : a.x;
   p.out = a.out;
+  p.res_smem = (p.nx == 2 && p.resid == a.x) ? 1 : 0;
   op->grid = std::min(p.tiles, device_sm_count());
   int rc;
   {

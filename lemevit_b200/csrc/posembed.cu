@@ -29,6 +29,7 @@ struct PosTileParams {
   float* stats;        // [B*T][2] or null
   int B, H, W, T, C;
   int TW, TH, tiles_x, tiles_y;
+  int col_threads;     // threads that own (tile column, channel vector) pairs: a multiple of V = CS / 8
   int cbox, ncb;       // channel box of one TMA load, number of boxes per CTA (CS = cbox * ncb)
   int CS, parts;       // channels per CTA (blockIdx.z selects the slice) and slices per row; C = CS * parts
   int sub_bytes;       // shared-memory bytes of one channel box of the input tile (128-byte multiple: TMA destination)
@@ -105,9 +106,11 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
     fence_mbar_init();
     if ((int)blockIdx.x < n_items) issue(blockIdx.x, 0);
   }
-  // one (column, channel vector) per thread: its 9 x 8 depthwise taps and 8 biases live in registers as packed pairs
-  const bool active = (int)threadIdx.x < p.TW * V;
-  const int tx = active ? (int)threadIdx.x / V : 0, v = active ? (int)threadIdx.x - tx * V : 0;
+  // thread = (tile column, channel vector): its 9 x 8 depthwise taps and 8 biases live in registers as packed pairs.  When the
+  // tile has more (column, vector) pairs than the CTA has threads, a thread keeps its vector and walks columns tx0, tx0 + tx_step, ..
+  const int tx_step = p.col_threads / V;
+  const bool active = (int)threadIdx.x < p.col_threads;
+  const int tx0 = active ? (int)threadIdx.x / V : 0, v = active ? (int)threadIdx.x - tx0 * V : 0;
   float2 w[9][4], bias[4];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
@@ -136,12 +139,15 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
     const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
     mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u, 20);
     float2* part = s_part + (size_t)buf * part_elems;
-    if (active) {
+    if (active)
+     for (int tx = tx0; tx < p.TW; tx += tx_step) {
       const int x = x0 + tx;
       const bool xok = x < p.W;
       const uint8_t* base = s_in + (size_t)buf * in_bytes + (size_t)cb * p.sub_bytes + (size_t)tx * col_pitch + (size_t)vv * 16;
       const long long row0 = (long long)b * p.T + (long long)y0 * p.W + x;
       float2 a0[4], a1[4], a2[4];    // accumulators of output rows (ir), (ir - 1), (ir - 2), rotated by the 3x unrolled loop
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a1[j] = make_float2(0.f, 0.f); a2[j] = make_float2(0.f, 0.f); }
       // one input row: three 16-byte vectors (kx = 0..2) feed NEW (ky = 0), MID (ky = 1) and OLD (ky = 2); OLD is then complete
       auto step = [&](int ir, float2 (&NEW)[4], float2 (&MID)[4], float2 (&OLD)[4]) {
         float2 in[3][4];
@@ -240,12 +246,15 @@ int posembed_tile_prepare(const PosLnArgs& a, PosEmbedOp* op) {
   int TW = a.W <= 16 ? a.W : ((a.W % 14 == 0) ? 14 : 16);
   int TH = (40 * 1024) / ((TW + 2) * CS * 2) - 2;
   TH = std::max(1, std::min(std::min(TH, 8), a.H));
+  TH = (a.H + (a.H + TH - 1) / TH - 1) / ((a.H + TH - 1) / TH);      // equal-height tiles (14 rows -> 7 + 7, not 8 + 6)
   op->TW = TW; op->TH = TH;
   op->tiles_x = (a.W + TW - 1) / TW;
   op->tiles_y = (a.H + TH - 1) / TH;
   op->sub_bytes = (((TH + 2) * (TW + 2) * op->cbox * 2 + 127) / 128) * 128;
-  LMV_REQUIRE(TW * (CS / 8) <= kThreads, "posembed: one thread per (tile column, channel vector) must fit the CTA");
-  op->threads = ((TW * (CS / 8) + 31) / 32) * 32;     // one thread per (tile column, 8-channel vector)
+  LMV_REQUIRE(CS / 8 <= kThreads, "posembed: channel slice wider than the CTA");
+  // one thread per (tile column, 8-channel vector) when that fits the CTA, else a multiple of V threads that walk the columns
+  op->col_threads = std::min(TW, kThreads / (CS / 8)) * (CS / 8);
+  op->threads = ((op->col_threads + 31) / 32) * 32;
   op->smem = 128 + 128 + 2 * op->ncb * op->sub_bytes + 2 * TH * TW * (CS / 8) * 8;
   LMV_REQUIRE(op->smem <= 200 * 1024, "posembed: tile does not fit in shared memory");
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
@@ -263,12 +272,12 @@ int posembed_tile_run(const PosEmbedOp& op, cudaStream_t s) {
   p.tokens = a.tokens; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.out = a.resid_out; p.stats = a.stats_out;
   p.H = a.H; p.W = a.W; p.T = a.T; p.C = a.C;
   p.TW = op.TW; p.TH = op.TH; p.tiles_x = op.tiles_x; p.tiles_y = op.tiles_y; p.cbox = op.cbox; p.ncb = op.ncb;
-  p.sub_bytes = op.sub_bytes; p.parts = op.parts; p.CS = a.C / op.parts; p.B = a.B;
+  p.sub_bytes = op.sub_bytes; p.parts = op.parts; p.CS = a.C / op.parts; p.B = a.B; p.col_threads = op.col_threads;
   // persistent CTAs: as many as can be resident (shared memory / registers allow 2-3 per SM), striding over the (image, tile) items;
   // blockIdx.y == 1: the CTAs that pass the meta-token rows of a unified buffer through
   const int n_items = op.tiles_x * op.tiles_y * a.B;
   const int per_sm = std::max(1, std::min(3, (200 * 1024) / std::max(op.smem, 1)));
-  dim3 grid(std::min(n_items, per_sm * device_sm_count()), a.T > a.H * a.W ? 2 : 1, op.parts);
+  dim3 grid(std::min(n_items, std::max(1, per_sm * device_sm_count() / op.parts)), a.T > a.H * a.W ? 2 : 1, op.parts);
   LMV_CUDA_OK(launch_kernel(posembed_tile_kernel, dim3(grid), dim3(op.threads), (size_t)(op.smem), s, op.tm, p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;

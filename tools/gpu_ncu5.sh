@@ -1,0 +1,17 @@
+#!/bin/bash
+# tests + full ncu captures (source-level) of the five kernels under work
+mkdir -p gpurun_out
+: > gpurun_out/summary.txt
+run() { local name=$1 t=$2; shift 2; echo "=== $name" | tee -a gpurun_out/summary.txt; timeout $t "$@" > gpurun_out/$name.log 2>&1; echo "exit $?" | tee -a gpurun_out/summary.txt; tail -n ${TAILN:-6} gpurun_out/$name.log | cut -c1-300 | tee -a gpurun_out/summary.txt; }
+run gpu_tests 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_kernels.py -q --maxfail=12
+M=gpu__time_duration.sum,sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum,dram__bytes_read.sum,dram__bytes_write.sum
+cap() { # name regex skip
+  run ncu_$1 400 ncu --set full --metrics $M --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o gpurun_out/r02_$1 python tools/ncu_target.py lemevit_base 256 1
+}
+cap mlp_c96 mlp_fused 0
+cap dca_d_c96 dca_x_kernel 2
+cap dca_d_c192 dca_x_kernel 6
+cap posembed_c96 posembed_tile 0
+cap attn_self attention_self_kernel 0
+cap gemm_fc1 gemm_bf16 ${GEMM_SKIP:-14}
+cap meta_post_c192 meta_post 6
