@@ -197,7 +197,8 @@ int lmv_attention_meta(const void* q, long long q_bs, int q_rs, const void* k, l
  *   wxt = transposed copies of the image-side projections that get absorbed: 'D' [2][C][C] = (wa[0:C]^T, wa[C:2C]^T), 'C' [C][C] = wb[0:C]^T.
  * scale_x / scale_c: softmax scales of the two branches (:235,255-256; 'C': scale_c = head_dim^-0.5, scale_x unused).
  * Requires 16 meta tokens, C = heads * 32 <= 192.  workspace: lmv_dca_workspace_bytes(...) bytes, 256-byte aligned.
- * flags bit 0: issue the c-branch accumulation per 64-channel block (test hook). */
+ * flags (test hooks) bit 0: issue the c-branch accumulation per 64-channel block; bit 1: one tile at a time even where the pipelined
+ * schedule (C <= 96, or 'C' blocks) fits. */
 size_t lmv_dca_workspace_bytes(int B, int N, int C, int heads);
 int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, void* xout, float* stats2, void* c, const void* wa,
                   const float* ba, const void* wb, const float* bb, const void* wxt, const void* wp1, const float* bp1, const void* wp2,

@@ -566,7 +566,7 @@ struct Builder {
     DcaXArgs xa{};
     xa.xt = xt; xa.stats1 = stats1; xa.parts1 = parts1; xa.eps = 1e-6f; xa.do_x = D ? 1 : 0;
     xa.bpx = D ? bw.bp1 : nullptr; xa.xout = D ? xout : nullptr; xa.stats2 = D ? stats2 : nullptr;
-    xa.g = g; xa.ws = w; xa.zsplit = zsplit;
+    xa.g = g; xa.ws = w; xa.zsplit = zsplit & 1; xa.force_serial = (zsplit >> 1) & 1;
     DcaXOp op;
     rc = dca_x_prepare(xa, &op);
     if (rc) return;
@@ -1278,7 +1278,7 @@ int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, voi
   Schedule sc;
   Builder b{nullptr, &sc, LMV_OK, false};
   b.dca_block((char)kind, static_cast<const bf16*>(xt), stats1, parts1, static_cast<bf16*>(xout), stats2, static_cast<bf16*>(c), bw, B, N, C,
-              heads, Hd, scale_x, scale_c, workspace, flags & 1);
+              heads, Hd, scale_x, scale_c, workspace, flags & 3);
   b.flush_meta();
   if (b.rc) return b.rc;
   for (auto& op : sc.ops) {

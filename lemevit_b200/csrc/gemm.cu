@@ -149,7 +149,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* tiles = smem + 1024 + kEpiWarps * kStageF32;   // [ctrl 1 KB][8 x 4 KB transpose buffers][stage ring]
   const int a_bytes = BM * BK * 2;
   const int stage_bytes = a_bytes + p.BN * BK * 2;
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the role branches stay uniform
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -202,7 +202,9 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // the whole warp runs the (uniform) control flow and one elected lane issues: descriptors and loop state stay in uniform
+    // registers (umma.cuh: under `if (lane == 0)` every tcgen05.mma drags a vote / elect / branch sequence behind it)
+    {
       const uint32_t idesc = make_idesc_bf16(BM, p.BN);
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
@@ -224,12 +226,12 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128B swizzle span: start-address field += 2
-            umma_bf16_ss(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (uint32_t)((kb | k) != 0));
+            umma_bf16_ss_warp(d_tmem, da + 2ull * k, db + 2ull * k, idesc, (uint32_t)((kb | k) != 0));
           }
-          umma_commit(&ctrl->empty[stage]);  // frees the smem slot once these MMAs retire
+          umma_commit_warp(&ctrl->empty[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&ctrl->acc_full[as]);  // accumulator complete -> epilogue
+        umma_commit_warp(&ctrl->acc_full[as]);  // accumulator complete -> epilogue
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }

@@ -245,10 +245,11 @@ struct DcaXArgs {
   DcaGeom g;
   DcaWs ws;
   int zsplit;                // test hook: issue the Z accumulation per 64-channel block instead of one MN-major operand spanning C
+  int force_serial;          // test hook: one tile at a time even where the pipelined schedule fits
 };
 struct DcaXParams {
   DcaGeom g;
-  int do_x, kb, kbr, nx, rq, zsplit, parts1;
+  int do_x, kb, kbr, nx, rq, zsplit, parts1, pipe;
   float eps, inv_c;
   const float* stats1;
   const float* cst;

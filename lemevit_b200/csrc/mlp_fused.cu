@@ -70,7 +70,8 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint8_t* sH = sX + (size_t)p.nx * x_bytes;                          // nh hidden buffers
   uint8_t* sW1 = sH + (size_t)p.nh * kHidBytes;                       // ring 1
   uint8_t* sW2 = sW1 + (size_t)p.n1slots * kW1BoxBytes;               // ring 2
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int J = p.chunks;
   const int my_tiles = ((int)blockIdx.x < p.tiles) ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -151,8 +152,8 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
     }
   } else if (warp == 2) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer: whole warp in uniform control flow, one elected lane issues (umma.cuh) ----------------
+    {
       const uint32_t idesc1 = make_idesc_bf16(BM, HC);
       const uint32_t idesc2 = make_idesc_bf16(BM, p.n2);
       const int G = my_tiles * J;
@@ -176,13 +177,13 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint64_t da = make_kmajor_desc<128>(xaddr + (uint32_t)kb * kXBlockBytes);
           const uint64_t db = make_kmajor_desc<128>(smem_u32(sW1 + (size_t)s1 * kW1BoxBytes));
           const int ks = min(BK / 16, (p.C - kb * BK) / 16);
-          for (int k = 0; k < ks; ++k) umma_bf16_ss(d, da + 2ull * k, db + 2ull * k, idesc1, (uint32_t)((kb | k) != 0));
-          umma_commit(&ctrl->w1_empty[s1]);
+          for (int k = 0; k < ks; ++k) umma_bf16_ss_warp(d, da + 2ull * k, db + 2ull * k, idesc1, (uint32_t)((kb | k) != 0));
+          umma_commit_warp(&ctrl->w1_empty[s1]);
           if (++s1 == p.n1slots) { s1 = 0; ph1 ^= 1u; }
         }
-        umma_commit(&ctrl->acc1_full[buf]);
+        umma_commit_warp(&ctrl->acc1_full[buf]);
         if (j == J - 1) {   // X tile no longer needed once the last fc1 of the tile retires
-          umma_commit(&ctrl->x_empty[xb]);
+          umma_commit_warp(&ctrl->x_empty[xb]);
           if (++xb == p.nx) { xb = 0; xphase ^= 1u; }
         }
       };
@@ -201,13 +202,13 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint64_t db = make_kmajor_desc<128>(smem_u32(sW2 + (size_t)s2 * p.slot2_bytes));
             const uint32_t d = tmem_base + (uint32_t)(q * p.n2);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | kb | k) != 0));
-            umma_commit(&ctrl->w2_empty[s2]);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_warp(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | kb | k) != 0));
+            umma_commit_warp(&ctrl->w2_empty[s2]);
             if (++s2 == p.n2slots) { s2 = 0; ph2 ^= 1u; }
           }
         }
-        umma_commit(&ctrl->hid_empty[hb]);
-        if (j == J - 1) umma_commit(&ctrl->acc2_full);
+        umma_commit_warp(&ctrl->hid_empty[hb]);
+        if (j == J - 1) umma_commit_warp(&ctrl->acc2_full);
       };
       while (i2 < G) {
         // fc1 runs one chunk ahead of fc2 (two accumulators); with a single X buffer never run ahead into the next tile

@@ -164,6 +164,9 @@ def test_dca_block_fused(kind, B, N, C, heads):
     assert torch.equal(c2, c_out) and (kind == "C" or torch.equal(x2, xout))
     x3, _, c3, _ = G.dca_block(kind, xt, c, W, heads, scale_x, scale_c, flags=1, stats_parts=2 if B % 2 else 1)
     assert G.rel_err(c3, ref_c) < TOL
+    # the pipelined schedule (C <= 96, 'C' blocks) and the one-tile-at-a-time schedule compute the same bits
+    x4, _, c4, _ = G.dca_block(kind, xt, c, W, heads, scale_x, scale_c, flags=2, stats_parts=2 if B % 2 else 1)
+    assert torch.equal(c4, c_out) and (kind == "C" or torch.equal(x4, xout))
 
 
 def test_dca_block_batch_invariance_and_peaked_softmax():
