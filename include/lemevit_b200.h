@@ -168,7 +168,7 @@ int lmv_attention(const void* q, long long q_bs, int q_rs, const void* k, long l
 /* Self-attention of an 'S' block (StandardAttention, models/lemevit.py:199-205) over T rows per image, head_dim 32, in ONE
  * persistent tcgen05 kernel: rows [0, N) (image tokens) attend keys [0, N); rows [N, T) (the meta tokens of a unified
  * [B, N+M, 3C] qkv buffer, forward_with_x :634) attend keys [N, T).  N == T: plain self-attention.  T > 224 (e.g. the 1024 tokens
- * of stage 3 at 512x512): N must equal T and ceil(T/128) be even; the keys are split into blocks of <= 224 whose partial
+ * of stage 3 at 512x512): N must equal T; the keys are split into blocks of <= 224 whose partial
  * (max, sum, output) go through `workspace` (lmv_attention_self_workspace bytes, 0 for T <= 224) and a merge kernel.  Same pointer /
  * stride conventions as lmv_attention. */
 size_t lmv_attention_self_workspace(int B, int heads, int T);

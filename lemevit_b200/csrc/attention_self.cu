@@ -85,7 +85,8 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   float* sXchg = reinterpret_cast<float*>(smem + 1024);   // [group][half][max | sum parity 0 | sum parity 1][128 rows]
   uint8_t* sStage = smem + 1024 + ((kXchgBytes + 1023) / 1024) * 1024;   // 2 x {Q0, Q1, K, V}
   uint8_t* sP = sStage + 2 * kStageBytes;              // 2 groups x 4 tiles
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const long long n_my = ((long long)blockIdx.x < p.items) ? (p.items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (threadIdx.x == 0) {
@@ -146,8 +147,8 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    // ---------------- MMA issuer: whole warp in uniform control flow, one elected lane issues (umma.cuh) ----------------
+    {
       const uint32_t idesc_s = make_idesc_bf16(kQTile, p.Lkp);
       const uint32_t idesc_o = make_idesc_bf16(kQTile, kD) | (1u << 16);   // b_major = MN (V as loaded)
       const int ksteps = p.Lkp >> 4;
@@ -156,8 +157,8 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const uint64_t dq = make_kmajor_desc<64>(smem_u32(st + (size_t)g * kQBytes));
         const uint64_t dk = make_kmajor_desc<64>(smem_u32(st + 2 * kQBytes));
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss(tmem + (uint32_t)(g * kSCols), dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)(k != 0));
-        umma_commit(&ctrl->s_full[g]);
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss_warp(tmem + (uint32_t)(g * kSCols), dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)(k != 0));
+        umma_commit_warp(&ctrl->s_full[g]);
       };
       // Event loop: per group the next S and the next P V to issue; whichever dependency completes first is served first, so
       // the two softmax groups never wait for each other's hand-shakes.
@@ -170,36 +171,36 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         bool progress = false;
         for (int g = 0; g < ng; ++g) {
           long long i = s_next[g];
-          if (i < n_my && i <= pv_next[g] + 1 && (i == 0 || mbar_test_wait(&ctrl->p_full[g], (uint32_t)(i - 1) & 1u)) &&
-              mbar_test_wait(&ctrl->ld_full[i & 1], (uint32_t)(i >> 1) & 1u)) {
+          if (i < n_my && i <= pv_next[g] + 1 && (i == 0 || mbar_test_wait_warp(&ctrl->p_full[g], (uint32_t)(i - 1) & 1u)) &&
+              mbar_test_wait_warp(&ctrl->ld_full[i & 1], (uint32_t)(i >> 1) & 1u)) {
             tc_fence_after();
             issue_s(i, g);
             ++s_next[g];
             progress = true;
           }
           i = pv_next[g];
-          if (i < n_my && i < s_next[g] && mbar_test_wait(&ctrl->p_full[g], (uint32_t)i & 1u) &&
-              (i == 0 || mbar_test_wait(&ctrl->o_empty[g], (uint32_t)(i - 1) & 1u))) {
+          if (i < n_my && i < s_next[g] && mbar_test_wait_warp(&ctrl->p_full[g], (uint32_t)i & 1u) &&
+              (i == 0 || mbar_test_wait_warp(&ctrl->o_empty[g], (uint32_t)(i - 1) & 1u))) {
             tc_fence_after();
             const uint8_t* st = sStage + (size_t)(i & 1) * kStageBytes;
             const uint32_t pbase = smem_u32(sP + (size_t)g * kPBytes), vbase = smem_u32(st + 2 * kQBytes + kKVBytes);
             for (int s = 0; s < ksteps; ++s) {
               const uint64_t da = make_kmajor_desc<128>(pbase + (uint32_t)(s >> 2) * kPTileBytes) + 2ull * (s & 3);
               const uint64_t db = make_mnmajor_sw64_desc(vbase + (uint32_t)s * (16 * kD * 2));
-              umma_bf16_ss(tmem + kOCol + (uint32_t)(g * kD), da, db, idesc_o, (uint32_t)(s != 0));
+              umma_bf16_ss_warp(tmem + kOCol + (uint32_t)(g * kD), da, db, idesc_o, (uint32_t)(s != 0));
             }
-            umma_commit(&ctrl->o_full[g]);
-            umma_commit(&ctrl->p_empty[g]);
+            umma_commit_warp(&ctrl->o_full[g]);
+            umma_commit_warp(&ctrl->p_empty[g]);
             ++pv_next[g];
             progress = true;
             // a K/V/Q stage is free once BOTH groups' P V of that item (and hence every MMA reading it) have been issued
             const long long both = ng == 2 ? (pv_next[0] < pv_next[1] ? pv_next[0] : pv_next[1]) : pv_next[0];
-            while (released < both) { umma_commit(&ctrl->ld_empty[released & 1]); ++released; }
+            while (released < both) { umma_commit_warp(&ctrl->ld_empty[released & 1]); ++released; }
           }
         }
         if (!progress) __nanosleep(40);
         if (!progress && clock64() - t_start > (1ll << 33)) {
-          printf("[lemevit_b200] attention_self MMA loop stuck: block %d s_next %lld %lld pv_next %lld %lld of %lld\n", (int)blockIdx.x, s_next[0],
+          if (lane == 0) printf("[lemevit_b200] attention_self MMA loop stuck: block %d s_next %lld %lld pv_next %lld %lld of %lld\n", (int)blockIdx.x, s_next[0],
                  s_next[1], pv_next[0], pv_next[1], n_my);
           __trap();
         }
@@ -428,7 +429,7 @@ static int self_kb(int T) { const int n = self_nkv(T); return (((T + n - 1) / n)
 bool attention_self_supported(const AttnArgs& a, int T, int N) {
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const int qtiles = (T + kQTile - 1) / kQTile;
-  const bool shape_ok = T >= 1 && N >= 1 && N <= T && (T <= kMaxKeys || (N == T && qtiles % 2 == 0 && self_kb(T) <= kMaxKeys));
+  const bool shape_ok = T >= 1 && N >= 1 && N <= T && (T <= kMaxKeys || (N == T && self_kb(T) <= kMaxKeys));   // (an odd number of query tiles leaves group 1 idle in the last pair)
   return shape_ok && a.B >= 1 && a.heads >= 1 && al16(a.q) && al16(a.k) && al16(a.v) && al16(a.out) &&
          a.q_rs % 8 == 0 && a.k_rs % 8 == 0 && a.v_rs % 8 == 0 && a.o_rs % 8 == 0 && a.q_bs % 8 == 0 && a.k_bs % 8 == 0 &&
          a.v_bs % 8 == 0 && a.o_bs % 8 == 0 && a.q_rs >= a.heads * kD && a.k_rs >= a.heads * kD && a.v_rs >= a.heads * kD;

@@ -76,11 +76,6 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
       : "memory");
 }
 
-// warp-collective non-blocking phase test with a provably uniform result
-__device__ __forceinline__ bool mbar_test_wait_warp(uint64_t* bar, uint32_t parity) {
-  return __all_sync(0xffffffffu, mbar_test_wait(bar, parity));
-}
-
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // Debug build (-DLMV_DCA_TRACE): cycle accounting per role (lane 0 of one warp per role), read back with lmv_debug_dca_trace().

@@ -205,6 +205,10 @@ __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
       ::"r"(smem_u32(bar))
       : "memory");
 }
+// warp-collective non-blocking phase test with a provably uniform result (for the event loops of the warp-collective issuers)
+__device__ __forceinline__ bool mbar_test_wait_warp(uint64_t* bar, uint32_t parity) {
+  return __all_sync(0xffffffffu, mbar_test_wait(bar, parity));
+}
 // Arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

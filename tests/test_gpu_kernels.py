@@ -438,7 +438,8 @@ def test_attention_meta_queries_over_image_tokens(B, h, Lq, Lk):
 
 # ---- tail / export ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,h,T,N", [(3, 12, 212, 196), (2, 16, 65, 49), (2, 6, 196, 196), (1, 3, 224, 208), (5, 2, 130, 128), (2, 4, 16, 16),
-                                     (300, 12, 212, 196), (2, 12, 1024, 1024), (3, 16, 256, 256), (1, 2, 500, 500), (2, 3, 2048, 2048)])
+                                     (300, 12, 212, 196), (2, 12, 1024, 1024), (3, 16, 256, 256), (1, 2, 500, 500), (2, 3, 2048, 2048),
+                                     (2, 3, 300, 300), (1, 3, 1900, 1900), (1, 4, 4096, 4096)])
 def test_attention_self_two_segments(B, h, T, N):
     """Image tokens (rows < N) and meta tokens (rows >= N) of a packed qkv buffer attend within their own segment."""
     Cc = h * 32
