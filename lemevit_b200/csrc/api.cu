@@ -46,6 +46,13 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(LMV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  A fresh thread (nn.DataParallel
+  // runs every replica in its own worker thread) only gets the runtime's primary context bound by its first runtime call.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    LMV_CUDA_OK(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   cuuint64_t gdims[5], gstrides[5];
   cuuint32_t gbox[5], estr[5];
   for (int i = 0; i < rank; ++i) {

@@ -210,7 +210,24 @@ class LeMeViT(nn.Module):
         replica = super()._replicate_for_data_parallel()
         replica.__dict__["_src_sig"] = self._signature()
         replica.__dict__["_sig_tensors"] = None
+        keys = self.__dict__.get("_sd_keys")
+        if keys is None:
+            keys = self.__dict__["_sd_keys"] = list(self.state_dict().keys())
+        replica.__dict__["_sd_keys"] = keys
         return replica
+
+    def _weights(self):
+        """state_dict of this module; for a DataParallel replica (whose parameters are plain tensor attributes, not registered
+        Parameters, so that ``state_dict()`` is empty) the same keys resolved attribute by attribute."""
+        if self.__dict__.get("_src_sig") is None:
+            return self.state_dict()
+        out = {}
+        for key in self.__dict__["_sd_keys"]:
+            obj = self
+            for part in key.split("."):
+                obj = getattr(obj, part)
+            out[key] = obj
+        return out
 
     def _drop_engine(self):
         """Close every native engine of this module (weights changed / module surgery)."""
@@ -221,6 +238,7 @@ class LeMeViT(nn.Module):
                     eng.close()
                 engines.clear()
         self.__dict__["_sig_tensors"] = None
+        self.__dict__["_sd_keys"] = None
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__["_sig_tensors"] = None      # .to() / .half() / .cuda() may replace Parameter objects
@@ -246,7 +264,7 @@ class LeMeViT(nn.Module):
                 # the weights of the source module changed: engines of other devices hold stale copies too
                 for k in [k for k, (e, sg) in self._engines.items() if sg != sig]:
                     self._engines.pop(k)[0].close()
-            eng = Engine(self.state_dict(), depth=self.depth, embed_dim=list(self.embed_dim),
+            eng = Engine(self._weights(), depth=self.depth, embed_dim=list(self.embed_dim),
                          mlp_ratios=self.mlp_ratios, attn_type=self.attn_type, head_dim=self.head_dim,
                          queries_len=self.queries_len, num_classes=self.num_classes, in_chans=self.in_chans,
                          backbone=self.backbone_mode, device=device, chunk=self.native_chunk)
@@ -264,7 +282,7 @@ class LeMeViT(nn.Module):
                 new.__dict__[k] = {}
             elif k == "_engines_lock":
                 new.__dict__[k] = threading.Lock()
-            elif k in ("_sig_tensors", "_src_sig"):
+            elif k in ("_sig_tensors", "_src_sig", "_sd_keys"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
@@ -276,6 +294,7 @@ class LeMeViT(nn.Module):
         d["_engines_lock"] = None
         d["_sig_tensors"] = None
         d["_src_sig"] = None
+        d["_sd_keys"] = None
         return d
 
     def __setstate__(self, d):
