@@ -85,7 +85,8 @@ def parse_args():
 
 # kernel class (native plan profile) -> kernel symbol in the ncu summaries under profiles/
 _CLASS_SYMBOL = {"gemm_tcgen05": "gemm_bf16_tn_tcgen05", "mlp_fused_tcgen05": "mlp_fused_tcgen05", "attention_self_tcgen05": "attention_self_kernel",
-                 "attention_tcgen05": "attention_tc_kernel", "attention_meta_tcgen05": "attention_meta_kernel", "posembed_layernorm": "posembed_tile_kernel"}
+                 "attention_tcgen05": "attention_tc_kernel", "attention_meta_tcgen05": "attention_meta_kernel", "posembed_layernorm": "posembed_tile_kernel",
+                 "dca_fused_tcgen05": "dca_x_kernel", "meta_branch": "meta_chain_kernel"}
 
 
 def ncu_traffic(kernel_class: str):
@@ -97,7 +98,8 @@ def ncu_traffic(kernel_class: str):
         try:
             k = json.load(open(path))["kernels"].get(sym)
             if k:
-                return {"bytes_per_launch": k["dram_bytes_per_launch"], "share_of_step_under_ncu": k["share"], "source": os.path.relpath(path, ROOT)}
+                return {"bytes_per_launch": k["dram_bytes_per_launch"], "share_of_step_under_ncu": k["share"], "source": os.path.relpath(path, ROOT),
+                        "tensor_pipe_util_ncu": k.get("tensor_pipe_util"), "tensor_pipe_util_best_launch_ncu": k.get("tensor_pipe_util_best_launch")}
         except Exception:
             continue
     return None
@@ -497,6 +499,14 @@ def run_ours(args):
                     "flops_per_launch": dom["flops"] / dom["launches"],
                     "step_achieved": value / world * gflop_img / 1e3, "step_frac": value / world * gflop_img / 1e3 / pk["bf16_tflops_sustained"],
                     "serial_step_ms": tot_ms / 3,
+                    # the fused cross-attention ('C' / 'D' block) kernel of the north star: algorithmic TFLOP/s of what it replaces
+                    # (live CUDA events) next to the hardware-counted tensor-pipe utilisation of the committed ncu launch list
+                    "fused_dca_kernel": (lambda d, t: None if d is None else {
+                        "ms_per_step": d["device_ms"] / 3, "launches_per_step": d["launches"] // 3,
+                        "algorithmic_tflops": d["flops"] / (d["device_ms"] * 1e-3) / 1e12,
+                        "frac_of_sustained_peak": d["flops"] / (d["device_ms"] * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                        "tensor_pipe_util_ncu": (t or {}).get("tensor_pipe_util_ncu"), "ncu_source": (t or {}).get("source")})(
+                        next((q for q in prof if q["name"] == "dca_fused_tcgen05"), None), ncu_traffic("dca_fused_tcgen05")),
                     "classes": {p["name"]: {"ms_per_step": p["device_ms"] / 3, "launches": p["launches"] // 3,
                                             "tflops": p["flops"] / (p["device_ms"] * 1e-3) / 1e12 if p["device_ms"] else 0.0,
                                             "gbs": p["bytes"] / (p["device_ms"] * 1e-3) / 1e9 if p["device_ms"] else 0.0} for p in prof}}

@@ -76,7 +76,9 @@ int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
  *   "fused_mlp" (default 1): run `x + mlp(norm2(x))` as ONE kernel (lmv_mlp_fused) where the shape allows it;
  *   "direct_stem" (default 1): first stem convolution as a direct kernel (lmv_stem_conv1) instead of im2col + GEMM;
  *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self);
- *   "fused_dca" (default 1): 'C' / 'D' blocks through the fused cross-attention kernels (lmv_dca_block) where the shape allows it. */
+ *   "fused_dca" (default 1): 'C' / 'D' blocks through the fused cross-attention kernels (lmv_dca_block) where the shape allows it;
+ *   "dca_pipe" (default 0): the pipelined schedule of the fused cross-attention kernel where tensor memory allows it (A/B switch;
+ *   measured slower than the one-tile-at-a-time schedule on B200). */
 int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
 /* test hook (block-level parity against the reference's forward hooks): after block `block` of stage `stage` every forward
  * copies the block's outputs to x_tokens_out [B, N, C] bf16 (token-major) and c_out [B, queries_len, C] bf16 (either may be

@@ -164,6 +164,7 @@ struct lmv_plan {
   int fused_mlp = 1;
   int fused_self_attn = 1;
   int fused_dca = 1;
+  int dca_pipe = 0;      // pipelined schedule of the fused cross-attention kernel: measured 5-10 % SLOWER than one tile at a time
   int direct_stem = 1;
   int profile = 0;
   int tap_stage = -1, tap_block = -1;       // test hook: copy (x, c) after this block to tap_x / tap_c
@@ -750,7 +751,8 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         // xn <- x + dw(x) (raw; norm1 is folded into the kv GEMM through stats1)
         const int sp = b.posln(xbuf[cur], bw.dw_w, bw.dw_b, xn, nullptr, B, g.H[i], g.W[i], T, C, stats1);
         if (fuse_dca) {
-          b.dca_block('C', xn, stats1, sp, nullptr, nullptr, cc, bw, B, N, C, heads, Hd, 0.f, 1.0f / sqrtf((float)c.head_dim), dca_ws);
+          b.dca_block('C', xn, stats1, sp, nullptr, nullptr, cc, bw, B, N, C, heads, Hd, 0.f, 1.0f / sqrtf((float)c.head_dim), dca_ws,
+                      plan->dca_pipe ? 0 : 2);
         } else {
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
         b.linear(cn, C, bw.wa, bw.ba, B * M, C, C, cqkv, C);
@@ -770,7 +772,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         const double scale = 1.0 / std::sqrt((double)C);                       // :235 full channel dim
         const double scale_x = std::log((double)M) / std::log((double)N) * scale;  // :255 math.log(M, N)
         if (fuse_dca) {
-          b.dca_block('D', x, stats1, sp, x, stats2, cc, bw, B, N, C, heads, Hd, (float)scale_x, (float)scale, dca_ws);
+          b.dca_block('D', x, stats1, sp, x, stats2, cc, bw, B, N, C, heads, Hd, (float)scale_x, (float)scale, dca_ws, plan->dca_pipe ? 0 : 2);
           b.mlp(x, stats2, 1, bw, B * N, C, Hd, hid);                                // norm2 folded, hidden stays on chip
         } else {
         b.ln(cc, cn, nullptr, nullptr, B * M, C, 1e-6f);
@@ -1059,6 +1061,7 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   else if (n == "fused_self_attn") plan->fused_self_attn = value ? 1 : 0;
   else if (n == "direct_stem") plan->direct_stem = value ? 1 : 0;
   else if (n == "fused_dca") plan->fused_dca = value ? 1 : 0;
+  else if (n == "dca_pipe") plan->dca_pipe = value ? 1 : 0;
   else return fail(LMV_ERR_INVALID, "set_option: unknown option " + n);
   plan->cache.clear();   // schedules are rebuilt with the new setting
   return LMV_OK;
