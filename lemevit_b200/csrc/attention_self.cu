@@ -6,7 +6,7 @@
 // sm_100a design — one CTA per SM, looping over work items (image, head, pair of 128-row query tiles):
 //   warp 0        TMA producer: K, V [Lkp x 32] and the two Q tiles [128 x 32] of the item (64B swizzle) into a 2-stage ring —
 //                 K and V are fetched ONCE for both query tiles
-//   warp 1        one thread issues tcgen05.mma:  S_g = Q_g K^T  (M=128, N=Lkp<=224, K=32)   -> TMEM columns [224 g, 224 g + Lkp)
+//   warps 1, 3    one issuer per softmax group:  S_g = Q_g K^T  (M=128, N=Lkp<=224, K=32)   -> TMEM columns [224 g, 224 g + Lkp)
 //                                                 O_g = P_g V    (M=128, N=32,  K=Lkp)       -> TMEM columns [448 + 32 g, +32)
 //                 S_g of item i+1 is issued BEFORE P_g V of item i, so a softmax group always finds its next scores ready
 //   warps 4..11   softmax group 0 (query tile 0): two warps per TMEM lane quarter, each owning half of the key columns of its 32
@@ -53,7 +53,8 @@ struct SelfParams {
 };
 
 struct Ctrl {
-  uint64_t ld_full[2], ld_empty[2];
+  uint64_t kq_full[2], kq_empty[2];   // Q tiles + K of a stage: free again as soon as the item's two S MMAs are done
+  uint64_t v_full[2], v_empty[2];     // V of a stage: read by the item's P V MMAs, one softmax later
   uint64_t s_full[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
   uint32_t tmem_base;
 };
@@ -75,6 +76,27 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw64_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Debug build (-DLMV_ATTN_TRACE): cycle account of one warp per (group, column half), read back with lmv_debug_attn_trace().
+// slots: 0 item setup, 1 wait s_full, 2 pass 1, 3 group sync, 4 wait p_empty, 5 pass 2, 6 output epilogue (incl. wait o_full), 7 total
+#ifdef LMV_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[148 * 5 * 8];
+#define TR_INIT unsigned long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t = clock64(); const long long tr_t0 = tr_t;
+#define TR(i) { const long long now_ = clock64(); tr[i] += (unsigned long long)(now_ - tr_t); tr_t = now_; }
+#define TR_FLUSH(role) { tr[7] = (unsigned long long)(clock64() - tr_t0); if (lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_attn_trace[((size_t)blockIdx.x * 5 + (role)) * 8 + i_] += tr[i_]; }
+#else
+#define TR_INIT
+#define TR(i)
+#define TR_FLUSH(role)
+#endif
+// -DLMV_ATTN_TRACE=3: absolute timestamps of CTA 0's first 16 items: [role 0..5][item][slot 0..7] (roles: softmax g0 h0, g0 h1, g1 h0, g1 h1
+// (lane quarter 0), issuer g0, issuer g1)
+#if defined(LMV_ATTN_TRACE) && LMV_ATTN_TRACE == 3
+__device__ long long g_attn_events[6 * 16 * 8];
+#define EV(role, item, slot) { if (blockIdx.x == 0 && lane == 0 && (item) < 16) g_attn_events[((role) * 16 + (int)(item)) * 8 + (slot)] = clock64(); }
+#else
+#define EV(role, item, slot)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1)
 attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const SelfParams p) {
@@ -91,8 +113,10 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctrl->ld_full[i], 1);
-      mbar_init(&ctrl->ld_empty[i], 1);
+      mbar_init(&ctrl->kq_full[i], 1);
+      mbar_init(&ctrl->kq_empty[i], p.qtiles > 1 ? 2 : 1);   // one commit per issuer warp
+      mbar_init(&ctrl->v_full[i], 1);
+      mbar_init(&ctrl->v_empty[i], p.qtiles > 1 ? 2 : 1);
       mbar_init(&ctrl->s_full[i], 1);
       mbar_init(&ctrl->p_full[i], kGroupWarps);
       mbar_init(&ctrl->p_empty[i], 1);
@@ -118,93 +142,118 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t kv_bytes = (uint32_t)(p.Lkp * kD * 2);
 
   // item -> (b, h, pair of query tiles, key block); the key block is the fastest index: neighbouring CTAs share Q in L2
+  // (32-bit arithmetic: the host checks items < 2^31; 64-bit divisions cost the softmax warps ~1.5k cycles per item)
   auto decode = [&](long long it, int& b, int& h, int& pr, int& kvb) {
-    long long item = blockIdx.x + it * gridDim.x;
-    kvb = (int)(item % p.nkv);
-    item /= p.nkv;
-    pr = (int)(item % p.pairs);
-    const long long bh = item / p.pairs;
-    h = (int)(bh % p.heads);
-    b = (int)(bh / p.heads);
+    uint32_t item = blockIdx.x + (uint32_t)it * gridDim.x;
+    kvb = 0; pr = 0;
+    if (p.nkv > 1) { const uint32_t t = item / (uint32_t)p.nkv; kvb = (int)(item - t * (uint32_t)p.nkv); item = t; }
+    if (p.pairs > 1) { const uint32_t t = item / (uint32_t)p.pairs; pr = (int)(item - t * (uint32_t)p.pairs); item = t; }
+    const uint32_t bq = item / (uint32_t)p.heads;
+    h = (int)(item - bq * (uint32_t)p.heads);
+    b = (int)bq;
   };
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
+    // Q/K of item i+1 are requested before V of item i: their slot was released an item earlier (after S(i-1)), so the S MMA of the
+    // next item never waits for memory; V(i) is only needed by P V(i), after the softmax of item i.
     if (lane == 0) {
-      for (long long it = 0; it < n_my; ++it) {
+      auto load_qk = [&](long long it) {
         const int s = (int)(it & 1);
         const uint32_t ph = (uint32_t)(it >> 1) & 1u;
         int b, h, pr, kvb;
         decode(it, b, h, pr, kvb);
         const bool has1 = (2 * pr + 1) < p.qtiles;
-        mbar_wait_lean(&ctrl->ld_empty[s], ph ^ 1u);
+        mbar_wait_lean(&ctrl->kq_empty[s], ph ^ 1u);
         uint8_t* st = sStage + (size_t)s * kStageBytes;
-        mbar_expect_tx(&ctrl->ld_full[s], (uint32_t)(kQBytes * (has1 ? 2 : 1)) + 2u * kv_bytes);
-        tma_load_3d(st, &tmQ, &ctrl->ld_full[s], h * kD, (2 * pr) * kQTile, b);
-        if (has1) tma_load_3d(st + kQBytes, &tmQ, &ctrl->ld_full[s], h * kD, (2 * pr + 1) * kQTile, b);
-        tma_load_3d(st + 2 * kQBytes, &tmK, &ctrl->ld_full[s], h * kD, kvb * p.KB, b);   // rows past T are zero-filled
-        tma_load_3d(st + 2 * kQBytes + kKVBytes, &tmV, &ctrl->ld_full[s], h * kD, kvb * p.KB, b);
+        mbar_expect_tx(&ctrl->kq_full[s], (uint32_t)(kQBytes * (has1 ? 2 : 1)) + kv_bytes);
+        tma_load_3d(st, &tmQ, &ctrl->kq_full[s], h * kD, (2 * pr) * kQTile, b);
+        if (has1) tma_load_3d(st + kQBytes, &tmQ, &ctrl->kq_full[s], h * kD, (2 * pr + 1) * kQTile, b);
+        tma_load_3d(st + 2 * kQBytes, &tmK, &ctrl->kq_full[s], h * kD, kvb * p.KB, b);   // rows past T are zero-filled
+      };
+      auto load_v = [&](long long it) {
+        const int s = (int)(it & 1);
+        const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+        int b, h, pr, kvb;
+        decode(it, b, h, pr, kvb);
+        mbar_wait_lean(&ctrl->v_empty[s], ph ^ 1u);
+        mbar_expect_tx(&ctrl->v_full[s], kv_bytes);
+        tma_load_3d(sStage + (size_t)s * kStageBytes + 2 * kQBytes + kKVBytes, &tmV, &ctrl->v_full[s], h * kD, kvb * p.KB, b);
+      };
+      if (n_my > 0) load_qk(0);
+      for (long long it = 0; it < n_my; ++it) {
+        if (it + 1 < n_my) load_qk(it + 1);
+        load_v(it);
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer: whole warp in uniform control flow, one elected lane issues (umma.cuh) ----------------
-    {
+  } else if (warp == 1 || warp == 3) {
+    // ---------------- MMA issuers: warp 1 for softmax group 0, warp 3 for group 1 ----------------
+    // (whole warp in uniform control flow, one elected lane issues: umma.cuh).  Both S_g(i+1) and P_g V(i) hang on ONE event, "group g
+    // has written P_g(i)", so each issuer blocks on p_full[g] (hardware-suspended try_wait: ~100 cycles from the arrive to the first
+    // MMA; an event loop polling four barriers per group needed ~900) and issues S_g(i+1) first — the group's warps are waiting for
+    // it — then the 14 small P V MMAs, whose ISSUE (~900 cycles next to four busy softmax warps on the same scheduler) is the slow
+    // part: with one issuer for both groups it sat in front of the other group's S.
+    //   S_g(i+1)  needs P_g(i) written (=> S_g(i) fully consumed) and the Q/K slot of item i+1
+    //   PV_g(i)   needs P_g(i) written, V(i), and the output epilogue of item i-1 done with O_g
+    const int g = warp >> 1;
+    if (g == 0 || two) {
       const uint32_t idesc_s = make_idesc_bf16(kQTile, p.Lkp);
       const uint32_t idesc_o = make_idesc_bf16(kQTile, kD) | (1u << 16);   // b_major = MN (V as loaded)
       const int ksteps = p.Lkp >> 4;
-      auto issue_s = [&](long long it, int g) {   // S_g(it) = Q_g K^T
+      const uint32_t d_s = tmem + (uint32_t)(g * kSCols), d_o = tmem + kOCol + (uint32_t)(g * kD);
+      auto issue_s = [&](long long it) {   // S_g(it) = Q_g K^T; the Q/K slot frees when both groups' S MMAs have finished
         const uint8_t* st = sStage + (size_t)(it & 1) * kStageBytes;
         const uint64_t dq = make_kmajor_desc<64>(smem_u32(st + (size_t)g * kQBytes));
         const uint64_t dk = make_kmajor_desc<64>(smem_u32(st + 2 * kQBytes));
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss_warp(tmem + (uint32_t)(g * kSCols), dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)(k != 0));
+        for (int k = 0; k < kD / 16; ++k) umma_bf16_ss_warp(d_s, dq + 2ull * k, dk + 2ull * k, idesc_s, (uint32_t)(k != 0));
         umma_commit_warp(&ctrl->s_full[g]);
+        umma_commit_warp(&ctrl->kq_empty[it & 1]);
       };
-      // Event loop: per group the next S and the next P V to issue; whichever dependency completes first is served first, so
-      // the two softmax groups never wait for each other's hand-shakes.
-      //   S_g(i)   needs the K/Q stage of item i and P_g(i-1) written (which implies S_g(i-1) fully consumed)
-      //   PV_g(i)  needs P_g(i) written and the output epilogue of item i-1 done with O_g
-      const int ng = two ? 2 : 1;
-      long long s_next[2] = {0, 0}, pv_next[2] = {0, 0}, released = 0;
-      const long long t_start = clock64();
-      while (pv_next[0] < n_my || (ng == 2 && pv_next[1] < n_my)) {
-        bool progress = false;
-        for (int g = 0; g < ng; ++g) {
-          long long i = s_next[g];
-          if (i < n_my && i <= pv_next[g] + 1 && (i == 0 || mbar_test_wait_warp(&ctrl->p_full[g], (uint32_t)(i - 1) & 1u)) &&
-              mbar_test_wait_warp(&ctrl->ld_full[i & 1], (uint32_t)(i >> 1) & 1u)) {
-            tc_fence_after();
-            issue_s(i, g);
-            ++s_next[g];
-            progress = true;
-          }
-          i = pv_next[g];
-          if (i < n_my && i < s_next[g] && mbar_test_wait_warp(&ctrl->p_full[g], (uint32_t)i & 1u) &&
-              (i == 0 || mbar_test_wait_warp(&ctrl->o_empty[g], (uint32_t)(i - 1) & 1u))) {
-            tc_fence_after();
-            const uint8_t* st = sStage + (size_t)(i & 1) * kStageBytes;
-            const uint32_t pbase = smem_u32(sP + (size_t)g * kPBytes), vbase = smem_u32(st + 2 * kQBytes + kKVBytes);
-            for (int s = 0; s < ksteps; ++s) {
-              const uint64_t da = make_kmajor_desc<128>(pbase + (uint32_t)(s >> 2) * kPTileBytes) + 2ull * (s & 3);
-              const uint64_t db = make_mnmajor_sw64_desc(vbase + (uint32_t)s * (16 * kD * 2));
-              umma_bf16_ss_warp(tmem + kOCol + (uint32_t)(g * kD), da, db, idesc_o, (uint32_t)(s != 0));
-            }
-            umma_commit_warp(&ctrl->o_full[g]);
-            umma_commit_warp(&ctrl->p_empty[g]);
-            ++pv_next[g];
-            progress = true;
-            // a K/V/Q stage is free once BOTH groups' P V of that item (and hence every MMA reading it) have been issued
-            const long long both = ng == 2 ? (pv_next[0] < pv_next[1] ? pv_next[0] : pv_next[1]) : pv_next[0];
-            while (released < both) { umma_commit_warp(&ctrl->ld_empty[released & 1]); ++released; }
-          }
-        }
-        if (!progress) __nanosleep(40);
-        if (!progress && clock64() - t_start > (1ll << 33)) {
-          if (lane == 0) printf("[lemevit_b200] attention_self MMA loop stuck: block %d s_next %lld %lld pv_next %lld %lld of %lld\n", (int)blockIdx.x, s_next[0],
-                 s_next[1], pv_next[0], pv_next[1], n_my);
-          __trap();
-        }
+      auto wait_warp = [&](uint64_t* bar, uint32_t parity) { mbar_wait_lean(bar, parity); __syncwarp(); };
+      TR_INIT
+      if (n_my > 0) {
+        wait_warp(&ctrl->kq_full[0], 0u);
+        tc_fence_after();
+        issue_s(0);
       }
+      for (long long i = 0; i < n_my; ++i) {
+        TR(2)
+        wait_warp(&ctrl->p_full[g], (uint32_t)i & 1u);
+        TR(0)
+        EV(4 + g, i, 0)
+        if (i + 1 < n_my) {
+          wait_warp(&ctrl->kq_full[(i + 1) & 1], (uint32_t)((i + 1) >> 1) & 1u);
+          EV(4 + g, i, 1)
+          tc_fence_after();
+          issue_s(i + 1);
+        }
+        TR(1)
+        EV(4 + g, i, 2)
+        if (i > 0) wait_warp(&ctrl->o_empty[g], (uint32_t)(i - 1) & 1u);
+        EV(4 + g, i, 3)
+        wait_warp(&ctrl->v_full[i & 1], (uint32_t)(i >> 1) & 1u);
+        EV(4 + g, i, 4)
+        tc_fence_after();
+        // descriptors advance by plain adds on the 16-byte-unit address field (all operands sit below 256 KB)
+        uint64_t da = make_kmajor_desc<128>(smem_u32(sP + (size_t)g * kPBytes));
+        uint64_t db = make_mnmajor_sw64_desc(smem_u32(sStage + (size_t)(i & 1) * kStageBytes + 2 * kQBytes + kKVBytes));
+        for (int s = 0; s < ksteps; ++s) {
+          umma_bf16_ss_warp(d_o, da, db, idesc_o, (uint32_t)(s != 0));
+          da += ((s & 3) == 3) ? (uint64_t)((kPTileBytes >> 4) - 6) : 2ull;   // next 16 keys: +32 B inside a 64-key tile, else the next tile
+          db += (uint64_t)((16 * kD * 2) >> 4);
+        }
+        umma_commit_warp(&ctrl->o_full[g]);
+        umma_commit_warp(&ctrl->p_empty[g]);
+        umma_commit_warp(&ctrl->v_empty[i & 1]);   // the V slot frees when both groups' P V MMAs of item i have finished
+        EV(4 + g, i, 5)
+#if defined(LMV_ATTN_TRACE) && LMV_ATTN_TRACE == 3
+        wait_warp(&ctrl->o_full[g], (uint32_t)i & 1u);   // probe: when did the P V MMAs complete (the issuer has nothing else to do until the next p_full)
+        EV(4 + g, i, 6)
+#endif
+      }
+      TR(2)
+      if (g == 0) { TR_FLUSH(4) }
     }
   } else if (warp >= kFirstSoftmaxWarp) {
     // ---------------- softmax groups ----------------
@@ -261,6 +310,7 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     };
     const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
+    TR_INIT
 
     for (long long it = 0; it < n_my; ++it) {
       if (g >= p.qtiles) break;                        // a single query tile per (image, head): nothing for group 1
@@ -280,14 +330,27 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         kend = max(0, min(p.KB, p.T - kvb * p.KB));
       }
       const bool warp_active = tile * kQTile + q * 32 < p.T;   // warp-uniform: any valid row in this warp
-      // bit c of full_mask: every lane of this warp sees all 32 keys of chunk c (no masking code needed)
-      uint32_t full_mask = 0;
+      // Visibility of the 32-key chunks, per lane (= row): fully visible, fully hidden, or partial.
+      //   bit c of full_mask: every lane of this warp sees all 32 keys of chunk c (no masking at all)
+      //   bit c of part_mask: some lane sees only part of chunk c -> per-element masking of the loaded registers (at most the chunk
+      //                       that holds the image/meta boundary and the last chunk of the key block)
+      //   otherwise every lane sees the chunk entirely or not at all (the warp that holds image AND meta rows): bit c of vis says
+      //   which, and a hidden chunk costs nothing — pass 1 skips its maximum, pass 2 runs it with (scale, -max) = (0, -inf), so P = 0
+      uint32_t full_mask = 0, part_mask = 0, vis = 0;
       for (int c = cbeg; c < cend; ++c) {
         const int c0 = c * 32;
-        if (__all_sync(0xffffffffu, kbeg <= c0 && c0 + 32 <= kend)) full_mask |= 1u << c;
+        const bool l_full = kbeg <= c0 && c0 + 32 <= kend, l_none = kend <= c0 || kbeg >= c0 + 32;
+        if (l_full) vis |= 1u << c;
+        if (__all_sync(0xffffffffu, l_full)) full_mask |= 1u << c;
+        // (columns at or beyond Lkp were never written by the S MMA: stale TMEM bits, possibly NaN, must go through the select)
+        else if (__any_sync(0xffffffffu, !(l_full || l_none)) || c0 + 32 > p.Lkp) part_mask |= 1u << c;
       }
+      TR(0)
+      if (q == 0) { EV(g * 2 + hcol, it, 0) }
       mbar_wait_lean(&ctrl->s_full[g], n_done & 1u);
       tc_fence_after();
+      TR(1)
+      if (q == 0) { EV(g * 2 + hcol, it, 1) }
       float psum = 0.f, mxs_item = 0.f;
       float pm = -INFINITY;
       auto mask_chunk = [&](uint32_t (&v)[32], int c0) {
@@ -305,21 +368,29 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           uint32_t v[32];
           tmem_ld_x32(t_s + (uint32_t)(c * 32), v);
           tmem_ld_wait();
-          if (!((full_mask >> c) & 1u)) mask_chunk(v, c * 32);
+          if ((part_mask >> c) & 1u) mask_chunk(v, c * 32);
+          const bool hide = !((full_mask | part_mask) >> c & 1u) && !((vis >> c) & 1u);   // this lane sees nothing of an unmasked chunk
+          float c0m = m0, c1m = m1, c2m = m2, c3m = m3;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            m0 = fmaxf(m0, __uint_as_float(v[j]));
-            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
-            m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
-            m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+            c0m = fmaxf(c0m, __uint_as_float(v[j]));
+            c1m = fmaxf(c1m, __uint_as_float(v[j + 1]));
+            c2m = fmaxf(c2m, __uint_as_float(v[j + 2]));
+            c3m = fmaxf(c3m, __uint_as_float(v[j + 3]));
           }
+          if (!hide) { m0 = c0m; m1 = c1m; m2 = c2m; m3 = c3m; }
         }
         pm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       x_max[r] = pm;
+      TR(2)
+      if (q == 0) { EV(g * 2 + hcol, it, 2) }
       group_sync();                                     // partial maxima (and the previous item's partial sums) are visible
+      TR(3)
       // the P V MMA of the previous item must have finished reading this group's P tiles
       mbar_wait_lean(&ctrl->p_empty[g], (n_done & 1u) ^ 1u);
+      TR(4)
+      if (q == 0) { EV(g * 2 + hcol, it, 3) }
       if (warp_active) {
         const float mxs = fmaxf(pm, y_max[r]) * p.scale_log2e;
         mxs_item = mxs;
@@ -332,12 +403,14 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           uint32_t v[32];
           tmem_ld_x32(t_s + (uint32_t)c0, v);
           tmem_ld_wait();
-          if (!((full_mask >> c) & 1u)) mask_chunk(v, c0);
+          if ((part_mask >> c) & 1u) mask_chunk(v, c0);
+          const bool hide = !((full_mask | part_mask) >> c & 1u) && !((vis >> c) & 1u);
+          const float2 scc = hide ? make_float2(0.f, 0.f) : sc2, nmc = hide ? make_float2(-INFINITY, -INFINITY) : nm2;
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            float2 a0 = ffma2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), sc2, nm2);
-            float2 a1 = ffma2(make_float2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), sc2, nm2);
+            float2 a0 = ffma2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), scc, nmc);
+            float2 a1 = ffma2(make_float2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), scc, nmc);
             a0.x = ex2_approx(a0.x); a0.y = ex2_approx(a0.y);
             a1.x = ex2_approx(a1.x); a1.y = ex2_approx(a1.y);
             s0 = fadd2(s0, a0);
@@ -368,8 +441,12 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctrl->p_full[g]);
+      TR(5)
+      if (q == 0) { EV(g * 2 + hcol, it, 4) }
       // ---- deferred output epilogue of the previous item, while the tensor pipe works on this one ----
       if (prev_any) output_epilogue();
+      TR(6)
+      if (q == 0) { EV(g * 2 + hcol, it, 5) }
       ++n_done;
       prev_any = true;
       prev_ps = psum;
@@ -386,6 +463,7 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       group_sync();                                     // the partner's partial sums of the last item
       output_epilogue();
     }
+    if (q == 0) { TR_FLUSH(g * 2 + hcol) }
   }
   tc_fence_before();
   __syncthreads();
@@ -458,6 +536,7 @@ int attention_self_run(const AttnArgs& a, int T, int N, void* workspace, size_t 
   p.qtiles = (T + kQTile - 1) / kQTile;
   p.pairs = (p.qtiles + 1) / 2;
   p.items = (long long)a.B * a.heads * p.pairs * p.nkv;
+  LMV_REQUIRE(p.items < (1ll << 31), "attention_self: too many work items");
   p.part_o = nullptr; p.part_ml = nullptr;
   if (p.nkv > 1) {
     const size_t rows = (size_t)a.B * a.heads * (p.qtiles * kQTile) * p.nkv;
@@ -489,3 +568,21 @@ int attention_self_run(const AttnArgs& a, int T, int N, void* workspace, size_t 
 }
 
 }  // namespace lmv
+
+#if defined(LMV_ATTN_TRACE) && LMV_ATTN_TRACE == 3
+extern "C" int lmv_debug_attn_events(long long* host, int n) {
+  if (n > 6 * 16 * 8) n = 6 * 16 * 8;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  return cudaMemcpyFromSymbol(host, lmv::g_attn_events, sizeof(long long) * n) != cudaSuccess;
+}
+#endif
+#ifdef LMV_ATTN_TRACE
+// copies out and clears the [148 CTAs][4 warps][8 counters] cycle table of the traced launches (debug builds only)
+extern "C" int lmv_debug_attn_trace(unsigned long long* host, int n) {
+  static unsigned long long zero[148 * 5 * 8];
+  if (n > 148 * 5 * 8) n = 148 * 5 * 8;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(host, lmv::g_attn_trace, sizeof(unsigned long long) * n) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(lmv::g_attn_trace, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif

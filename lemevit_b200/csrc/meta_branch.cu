@@ -96,6 +96,28 @@ __device__ __forceinline__ void rows16_mma(const bf16* __restrict__ A0, int lda,
   else rows16_mma_nt<1>(A0, lda, W, ldw, N, K, epi, a_group_stride);
 }
 
+// Per-head contractions with K = 32 (the absorbed projections of meta_pre): out_h[m][n] = sum_d A[m][32h + d] W[n][32h + d] for every
+// head h and column n < N.  All (head, 8-column tile) pairs form ONE flat work list over the 16 warps, so the single 16-byte weight
+// load each pair needs is in flight for several pairs at once (a rows16_mma call per head would serialise heads x L2 latency).
+template <typename Epi>
+__device__ __forceinline__ void heads16_mma_k32(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, int heads, int N, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const int ntiles = N >> 3, total = heads * ntiles;
+#pragma unroll 4
+  for (int w = warp; w < total; w += kWarps) {
+    const int h = w / ntiles, tile = w - h * ntiles;
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(W + (size_t)(tile * 8 + g) * ldw + 32 * h + tq * 8));
+    const uint4 alo = *reinterpret_cast<const uint4*>(A + (size_t)g * lda + 32 * h + tq * 8);
+    const uint4 ahi = *reinterpret_cast<const uint4*>(A + (size_t)(g + 8) * lda + 32 * h + tq * 8);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_bf16_16816(acc, alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+    mma_bf16_16816(acc, alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+    const int n = tile * 8 + tq * 2;
+    epi(h, n, g, acc[0], acc[1]);
+    epi(h, n, g + 8, acc[2], acc[3]);
+  }
+}
+
 // LayerNorm without affine of the 16 fp32 rows -> bf16 rows (A operand of the next contraction); one warp per row
 __device__ __forceinline__ void rows16_layernorm(const float* in, int ld, bf16* out, int ldo, int C, float eps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,10 +159,9 @@ __device__ __forceinline__ void meta_pre_body(const MetaPreArgs& a, float* s_c, 
   // T[(h,m)][j] = scale * sum_d vec[m][32h + d] Wx[32h + d][j], through the transposed copy WxT[j][i] (K contiguous);
   // then the row sums of the bf16-rounded T and the bias constant scale * sum_d bx[32h + d] vec[m][32h + d]
   auto absorb = [&](int off, const bf16* WxT, const float* bx, float scale, bf16* out_g, float* sum_g, float* cst_g) {
-    for (int h = 0; h < a.heads; ++h)
-      rows16_mma(s_p + off + 32 * h, ldp, WxT + 32 * h, C, C, 32, [&](int n, int m, float v0, float v1) {
-        *reinterpret_cast<uint32_t*>(s_t + (size_t)(h * M + m) * C + n) = pack_bf16x2(v0 * scale, v1 * scale);
-      });
+    heads16_mma_k32(s_p + off, ldp, WxT, C, a.heads, C, [&](int h, int n, int m, float v0, float v1) {
+      *reinterpret_cast<uint32_t*>(s_t + (size_t)(h * M + m) * C + n) = pack_bf16x2(v0 * scale, v1 * scale);
+    });
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < R; r += kWarps) {
@@ -163,11 +184,10 @@ __device__ __forceinline__ void meta_pre_body(const MetaPreArgs& a, float* s_c, 
   absorb(a.q_off, a.WxkT, a.bxk, a.scale_c * kLog2e, a.ws.qt + (size_t)b * R * C, cst + 2 * R, cst + 3 * R);
   if (a.Wpx) {
     // Vt^T[j][(h,m)] = sum_d Wpx[j][32h + d] v2[m][32h + d]
-    for (int h = 0; h < a.heads; ++h)
-      rows16_mma(s_p + a.v_off + 32 * h, ldp, a.Wpx + 32 * h, C, C, 32, [&](int n, int m, float v0, float v1) {
-        s_t[(size_t)n * R + h * M + m] = __float2bfloat16(v0);
-        s_t[(size_t)(n + 1) * R + h * M + m] = __float2bfloat16(v1);
-      });
+    heads16_mma_k32(s_p + a.v_off, ldp, a.Wpx, C, a.heads, C, [&](int h, int n, int m, float v0, float v1) {
+      s_t[(size_t)n * R + h * M + m] = __float2bfloat16(v0);
+      s_t[(size_t)(n + 1) * R + h * M + m] = __float2bfloat16(v1);
+    });
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(s_t);
     uint4* dst = reinterpret_cast<uint4*>(a.ws.vt + (size_t)b * C * R);

@@ -1,0 +1,10 @@
+#!/bin/bash
+# self-attention kernel iteration: tests, per-op profile, bench, event timeline (trace build)
+mkdir -p gpurun_out
+: > gpurun_out/summary.txt
+run() { local name=$1 t=$2; shift 2; echo "=== $name" | tee -a gpurun_out/summary.txt; timeout $t "$@" > gpurun_out/$name.log 2>&1; echo "exit $?" | tee -a gpurun_out/summary.txt; tail -n ${TAILN:-6} gpurun_out/$name.log | cut -c1-400 | tee -a gpurun_out/summary.txt; }
+run gpu_tests 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_kernels.py -q --maxfail=12
+TAILN=100 run ops_base256 300 python tools/quick_bench.py lemevit_base 256 --ops --lanes=1
+CUTW=5000 TAILN=3 run bench_quick 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager-reference
+LEMEVIT_B200_LIB=$PWD/lemevit_b200/liblemevit_b200_trace.so timeout 120 python tools/attn_trace.py 256 12 212 196 > gpurun_out/attn_events.txt 2>&1
+true
