@@ -56,6 +56,7 @@ struct Ctrl {
   uint64_t kq_full[2], kq_empty[2];   // Q tiles + K of a stage: free again as soon as the item's two S MMAs are done
   uint64_t v_full[2], v_empty[2];     // V of a stage: read by the item's P V MMAs, one softmax later
   uint64_t s_full[2], p_full[2], p_empty[2], o_full[2], o_empty[2];
+
   uint32_t tmem_base;
 };
 
@@ -310,40 +311,46 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     };
     const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
+    // per-(query pair, key block) state: recomputed only when the pair or the key block changes (never, in the single-block case)
+    int st_pr = -1, st_kvb = -1, tile = 0, row = 0, kbeg = 0, kend = 0;
+    bool rok = false, warp_active = false;
+    uint32_t full_mask = 0, part_mask = 0, vis = 0;
     TR_INIT
 
     for (long long it = 0; it < n_my; ++it) {
       if (g >= p.qtiles) break;                        // a single query tile per (image, head): nothing for group 1
       int b, h, pr, kvb;
       decode(it, b, h, pr, kvb);
-      const int tile = 2 * pr + g;
-      const int row = tile * kQTile + r;
-      const bool rok = row < p.T;
-      // key range of this row inside the key block.  One block (T <= 224): image tokens attend image tokens, meta tokens attend
-      // meta tokens (rows that do not exist behave like image rows).  Split-KV: every row sees the block's keys below T.
-      int kbeg, kend;
-      if (p.nkv == 1) {
-        kbeg = (rok && row >= p.N) ? p.N : 0;
-        kend = (rok && row >= p.N) ? p.T : p.N;
-      } else {
-        kbeg = 0;
-        kend = max(0, min(p.KB, p.T - kvb * p.KB));
-      }
-      const bool warp_active = tile * kQTile + q * 32 < p.T;   // warp-uniform: any valid row in this warp
-      // Visibility of the 32-key chunks, per lane (= row): fully visible, fully hidden, or partial.
-      //   bit c of full_mask: every lane of this warp sees all 32 keys of chunk c (no masking at all)
-      //   bit c of part_mask: some lane sees only part of chunk c -> per-element masking of the loaded registers (at most the chunk
-      //                       that holds the image/meta boundary and the last chunk of the key block)
-      //   otherwise every lane sees the chunk entirely or not at all (the warp that holds image AND meta rows): bit c of vis says
-      //   which, and a hidden chunk costs nothing — pass 1 skips its maximum, pass 2 runs it with (scale, -max) = (0, -inf), so P = 0
-      uint32_t full_mask = 0, part_mask = 0, vis = 0;
-      for (int c = cbeg; c < cend; ++c) {
-        const int c0 = c * 32;
-        const bool l_full = kbeg <= c0 && c0 + 32 <= kend, l_none = kend <= c0 || kbeg >= c0 + 32;
-        if (l_full) vis |= 1u << c;
-        if (__all_sync(0xffffffffu, l_full)) full_mask |= 1u << c;
-        // (columns at or beyond Lkp were never written by the S MMA: stale TMEM bits, possibly NaN, must go through the select)
-        else if (__any_sync(0xffffffffu, !(l_full || l_none)) || c0 + 32 > p.Lkp) part_mask |= 1u << c;
+      if (pr != st_pr || kvb != st_kvb) {
+        st_pr = pr; st_kvb = kvb;
+        tile = 2 * pr + g;
+        row = tile * kQTile + r;
+        rok = row < p.T;
+        // key range of this row inside the key block.  One block (T <= 224): image tokens attend image tokens, meta tokens attend
+        // meta tokens (rows that do not exist behave like image rows).  Split-KV: every row sees the block's keys below T.
+        if (p.nkv == 1) {
+          kbeg = (rok && row >= p.N) ? p.N : 0;
+          kend = (rok && row >= p.N) ? p.T : p.N;
+        } else {
+          kbeg = 0;
+          kend = max(0, min(p.KB, p.T - kvb * p.KB));
+        }
+        warp_active = tile * kQTile + q * 32 < p.T;   // warp-uniform: any valid row in this warp
+        // Visibility of the 32-key chunks, per lane (= row): fully visible, fully hidden, or partial.
+        //   bit c of full_mask: every lane of this warp sees all 32 keys of chunk c (no masking at all)
+        //   bit c of part_mask: some lane sees only part of chunk c -> per-element masking of the loaded registers (at most the chunk
+        //                       that holds the image/meta boundary and the last chunk of the key block)
+        //   otherwise every lane sees the chunk entirely or not at all (the warp that holds image AND meta rows): bit c of vis says
+        //   which, and a hidden chunk costs nothing — pass 1 skips its maximum, pass 2 runs it with (scale, -max) = (0, -inf), so P = 0
+        full_mask = 0; part_mask = 0; vis = 0;
+        for (int c = cbeg; c < cend; ++c) {
+          const int c0 = c * 32;
+          const bool l_full = kbeg <= c0 && c0 + 32 <= kend, l_none = kend <= c0 || kbeg >= c0 + 32;
+          if (l_full) vis |= 1u << c;
+          if (__all_sync(0xffffffffu, l_full)) full_mask |= 1u << c;
+          // (columns at or beyond Lkp were never written by the S MMA: stale TMEM bits, possibly NaN, must go through the select)
+          else if (__any_sync(0xffffffffu, !(l_full || l_none)) || c0 + 32 > p.Lkp) part_mask |= 1u << c;
+        }
       }
       TR(0)
       if (q == 0) { EV(g * 2 + hcol, it, 0) }
@@ -372,11 +379,11 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const bool hide = !((full_mask | part_mask) >> c & 1u) && !((vis >> c) & 1u);   // this lane sees nothing of an unmasked chunk
           float c0m = m0, c1m = m1, c2m = m2, c3m = m3;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            c0m = fmaxf(c0m, __uint_as_float(v[j]));
-            c1m = fmaxf(c1m, __uint_as_float(v[j + 1]));
-            c2m = fmaxf(c2m, __uint_as_float(v[j + 2]));
-            c3m = fmaxf(c3m, __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 8) {   // FMNMX3: two new values per instruction
+            c0m = fmax3(c0m, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            c1m = fmax3(c1m, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            c2m = fmax3(c2m, __uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+            c3m = fmax3(c3m, __uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
           }
           if (!hide) { m0 = c0m; m1 = c1m; m2 = c2m; m3 = c3m; }
         }
@@ -389,6 +396,9 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       TR(3)
       // the P V MMA of the previous item must have finished reading this group's P tiles
       mbar_wait_lean(&ctrl->p_empty[g], (n_done & 1u) ^ 1u);
+      // (Measured: forcing the two groups to take turns at the exp pass does not help — one group alone is latency-bound in it, ~3.5k
+      // cycles per item either way — so the groups are left to run in lockstep, where the four warps of a scheduler keep MUFU busy
+      // (~80% during pass 2).  Walking the chunks in 16-column halves with the next tcgen05.ld in flight changes nothing either.)
       TR(4)
       if (q == 0) { EV(g * 2 + hcol, it, 3) }
       if (warp_active) {

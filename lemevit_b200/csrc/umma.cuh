@@ -290,6 +290,12 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // packed fp32 (two lanes per register pair: FFMA2 / FMUL2 / FADD2 on sm_100)
+// three-input maximum (FMNMX3 on sm_100a)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
                      rc = *reinterpret_cast<unsigned long long*>(&c), rd;
