@@ -18,6 +18,12 @@
 //               128B-swizzled K-major smem tiles H_g (the A operand of fc2).  After the last chunk of a tile they run the
 //               output epilogue: acc2 + b2 + residual -> bf16 -> global.
 // TMEM: acc2 in columns [0, C <= 256), the two acc1 buffers in columns [256, 512).
+// Wide variant (C = 384, the 'S' blocks of stage 3; HC = 64): acc2 [0, 384), two 64-column acc1 buffers [384, 512); fc2 is
+// issued as two N = C/2 halves; one X buffer (96 KB); the epilogue constants come through L1 (__ldg broadcasts) instead of
+// shared memory, and ONE ring of four 24 KB slots carries both weights in the order the tensor pipe consumes them —
+// W1'(j+1) as two 3-D boxes of three K-blocks, then the two [C/2 x 64] halves of W2(j) — so every byte of the 96 KB left
+// beside X and the hidden buffers is lookahead.  Per 128-row tile the weights (2.4 MB) stream from L2; unfused, the same
+// block writes and re-reads a [rows, 4C] hidden activation that no longer fits the L2.
 // LayerNorm (norm2) is folded exactly as in gemm.cu: the producer of x emitted per-row (sum, sum^2) partials.
 #include <algorithm>
 #include <mutex>
@@ -32,15 +38,11 @@ namespace {
 
 constexpr int BM = 128;          // rows per tile
 constexpr int BK = 64;           // K-block (one 128B swizzle span of bf16)
-constexpr int HC = 128;          // hidden columns per chunk
 constexpr int kEpiWarps = 16;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 constexpr int kMaxSlots = 8;
 constexpr int kXBlockBytes = BM * BK * 2;      // 16 KB
-constexpr int kHidBytes = BM * HC * 2;         // 32 KB per hidden buffer (2 K-blocks)
-constexpr int kW1BoxBytes = HC * BK * 2;       // 16 KB
-constexpr int kAcc1Col = 256;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct Ctrl {
@@ -56,6 +58,7 @@ static_assert(sizeof(Ctrl) <= 1024, "control block");
 
 
 
+template <int HC>   // hidden columns per chunk
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
@@ -63,13 +66,19 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
+  constexpr bool WIDE = HC == 64;
+  constexpr int kHidBytes = BM * HC * 2;         // hidden buffer: HC / 64 K-blocks of [128 rows x 128 B]
+  constexpr int kW1KbBytes = HC * BK * 2;        // one K-block of a W1' box
+  constexpr int kAcc1Col = WIDE ? 384 : 256;     // first TMEM column of the two fc1 accumulators
+  constexpr int kW1Kpb = WIDE ? 3 : 1;           // K-blocks per W1' box
+  constexpr int kW1BoxBytes = kW1Kpb * kW1KbBytes;   // 16 KB (narrow) / 24 KB (wide: == one W2 half, the unified ring's slot)
   const int x_bytes = p.kb1 * kXBlockBytes;
-  float4* sCB = reinterpret_cast<float4*>(smem + 1024);               // [Hd/2] (cs0, cs1, b0, b1) of two hidden columns
-  float* sB2 = reinterpret_cast<float*>(smem + 1024 + (size_t)p.Hd * 8);   // [C]
+  float4* sCB = reinterpret_cast<float4*>(smem + 1024);               // [Hd/2] (cs0, cs1, b0, b1) of two hidden columns   (narrow only)
+  float* sB2 = reinterpret_cast<float*>(smem + 1024 + (size_t)p.Hd * 8);   // [C]                                            (narrow only)
   uint8_t* sX = smem + 1024 + p.const_bytes;                          // nx buffers of kb1 K-blocks
   uint8_t* sH = sX + (size_t)p.nx * x_bytes;                          // nh hidden buffers
   uint8_t* sW1 = sH + (size_t)p.nh * kHidBytes;                       // ring 1
-  uint8_t* sW2 = sW1 + (size_t)p.n1slots * kW1BoxBytes;               // ring 2
+  uint8_t* sW2 = sW1 + (size_t)p.n1slots * kW1BoxBytes;               // ring 2 (narrow only)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const int J = p.chunks;
@@ -104,12 +113,14 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   pdl_launch_dependents();
   pdl_wait();   // barrier init / TMEM allocation above overlapped the previous kernel's tail
   // epilogue constants -> shared memory (read on every chunk by every epilogue warp)
-  for (int i = threadIdx.x; i < p.Hd / 2; i += kThreads) {
-    const float2 b = __ldg(reinterpret_cast<const float2*>(p.b1) + i);
-    const float2 c = p.cs1 ? __ldg(reinterpret_cast<const float2*>(p.cs1) + i) : make_float2(0.f, 0.f);
-    sCB[i] = make_float4(c.x, c.y, b.x, b.y);
+  if constexpr (!WIDE) {
+    for (int i = threadIdx.x; i < p.Hd / 2; i += kThreads) {
+      const float2 b = __ldg(reinterpret_cast<const float2*>(p.b1) + i);
+      const float2 c = p.cs1 ? __ldg(reinterpret_cast<const float2*>(p.cs1) + i) : make_float2(0.f, 0.f);
+      sCB[i] = make_float4(c.x, c.y, b.x, b.y);
+    }
+    for (int i = threadIdx.x; i < p.C; i += kThreads) sB2[i] = __ldg(p.b2 + i);
   }
-  for (int i = threadIdx.x; i < p.C; i += kThreads) sB2[i] = __ldg(p.b2 + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -127,13 +138,15 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int kb = 0; kb < p.kb1; ++kb)
           tma_load_2d(sX + (size_t)xb * x_bytes + (size_t)kb * kXBlockBytes, &tmX, &ctrl->x_full[xb], kb * BK, t * BM);
         if (++xb == p.nx) { xb = 0; xphase ^= 1u; }
-        for (int j = 0; j < J; ++j)
-          for (int kb = 0; kb < p.kb1; ++kb) {
-            mbar_wait(&ctrl->w1_empty[slot], wphase ^ 1u, 41);
-            mbar_expect_tx(&ctrl->w1_full[slot], (uint32_t)kW1BoxBytes);
-            tma_load_2d(sW1 + (size_t)slot * kW1BoxBytes, &tmW1, &ctrl->w1_full[slot], kb * BK, j * HC);
-            if (++slot == p.n1slots) { slot = 0; wphase ^= 1u; }
-          }
+        if constexpr (!WIDE) {
+          for (int j = 0; j < J; ++j)
+            for (int kb = 0; kb < p.kb1; ++kb) {
+              mbar_wait(&ctrl->w1_empty[slot], wphase ^ 1u, 41);
+              mbar_expect_tx(&ctrl->w1_full[slot], (uint32_t)kW1BoxBytes);
+              tma_load_2d(sW1 + (size_t)slot * kW1BoxBytes, &tmW1, &ctrl->w1_full[slot], kb * BK, j * HC);
+              if (++slot == p.n1slots) { slot = 0; wphase ^= 1u; }
+            }
+        }
       }
     }
   } else if (warp == 1) {
@@ -141,15 +154,40 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (lane == 0) {
       int slot = 0;
       uint32_t wphase = 0;
-      for (int it = 0; it < my_tiles; ++it)
-        for (int j = 0; j < J; ++j)
-          for (int kb = 0; kb < HC / BK; ++kb)
-            for (int q = 0; q < p.nparts2; ++q) {
-              mbar_wait(&ctrl->w2_empty[slot], wphase ^ 1u, 42);
-              mbar_expect_tx(&ctrl->w2_full[slot], (uint32_t)(p.n2 * BK * 2));
-              tma_load_2d(sW2 + (size_t)slot * p.slot2_bytes, &tmW2, &ctrl->w2_full[slot], j * HC + kb * BK, q * p.n2);
-              if (++slot == p.n2slots) { slot = 0; wphase ^= 1u; }
-            }
+      if constexpr (!WIDE) {
+        for (int it = 0; it < my_tiles; ++it)
+          for (int j = 0; j < J; ++j)
+            for (int kb = 0; kb < HC / BK; ++kb)
+              for (int q = 0; q < p.nparts2; ++q) {
+                mbar_wait(&ctrl->w2_empty[slot], wphase ^ 1u, 42);
+                mbar_expect_tx(&ctrl->w2_full[slot], (uint32_t)(p.n2 * BK * 2));
+                tma_load_2d(sW2 + (size_t)slot * p.slot2_bytes, &tmW2, &ctrl->w2_full[slot], j * HC + kb * BK, q * p.n2);
+                if (++slot == p.n2slots) { slot = 0; wphase ^= 1u; }
+              }
+      } else {
+        // unified ring (the w1_* barriers), in the issuer's consumption order: W1'(0), W1'(1), W2(0), W1'(2), W2(1), ..., W2(J-1)
+        auto put_w1 = [&](int j) {
+          for (int bx = 0; bx < p.w1_boxes; ++bx) {
+            mbar_wait(&ctrl->w1_empty[slot], wphase ^ 1u, 41);
+            mbar_expect_tx(&ctrl->w1_full[slot], (uint32_t)kW1BoxBytes);
+            tma_load_3d(sW1 + (size_t)slot * kW1BoxBytes, &tmW1, &ctrl->w1_full[slot], 0, j * HC, bx * kW1Kpb);   // (k in block, hidden row, K-block)
+            if (++slot == p.n1slots) { slot = 0; wphase ^= 1u; }
+          }
+        };
+        auto put_w2 = [&](int j) {
+          for (int q = 0; q < p.nparts2; ++q) {
+            mbar_wait(&ctrl->w1_empty[slot], wphase ^ 1u, 42);
+            mbar_expect_tx(&ctrl->w1_full[slot], (uint32_t)(p.n2 * BK * 2));
+            tma_load_2d(sW1 + (size_t)slot * kW1BoxBytes, &tmW2, &ctrl->w1_full[slot], j * HC, q * p.n2);
+            if (++slot == p.n1slots) { slot = 0; wphase ^= 1u; }
+          }
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+          put_w1(0);
+          for (int j = 1; j < J; ++j) { put_w1(j); put_w2(j - 1); }
+          put_w2(J - 1);
+        }
+      }
     }
   } else if (warp == 2) {
     // ---------------- MMA issuer: whole warp in uniform control flow, one elected lane issues (umma.cuh) ----------------
@@ -171,13 +209,17 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(&ctrl->acc1_empty[buf], (use & 1u) ^ 1u, 51);
         tc_fence_after();
         const uint32_t d = tmem_base + kAcc1Col + buf * HC;
-        for (int kb = 0; kb < p.kb1; ++kb) {
+        for (int bx = 0; bx < p.w1_boxes; ++bx) {
           mbar_wait(&ctrl->w1_full[s1], ph1, 52);
           tc_fence_after();
-          const uint64_t da = make_kmajor_desc<128>(xaddr + (uint32_t)kb * kXBlockBytes);
-          const uint64_t db = make_kmajor_desc<128>(smem_u32(sW1 + (size_t)s1 * kW1BoxBytes));
-          const int ks = min(BK / 16, (p.C - kb * BK) / 16);
-          for (int k = 0; k < ks; ++k) umma_bf16_ss_warp(d, da + 2ull * k, db + 2ull * k, idesc1, (uint32_t)((kb | k) != 0));
+#pragma unroll
+          for (int kk = 0; kk < kW1Kpb; ++kk) {
+            const int kb = bx * kW1Kpb + kk;
+            const uint64_t da = make_kmajor_desc<128>(xaddr + (uint32_t)kb * kXBlockBytes);
+            const uint64_t db = make_kmajor_desc<128>(smem_u32(sW1 + (size_t)s1 * kW1BoxBytes + (size_t)kk * kW1KbBytes));
+            const int ks = WIDE ? BK / 16 : min(BK / 16, (p.C - kb * BK) / 16);
+            for (int k = 0; k < ks; ++k) umma_bf16_ss_warp(d, da + 2ull * k, db + 2ull * k, idesc1, (uint32_t)((kb | k) != 0));
+          }
           umma_commit_warp(&ctrl->w1_empty[s1]);
           if (++s1 == p.n1slots) { s1 = 0; ph1 ^= 1u; }
         }
@@ -197,14 +239,24 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int kb = 0; kb < HC / BK; ++kb) {
           const uint64_t da = make_kmajor_desc<128>(smem_u32(sH + (size_t)hb * kHidBytes + (size_t)kb * kXBlockBytes));
           for (int q = 0; q < p.nparts2; ++q) {
-            mbar_wait(&ctrl->w2_full[s2], ph2, 55);
-            tc_fence_after();
-            const uint64_t db = make_kmajor_desc<128>(smem_u32(sW2 + (size_t)s2 * p.slot2_bytes));
             const uint32_t d = tmem_base + (uint32_t)(q * p.n2);
+            if constexpr (!WIDE) {
+              mbar_wait(&ctrl->w2_full[s2], ph2, 55);
+              tc_fence_after();
+              const uint64_t db = make_kmajor_desc<128>(smem_u32(sW2 + (size_t)s2 * p.slot2_bytes));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_warp(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | kb | k) != 0));
-            umma_commit_warp(&ctrl->w2_empty[s2]);
-            if (++s2 == p.n2slots) { s2 = 0; ph2 ^= 1u; }
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_warp(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | kb | k) != 0));
+              umma_commit_warp(&ctrl->w2_empty[s2]);
+              if (++s2 == p.n2slots) { s2 = 0; ph2 ^= 1u; }
+            } else {   // unified ring: the next slot holds this half of W2(j)
+              mbar_wait(&ctrl->w1_full[s1], ph1, 55);
+              tc_fence_after();
+              const uint64_t db = make_kmajor_desc<128>(smem_u32(sW1 + (size_t)s1 * kW1BoxBytes));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_warp(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | kb | k) != 0));
+              umma_commit_warp(&ctrl->w1_empty[s1]);
+              if (++s1 == p.n1slots) { s1 = 0; ph1 ^= 1u; }
+            }
           }
         }
         umma_commit_warp(&ctrl->hid_empty[hb]);
@@ -220,7 +272,8 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ---------------- epilogue warps ----------------
     const int q = warp & 3;                        // TMEM lane quarter
     const int e = (warp - kFirstEpiWarp) >> 2;     // 0..3
-    // this warp's 32 of the chunk's 128 hidden columns: K-block (e >> 1) of the hidden tile, 16-byte chunks (e & 1) * 4 ..
+    // this warp's HC / 4 of the chunk's hidden columns: columns e * HCW .. of the hidden tile (K-blocks of 64 columns, 16-byte chunks of 8)
+    constexpr int HCW = HC / 4;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int rloc = q * 32 + lane;                // row inside the tile == TMEM lane
     // LayerNorm statistics of this thread's row are fetched one tile ahead (<= 4 partial pairs)
@@ -271,8 +324,8 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             uint4 o[4];
   #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b0 = *reinterpret_cast<const float4*>(sB2 + c0 + 8 * i);
-              const float4 b1 = *reinterpret_cast<const float4*>(sB2 + c0 + 8 * i + 4);
+              const float4 b0 = WIDE ? __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + 8 * i)) : *reinterpret_cast<const float4*>(sB2 + c0 + 8 * i);
+              const float4 b1 = WIDE ? __ldg(reinterpret_cast<const float4*>(p.b2 + c0 + 8 * i + 4)) : *reinterpret_cast<const float4*>(sB2 + c0 + 8 * i + 4);
               const float2 r0 = unpack_bf16x2(res[i].x), r1 = unpack_bf16x2(res[i].y), r2_ = unpack_bf16x2(res[i].z),
                            r3 = unpack_bf16x2(res[i].w);
               o[i].x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + b0.x + r0.x, __uint_as_float(v[8 * i + 1]) + b0.y + r0.y);
@@ -316,29 +369,46 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t g = (uint32_t)(it * J + j);
         const uint32_t buf = g & 1u, use1 = g >> 1;
         const uint32_t hb = g & 1u, useh = g >> 1;
+        // wide variant: the constants of this warp's 16 hidden columns come through L1 (uniform addresses: one broadcast per load),
+        // requested before the accumulator wait
+        float4 gc[WIDE ? HCW / 4 : 1], gb[WIDE ? HCW / 4 : 1];
+        if constexpr (WIDE) {
+#pragma unroll
+          for (int i = 0; i < HCW / 4; ++i) {
+            gb[i] = __ldg(reinterpret_cast<const float4*>(p.b1 + j * HC + e * HCW) + i);
+            gc[i] = p.cs1 ? __ldg(reinterpret_cast<const float4*>(p.cs1 + j * HC + e * HCW) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         mbar_wait(&ctrl->acc1_full[buf], use1 & 1u, 60);
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld_x32(lane_addr + kAcc1Col + buf * HC + (uint32_t)(e * 32), v);
+        uint32_t v[HCW];
+        if constexpr (HCW == 32) tmem_ld_x32(lane_addr + kAcc1Col + buf * HC + (uint32_t)(e * HCW), v);
+        else tmem_ld_x16(lane_addr + kAcc1Col + buf * HC + (uint32_t)(e * HCW), v);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctrl->acc1_empty[buf]);   // accumulator drained: the next fc1 may overwrite it
-        const float4* cb = sCB + ((j * HC + e * 32) >> 1);
-        uint32_t pk[16];
+        const float4* cb = sCB + ((j * HC + e * HCW) >> 1);
+        uint32_t pk[HCW / 2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 c = cb[i];   // (cs, cs, b1, b1) of hidden columns 2i, 2i+1 of this warp's 32 — broadcast read
+        for (int i = 0; i < HCW / 2; ++i) {
+          float4 c;   // (cs, cs, b1, b1) of hidden columns 2i, 2i+1 of this warp's columns
+          if constexpr (WIDE) {
+            const float4 c4 = gc[i >> 1], b4 = gb[i >> 1];
+            c = (i & 1) ? make_float4(c4.z, c4.w, b4.z, b4.w) : make_float4(c4.x, c4.y, b4.x, b4.y);
+          } else {
+            c = cb[i];   // broadcast read from shared memory
+          }
           float2 a = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
           a = ffma2(r2, a, ffma2(n2v, make_float2(c.x, c.y), make_float2(c.z, c.w)));
           a = gelu_fast2(a);
           pk[i] = pack_bf16x2(a.x, a.y);
         }
         mbar_wait(&ctrl->hid_empty[hb], (useh & 1u) ^ 1u, 61);   // the fc2 that last read this buffer has retired
-        uint8_t* hrow = sH + (size_t)hb * kHidBytes + (size_t)(e >> 1) * kXBlockBytes + (size_t)rloc * 128;
+        uint8_t* hrow = sH + (size_t)hb * kHidBytes + (size_t)((e * HCW) >> 6) * kXBlockBytes + (size_t)rloc * 128;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ch = (e & 1) * 4 + i;
+        for (int i = 0; i < HCW / 8; ++i) {
+          const int ch = (((e * HCW) & 63) >> 3) + i;
           *reinterpret_cast<uint4*>(hrow + ((ch ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
         fence_proxy_async_smem();
@@ -359,17 +429,22 @@ PerDeviceOnce g_attr_once;
 
 }  // namespace
 
+static int mlp_hc(int C) { return C <= 256 ? 128 : 64; }
+
 bool mlp_fused_supported(int C, int Hd) {
   // acc2 [128 x C] + two acc1 buffers must fit the 512 TMEM columns; the X tile, two hidden buffers and both weight rings
-  // must fit 227 KB of shared memory
-  return C >= 32 && C <= 192 && C % 32 == 0 && Hd % HC == 0 && Hd >= HC && Hd <= 4096;
+  // must fit 227 KB of shared memory (C = 384: 96 KB X tile, 14 KB constants at Hd = 1536)
+  static const int wide = [] { const char* e = getenv("LMV_MLP_WIDE"); return e ? atoi(e) : 1; }();
+  const bool narrow = C >= 32 && C <= 192 && C % 32 == 0;
+  const bool wide_ok = wide && C == 384 && Hd <= 1536;
+  return (narrow || wide_ok) && Hd % 128 == 0 && Hd >= 128 && Hd <= 4096;
 }
 
 int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
   LMV_REQUIRE(a.x && a.W1 && a.W2 && a.b1 && a.b2 && a.out, "mlp_fused: null pointer");
   LMV_REQUIRE(a.R > 0, "mlp_fused: empty problem");
   if (!mlp_fused_supported(a.C, a.Hd))
-    return fail(LMV_ERR_UNSUPPORTED, "mlp_fused: needs C % 32 == 0, 32 <= C <= 192, hidden % 128 == 0, hidden <= 4096");
+    return fail(LMV_ERR_UNSUPPORTED, "mlp_fused: needs C % 32 == 0 with 32 <= C <= 192 (or C == 384 with hidden <= 1536), hidden % 128 == 0, hidden <= 4096");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   LMV_REQUIRE(al16(a.x) && al16(a.W1) && al16(a.W2) && al16(a.b1) && al16(a.b2) && al16(a.out) && al16(a.resid ? a.resid : a.x),
               "mlp_fused: pointers must be 16-byte aligned");
@@ -379,23 +454,40 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
   MlpParams& p = op->p;
   p.R = a.R; p.C = a.C; p.Hd = a.Hd;
   p.tiles = (a.R + BM - 1) / BM;
+  const int HC = mlp_hc(a.C);
+  const int kHidBytes = BM * HC * 2, kW1KbBytes = HC * BK * 2;
+  p.hc = HC;
   p.kb1 = (a.C + BK - 1) / BK;
   p.chunks = a.Hd / HC;
-  p.nparts2 = 1;
-  p.n2 = a.C;
+  p.nparts2 = a.C <= 256 ? 1 : 2;
+  p.n2 = a.C / p.nparts2;
   p.slot2_bytes = p.n2 * BK * 2;
-  p.const_bytes = ((a.Hd * 8 + a.C * 4 + 1023) / 1024) * 1024;
+  p.const_bytes = HC == 128 ? ((a.Hd * 8 + a.C * 4 + 1023) / 1024) * 1024 : 0;   // wide: constants come through L1
   const int x_bytes = p.kb1 * kXBlockBytes;
   const int budget = kSmemLimit - 2048 - p.const_bytes;     // ctrl + alignment slack
-  // X double-buffered when that still leaves one chunk of lookahead in each ring (kb1 W1' boxes, 2 W2 boxes)
-  const int min_rings = (p.kb1 + 1) * kW1BoxBytes + 3 * p.slot2_bytes;
-  p.nx = 2; p.nh = 2;
-  if (budget - p.nx * x_bytes - p.nh * kHidBytes < min_rings) p.nx = 1;
-  const int rest = budget - p.nx * x_bytes - p.nh * kHidBytes;
-  p.n2slots = std::min(4, std::max(2, (rest - (p.kb1 + 1) * kW1BoxBytes) / p.slot2_bytes));
-  p.n1slots = std::min(kMaxSlots, (rest - p.n2slots * p.slot2_bytes) / kW1BoxBytes);
-  LMV_REQUIRE(p.n1slots >= 2 && p.n2slots >= 2, "mlp_fused: shared memory budget (weight rings)");
-  op->smem_bytes = 2048 + p.const_bytes + p.nx * x_bytes + p.nh * kHidBytes + p.n1slots * kW1BoxBytes + p.n2slots * p.slot2_bytes;
+  p.nh = 2;
+  if (HC == 128) {
+    p.w1_kpb = 1;
+    p.w1_boxes = p.kb1;
+    // X double-buffered when that still leaves one chunk of lookahead in each ring (kb1 W1' boxes, 2 W2 boxes)
+    const int min_rings = (p.kb1 + 1) * kW1KbBytes + 3 * p.slot2_bytes;
+    p.nx = 2;
+    if (budget - p.nx * x_bytes - p.nh * kHidBytes < min_rings) p.nx = 1;
+    const int rest = budget - p.nx * x_bytes - p.nh * kHidBytes;
+    p.n2slots = std::min(4, std::max(2, (rest - (p.kb1 + 1) * kW1KbBytes) / p.slot2_bytes));
+    p.n1slots = std::min(kMaxSlots, (rest - p.n2slots * p.slot2_bytes) / kW1KbBytes);
+  } else {
+    // wide variant: one X buffer and ONE ring of 24 KB slots for both weights (W1' boxes of 3 K-blocks, W2 halves [C/2 x 64])
+    LMV_REQUIRE(p.kb1 % 3 == 0 && p.n2 * BK * 2 == 3 * kW1KbBytes, "mlp_fused: wide variant needs C == 384");
+    p.nx = 1;
+    p.w1_kpb = 3;
+    p.w1_boxes = p.kb1 / 3;
+    p.n2slots = 0;
+    p.n1slots = std::min(kMaxSlots, (budget + 1024 - p.nx * x_bytes - p.nh * kHidBytes) / (3 * kW1KbBytes));   // (no constants page: only the alignment slack is reserved)
+    LMV_REQUIRE(p.n1slots >= 3, "mlp_fused: shared memory budget (weight ring)");
+  }
+  LMV_REQUIRE(p.n1slots >= 2 && (HC == 64 || p.n2slots >= 2), "mlp_fused: shared memory budget (weight rings)");
+  op->smem_bytes = (HC == 128 ? 2048 : 1024 + 1023) + p.const_bytes + p.nx * x_bytes + p.nh * kHidBytes + p.n1slots * p.w1_kpb * kW1KbBytes + p.n2slots * p.slot2_bytes;
   LMV_REQUIRE(op->smem_bytes <= kSmemLimit, "mlp_fused: shared memory budget");
   p.b1 = a.b1; p.cs1 = a.cs1; p.b2 = a.b2;
   p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1; p.ln_eps = a.ln_eps; p.ln_inv_k = 1.0f / (float)a.C;
@@ -411,10 +503,17 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
     if ((rc = encode_tmap_bf16(&op->tmX, a.x, 2, dims, strides, box, 128))) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)a.C, (uint64_t)a.Hd};
-    uint64_t strides[1] = {(uint64_t)a.C * 2};
-    uint32_t box[2] = {BK, HC};
-    if ((rc = encode_tmap_bf16(&op->tmW1, a.W1, 2, dims, strides, box, 128))) return rc;
+    if (HC == 128) {
+      uint64_t dims[2] = {(uint64_t)a.C, (uint64_t)a.Hd};
+      uint64_t strides[1] = {(uint64_t)a.C * 2};
+      uint32_t box[2] = {BK, (uint32_t)HC};
+      if ((rc = encode_tmap_bf16(&op->tmW1, a.W1, 2, dims, strides, box, 128))) return rc;
+    } else {   // (k inside a K-block, hidden row, K-block): one box = w1_kpb stacked [HC x 64] K-blocks
+      uint64_t dims[3] = {(uint64_t)BK, (uint64_t)a.Hd, (uint64_t)p.kb1};
+      uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)BK * 2};
+      uint32_t box[3] = {BK, (uint32_t)HC, (uint32_t)p.w1_kpb};
+      if ((rc = encode_tmap_bf16(&op->tmW1, a.W1, 3, dims, strides, box, 128))) return rc;
+    }
   }
   {
     uint64_t dims[2] = {(uint64_t)a.Hd, (uint64_t)a.C};
@@ -426,8 +525,13 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
 }
 
 int mlp_fused_run(const MlpOp& op, cudaStream_t stream) {
-  LMV_CUDA_OK(g_attr_once.run([] { return cudaFuncSetAttribute(mlp_fused_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit); }));
-  LMV_CUDA_OK(launch_kernel(mlp_fused_tcgen05, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmX, op.tmW1, op.tmW2, op.p));
+  LMV_CUDA_OK(g_attr_once.run([] {
+    const cudaError_t e0 = cudaFuncSetAttribute(mlp_fused_tcgen05<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    const cudaError_t e1 = cudaFuncSetAttribute(mlp_fused_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    return e0 != cudaSuccess ? e0 : e1;
+  }));
+  auto fn = op.p.hc == 128 ? mlp_fused_tcgen05<128> : mlp_fused_tcgen05<64>;
+  LMV_CUDA_OK(launch_kernel(fn, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmX, op.tmW1, op.tmW2, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

@@ -188,7 +188,9 @@ def test_dca_block_batch_invariance_and_peaked_softmax():
 
 
 MLP_SHAPES = [(1000, 96, 384), (777, 192, 768), (300, 64, 256), (260, 160, 640), (130, 128, 512), (129, 192, 1280),
-              (40000, 96, 384), (25000, 192, 768)]
+              (40000, 96, 384), (25000, 192, 768),
+              # wide variant (256 < C <= 384: 64-column hidden chunks, fc2 in two halves, 3-D W1' boxes) — the stage-3 'S' blocks
+              (1000, 384, 1536), (130, 384, 512), (54272, 384, 1536), (333, 384, 128)]
 
 
 @pytest.mark.parametrize("R,C,Hd", MLP_SHAPES)
