@@ -162,6 +162,7 @@ struct lmv_plan {
   int chunk = 0;
   int debug_simt = 0;
   int fused_mlp = 1;
+  int fused_mlp_wide = 0;   // also fuse the C = 384 MLP of the 'S' blocks (measured: 175 us against 168 us for the two GEMMs — DESIGN.md §4)
   int fused_self_attn = 1;
   int fused_dca = 1;
   int dca_pipe = 0;      // pipelined schedule of the fused cross-attention kernel: measured 5-10 % SLOWER than one tile at a time
@@ -480,7 +481,7 @@ struct Builder {
   // otherwise fc1 (+LN fold, bias, GELU) and fc2 (+bias, residual) on the GEMM with the hidden activation in `hid`
   void mlp(bf16* x, const float* stats, int parts, const BlockW& bw, int R, int C, int Hd, bf16* hid) {
     if (rc) return;
-    if (!simt && plan->fused_mlp && mlp_fused_supported(C, Hd)) {
+    if (!simt && plan->fused_mlp && mlp_fused_supported(C, Hd) && (C <= 256 || plan->fused_mlp_wide)) {
       MlpArgs a;
       a.x = x; a.out = x; a.W1 = bw.w1; a.b1 = bw.b1; a.cs1 = bw.cs1; a.W2 = bw.w2; a.b2 = bw.b2;
       a.ln_stats = stats; a.ln_parts = parts; a.ln_eps = 1e-6f; a.R = R; a.C = C; a.Hd = Hd;
@@ -1058,6 +1059,7 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   if (rc) return rc;
   const std::string n(name);
   if (n == "fused_mlp") plan->fused_mlp = value ? 1 : 0;
+  else if (n == "fused_mlp_wide") plan->fused_mlp_wide = value ? 1 : 0;
   else if (n == "fused_self_attn") plan->fused_self_attn = value ? 1 : 0;
   else if (n == "direct_stem") plan->direct_stem = value ? 1 : 0;
   else if (n == "fused_dca") plan->fused_dca = value ? 1 : 0;

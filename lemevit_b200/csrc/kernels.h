@@ -130,6 +130,7 @@ struct MlpParams {
   int hc;          // hidden columns per chunk: 128 (C <= 256) or 64 (256 < C <= 384: acc2 takes 384 of the 512 TMEM columns)
   int w1_kpb;      // K-blocks per W1' TMA box (> 1: one 3-D box per slot, so 8 KB K-blocks do not pay the per-box cost)
   int w1_boxes;    // W1' boxes per hidden chunk = kb1 / w1_kpb
+  int pair;        // 1: CTA-pair kernel (cta_group::2, 256 rows per cluster; `tiles` counts pair tiles)
   const float *b1, *cs1, *b2, *ln_stats;
   int ln_parts;
   float ln_eps, ln_inv_k;

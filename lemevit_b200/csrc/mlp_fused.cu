@@ -425,6 +425,386 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Pair variant of the wide MLP (C = 384): two CTAs of a cluster (one TPC) work on 256 rows with cta_group::2 MMAs (M = 256).
+// Each CTA keeps ITS 128 rows of X, of the hidden tiles and of both accumulators, but only HALF of every weight box (the B
+// operand of a pair MMA is split along N: rank r holds rows [r N/2, (r+1) N/2)), so the same 96 KB ring holds two hidden chunks
+// of lookahead instead of one and the L2 -> SM weight traffic per row halves — the single-CTA wide variant is bound by the bytes
+// it can keep in flight (~2k cycles of L2 latency under load x 48 B/clk needed).
+//   leader (rank 0)  warp 2 issues every MMA; its mbarriers collect the TMA bytes of both CTAs (x_full, w_full), the arrivals of
+//                    its own epilogue warps and ONE forwarded arrival per event from the peer (acc1_empty, hid_full, acc2_empty)
+//   both CTAs        producers load their halves (completing on the leader's barriers), epilogue warps work on their own rows
+//                    and only ever arrive on their OWN CTA's barriers; tcgen05.commit multicasts to the barrier at the same
+//                    offset in both CTAs (w_empty, x_empty, acc1_full, hid_empty, acc2_full)
+//   peer (rank 1)    warps 2 and 3 forward "all 16 epilogue warps have arrived" to the leader's barrier: a cluster-scope
+//                    release arrive costs the issuing warp ~700 cycles, twice per 64-column chunk in every epilogue warp when
+//                    they signalled the leader directly (measured: the epilogue, not the tensor pipe, set the pace)
+// Ring slot (24 KB per CTA): W1'(j) = one 3-D box [6 K-blocks][32 hidden rows][64]; W2(j) = two boxes [96 out rows][64 hidden].
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairHC = 64;                     // hidden columns per chunk
+constexpr int kPairC = 384;
+constexpr int kPairKb = kPairC / BK;            // 6 K-blocks of X
+constexpr int kPairXBytes = kPairKb * kXBlockBytes;   // 96 KB
+constexpr int kPairHidBytes = BM * kPairHC * 2;       // 16 KB
+constexpr int kPairSlotBytes = 24 * 1024;
+constexpr int kPairSlots = 4;
+constexpr int kPairW1KbBytes = (kPairHC / 2) * BK * 2;   // 4 KB: this CTA's 32 hidden rows of one K-block
+constexpr int kPairN2 = kPairC / 2;             // fc2 in two N = 192 halves
+constexpr int kPairW2PartBytes = (kPairN2 / 2) * BK * 2;   // 12 KB: this CTA's 96 out rows of one half
+constexpr int kPairAcc1Col = 384;
+constexpr int kPairSmemBytes = 1024 + 1023 + kPairXBytes + 2 * kPairHidBytes + kPairSlots * kPairSlotBytes;
+static_assert(kPairSmemBytes <= kSmemLimit, "pair MLP shared memory");
+static_assert(kPairKb * kPairW1KbBytes == kPairSlotBytes && 2 * kPairW2PartBytes == kPairSlotBytes, "ring slot layout");
+
+// Debug build (-DLMV_MLP_TRACE): cycle account of the pair kernel's MMA issuer (leader CTAs), read back with lmv_debug_mlp_trace().
+// slots: 0 wait x_full, 1 wait acc1_empty, 2 wait w_full (fc1), 3 issue fc1, 4 wait hid_full (+ acc2_empty), 5 wait w_full (fc2), 6 issue fc2, 7 total
+#ifdef LMV_MLP_TRACE
+__device__ unsigned long long g_mlp_trace[148 * 8];
+__device__ int g_mlp_debug;   // timing experiments (lmv_debug_mlp_flags; results become wrong): 1 skip the fc1 MMAs, 2 skip the fc2 MMAs
+#define DBG(bit) (dbg_flags & (bit))
+#define DBG_INIT const int dbg_flags = g_mlp_debug;
+#define TR_INIT unsigned long long tr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tr_t = clock64(); const long long tr_t0 = tr_t;
+#define TR(i) { const long long now_ = clock64(); tr[i] += (unsigned long long)(now_ - tr_t); tr_t = now_; }
+#define TR_FLUSH { tr[7] = (unsigned long long)(clock64() - tr_t0); if (lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_mlp_trace[(size_t)blockIdx.x * 8 + i_] += tr[i_]; }
+#else
+#define TR_INIT
+#define TR(i)
+#define TR_FLUSH
+#define DBG(bit) 0
+#define DBG_INIT
+#endif
+
+struct CtrlPair {
+  uint64_t x_full, x_empty;
+  uint64_t w_full[kPairSlots], w_empty[kPairSlots];
+  uint64_t acc1_full[2], acc1_empty[2];
+  uint64_t hid_full[2], hid_empty[2];
+  uint64_t acc2_full, acc2_empty;
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  CtrlPair* ctrl = reinterpret_cast<CtrlPair*>(smem);
+  uint8_t* sX = smem + 1024;
+  uint8_t* sH = sX + kPairXBytes;
+  uint8_t* sW = sH + 2 * kPairHidBytes;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int J = p.chunks;
+  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  const int my_tiles = (pair < p.tiles) ? (p.tiles - 1 - pair) / npairs + 1 : 0;   // p.tiles counts 256-row pair tiles
+  auto row0_of = [&](int it) { return ((pair + it * npairs) * 2 + (int)rank) * BM; };
+  auto leader = [&](uint64_t* bar) { return mapa_u32(smem_u32(bar), 0u); };   // the leader's copy of a barrier
+
+  if (threadIdx.x == 0) {
+    mbar_init(&ctrl->x_full, 1);
+    mbar_init(&ctrl->x_empty, 1);
+    for (int i = 0; i < kPairSlots; ++i) {
+      mbar_init(&ctrl->w_full[i], 1);
+      mbar_init(&ctrl->w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctrl->acc1_full[i], 1);
+      mbar_init(&ctrl->acc1_empty[i], kEpiWarps + (rank == 0 ? 1 : 0));   // own epilogue warps (+ the peer's forwarder on the leader)
+      mbar_init(&ctrl->hid_full[i], kEpiWarps + (rank == 0 ? 1 : 0));
+      mbar_init(&ctrl->hid_empty[i], 1);
+    }
+    mbar_init(&ctrl->acc2_full, 1);
+    mbar_init(&ctrl->acc2_empty, kEpiWarps + (rank == 0 ? 1 : 0));
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(&ctrl->tmem_base, 512);
+    tmem_relinquish_2sm();
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs' barriers are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_base;
+
+  if (warp == 0) {
+    // ---------------- TMA producer A: this CTA's 128 rows of X ----------------
+    if (lane == 0) {
+      const uint32_t bar = leader(&ctrl->x_full);
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(&ctrl->x_empty, ((uint32_t)it & 1u) ^ 1u, 40);
+        if (rank == 0) mbar_expect_tx(&ctrl->x_full, 2u * kPairXBytes);
+        for (int kb = 0; kb < kPairKb; ++kb) tma_load_2d_2sm(sX + (size_t)kb * kXBlockBytes, &tmX, bar, kb * BK, row0_of(it));
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- TMA producer B: this CTA's halves of the weight boxes, in the issuer's consumption order ----------------
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t wphase = 0;
+      auto next = [&]() { if (++slot == kPairSlots) { slot = 0; wphase ^= 1u; } };
+      auto put_w1 = [&](int j) {
+        mbar_wait(&ctrl->w_empty[slot], wphase ^ 1u, 41);
+        if (rank == 0) mbar_expect_tx(&ctrl->w_full[slot], 2u * kPairSlotBytes);
+        tma_load_3d_2sm(sW + (size_t)slot * kPairSlotBytes, &tmW1, leader(&ctrl->w_full[slot]), 0, j * kPairHC + (int)rank * (kPairHC / 2), 0);
+        next();
+      };
+      auto put_w2 = [&](int j) {
+        mbar_wait(&ctrl->w_empty[slot], wphase ^ 1u, 42);
+        if (rank == 0) mbar_expect_tx(&ctrl->w_full[slot], 2u * kPairSlotBytes);
+        const uint32_t bar = leader(&ctrl->w_full[slot]);
+        for (int q = 0; q < 2; ++q)
+          tma_load_2d_2sm(sW + (size_t)slot * kPairSlotBytes + (size_t)q * kPairW2PartBytes, &tmW2, bar, j * kPairHC, q * kPairN2 + (int)rank * (kPairN2 / 2));
+        next();
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        put_w1(0);
+        for (int j = 1; j < J; ++j) { put_w1(j); put_w2(j - 1); }
+        put_w2(J - 1);
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer (leader CTA only): whole warp in uniform control flow, one elected lane issues ----------------
+    if (rank == 0) {
+      const uint32_t idesc1 = make_idesc_bf16(2 * BM, kPairHC);
+      const uint32_t idesc2 = make_idesc_bf16(2 * BM, kPairN2);
+      const int G = my_tiles * J;
+      int s = 0;
+      uint32_t ph = 0;
+      int i1 = 0, i2 = 0;     // next fc1 / fc2 chunk (global over this pair's tiles)
+      const uint32_t xaddr = smem_u32(sX);
+      auto wait_warp = [&](uint64_t* bar, uint32_t parity) { mbar_wait_cluster(bar, parity); __syncwarp(); };
+      TR_INIT
+      DBG_INIT
+      auto fc1 = [&](int g) {
+        const int j = g % J;
+        TR(6)
+        if (j == 0) wait_warp(&ctrl->x_full, (uint32_t)(g / J) & 1u);   // both CTAs' X tiles have landed
+        TR(0)
+        const uint32_t buf = (uint32_t)g & 1u, use = (uint32_t)g >> 1;
+        wait_warp(&ctrl->acc1_empty[buf], (use & 1u) ^ 1u);
+        TR(1)
+        wait_warp(&ctrl->w_full[s], ph);
+        TR(2)
+        tc_fence_after();
+        const uint32_t d = tmem_base + kPairAcc1Col + buf * kPairHC;
+        const uint32_t wbase = smem_u32(sW + (size_t)s * kPairSlotBytes);
+#pragma unroll
+        for (int kb = 0; kb < kPairKb; ++kb) {
+          const uint64_t da = make_kmajor_desc<128>(xaddr + (uint32_t)kb * kXBlockBytes);
+          const uint64_t db = make_kmajor_desc<128>(wbase + (uint32_t)kb * kPairW1KbBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            if (!DBG(1)) umma_bf16_ss_warp_2sm(d, da + 2ull * k, db + 2ull * k, idesc1, (uint32_t)((kb | k) != 0));
+        }
+        umma_commit_warp_2sm(&ctrl->w_empty[s]);
+        if (++s == kPairSlots) { s = 0; ph ^= 1u; }
+        umma_commit_warp_2sm(&ctrl->acc1_full[buf]);
+        if (j == J - 1) umma_commit_warp_2sm(&ctrl->x_empty);   // the X tiles are free once the last fc1 of the tile retires
+      };
+      auto fc2 = [&](int g) {
+        const int j = g % J;
+        const uint32_t tile_it = (uint32_t)(g / J);
+        const uint32_t hb = (uint32_t)g & 1u, use = (uint32_t)g >> 1;
+        TR(3)
+        wait_warp(&ctrl->hid_full[hb], use & 1u);
+        if (j == 0) wait_warp(&ctrl->acc2_empty, (tile_it & 1u) ^ 1u);
+        TR(4)
+        wait_warp(&ctrl->w_full[s], ph);
+        TR(5)
+        tc_fence_after();
+        const uint64_t da = make_kmajor_desc<128>(smem_u32(sH + (size_t)hb * kPairHidBytes));
+        const uint32_t wbase = smem_u32(sW + (size_t)s * kPairSlotBytes);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint64_t db = make_kmajor_desc<128>(wbase + (uint32_t)q * kPairW2PartBytes);
+          const uint32_t d = tmem_base + (uint32_t)(q * kPairN2);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            if (!DBG(2)) umma_bf16_ss_warp_2sm(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | k) != 0));
+        }
+        umma_commit_warp_2sm(&ctrl->w_empty[s]);
+        if (++s == kPairSlots) { s = 0; ph ^= 1u; }
+        umma_commit_warp_2sm(&ctrl->hid_empty[hb]);
+        if (j == J - 1) umma_commit_warp_2sm(&ctrl->acc2_full);
+      };
+      while (i2 < G) {
+        // fc1 runs one chunk ahead of fc2 (two accumulators); a single X buffer: never run ahead into the next tile
+        while (i1 < G && i1 < i2 + 2 && i1 / J == i2 / J) fc1(i1++);
+        fc2(i2++);
+      }
+      TR(6)
+      TR_FLUSH
+    } else {
+      // peer CTA: forward hid_full (all 16 local epilogue warps have written their part of H_g) to the leader
+      const uint32_t dst[2] = {leader(&ctrl->hid_full[0]), leader(&ctrl->hid_full[1])};
+      const int G = my_tiles * J;
+      for (int g = 0; g < G; ++g) {
+        mbar_wait(&ctrl->hid_full[g & 1], ((uint32_t)g >> 1) & 1u, 70);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(dst[g & 1]);
+      }
+    }
+  } else if (warp == 3) {
+    if (rank == 1) {
+      // peer CTA: forward acc1_empty (per chunk) and acc2_empty (per tile) to the leader
+      const uint32_t dst1[2] = {leader(&ctrl->acc1_empty[0]), leader(&ctrl->acc1_empty[1])};
+      const uint32_t dst2 = leader(&ctrl->acc2_empty);
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int j = 0; j < J; ++j) {
+          const uint32_t g = (uint32_t)(it * J + j);
+          mbar_wait(&ctrl->acc1_empty[g & 1u], (g >> 1) & 1u, 71);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(dst1[g & 1u]);
+        }
+        mbar_wait(&ctrl->acc2_empty, (uint32_t)it & 1u, 72);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(dst2);
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ---------------- epilogue warps (both CTAs, on their own 128 rows) ----------------
+    const int q = warp & 3;                        // TMEM lane quarter
+    const int e = (warp - kFirstEpiWarp) >> 2;     // 0..3
+    constexpr int HCW = kPairHC / 4;               // 16 hidden columns per warp and chunk
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int rloc = q * 32 + lane;                // row inside this CTA's tile == TMEM lane
+    float2 nst[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
+    auto load_stats = [&](int it) {
+      const int r = row0_of(it) + rloc;
+      if (r < p.R) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (long long)r * p.ln_parts;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < p.ln_parts) nst[k] = __ldg(st + k);
+      }
+    };
+    if (p.ln_stats && my_tiles > 0) load_stats(0);
+    // Epilogue constants of this warp's 16 hidden columns of a chunk, one register per lane: lanes 0..15 hold colsum(W1') of column
+    // (lane), lanes 16..31 hold b1 of column (lane - 16); one coalesced load per chunk, requested a whole chunk ahead (there is no
+    // shared memory left for a constants page, and an L1 miss in the chunk's critical path costs more than 32 shuffles).
+    auto load_consts = [&](int j) {
+      const int col = j * kPairHC + e * HCW + (lane & 15);
+      return lane < 16 ? (p.cs1 ? __ldg(p.cs1 + col) : 0.f) : __ldg(p.b1 + col);
+    };
+    float cnext = my_tiles > 0 ? load_consts(0) : 0.f;
+    TR_INIT
+    for (int it = 0; it < my_tiles; ++it) {
+      const int row = row0_of(it) + rloc;
+      const bool rok = row < p.R;
+      float own_r = 1.f, own_n = 0.f;
+      if (p.ln_stats) {
+        const float s1 = (nst[0].x + nst[1].x) + (nst[2].x + nst[3].x), s2 = (nst[0].y + nst[1].y) + (nst[2].y + nst[3].y);
+        const float mu = s1 * p.ln_inv_k;
+        const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mu * mu), 0.f);
+        own_r = rsqrtf(var + p.ln_eps);
+        own_n = -own_r * mu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
+        if (it + 1 < my_tiles) load_stats(it + 1);
+      }
+      const float2 r2 = make_float2(own_r, own_r), n2v = make_float2(own_n, own_n);
+      for (int j = 0; j < J; ++j) {
+        const uint32_t g = (uint32_t)(it * J + j);
+        const uint32_t buf = g & 1u, use1 = g >> 1;
+        const uint32_t hb = g & 1u, useh = g >> 1;
+        const float ccur = cnext;
+        cnext = load_consts(j + 1 < J ? j + 1 : 0);
+        TR(3)
+        mbar_wait(&ctrl->acc1_full[buf], use1 & 1u, 60);
+        TR(0)
+        tc_fence_after();
+        uint32_t v[HCW];
+        tmem_ld_x16(lane_addr + kPairAcc1Col + buf * kPairHC + (uint32_t)(e * HCW), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->acc1_empty[buf]);   // accumulator drained (own CTA's barrier; the peer's is forwarded)
+        uint32_t pk[HCW / 2];
+#pragma unroll
+        for (int i = 0; i < HCW / 2; ++i) {
+          const float2 cs = make_float2(__shfl_sync(0xffffffffu, ccur, 2 * i), __shfl_sync(0xffffffffu, ccur, 2 * i + 1));
+          const float2 bb = make_float2(__shfl_sync(0xffffffffu, ccur, 16 + 2 * i), __shfl_sync(0xffffffffu, ccur, 17 + 2 * i));
+          float2 a = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          a = ffma2(r2, a, ffma2(n2v, cs, bb));
+          a = gelu_fast2(a);
+          pk[i] = pack_bf16x2(a.x, a.y);
+        }
+        TR(1)
+        mbar_wait(&ctrl->hid_empty[hb], (useh & 1u) ^ 1u, 61);   // the fc2 that last read this buffer has retired
+        TR(2)
+        uint8_t* hrow = sH + (size_t)hb * kPairHidBytes + (size_t)rloc * 128;
+#pragma unroll
+        for (int i = 0; i < HCW / 8; ++i) {
+          const int ch = ((e * HCW) >> 3) + i;
+          *reinterpret_cast<uint4*>(hrow + ((ch ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->hid_full[hb]);
+      }
+      // ---- output epilogue of this tile: acc2 + b2 + residual -> out ----
+      {
+        TR(3)
+        bool waited = false;
+        for (int c0 = e * 32; c0 < kPairC; c0 += 128) {
+          uint4 res[4];
+          if (rok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (long long)row * kPairC + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) res[i] = rp[i];   // plain loads: resid may alias out
+          }
+          float4 b2v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b2v[i] = __ldg(reinterpret_cast<const float4*>(p.b2 + c0) + i);
+          if (!waited) {
+            mbar_wait(&ctrl->acc2_full, (uint32_t)it & 1u, 62);
+            tc_fence_after();
+            waited = true;
+          }
+          uint32_t v[32];
+          tmem_ld_x32(lane_addr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (rok) {
+            uint4 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b0 = b2v[2 * i], b1 = b2v[2 * i + 1];
+              const float2 r0 = unpack_bf16x2(res[i].x), r1 = unpack_bf16x2(res[i].y), r2_ = unpack_bf16x2(res[i].z), r3 = unpack_bf16x2(res[i].w);
+              o[i].x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + b0.x + r0.x, __uint_as_float(v[8 * i + 1]) + b0.y + r0.y);
+              o[i].y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + b0.z + r1.x, __uint_as_float(v[8 * i + 3]) + b0.w + r1.y);
+              o[i].z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + b1.x + r2_.x, __uint_as_float(v[8 * i + 5]) + b1.y + r2_.y);
+              o[i].w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + b1.z + r3.x, __uint_as_float(v[8 * i + 7]) + b1.w + r3.y);
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + (long long)row * kPairC + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = o[i];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->acc2_empty);
+        TR(4)
+      }
+    }
+#ifdef LMV_MLP_TRACE
+    if (warp == kFirstEpiWarp && rank == 0) { tr[7] = (unsigned long long)(clock64() - tr_t0); if (lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_mlp_trace[(size_t)(blockIdx.x + 1) * 8 + i_] += tr[i_]; }
+#endif
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer may still be signalling this CTA's barriers / reading its shared memory
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
 PerDeviceOnce g_attr_once;
 
 }  // namespace
@@ -434,9 +814,8 @@ static int mlp_hc(int C) { return C <= 256 ? 128 : 64; }
 bool mlp_fused_supported(int C, int Hd) {
   // acc2 [128 x C] + two acc1 buffers must fit the 512 TMEM columns; the X tile, two hidden buffers and both weight rings
   // must fit 227 KB of shared memory (C = 384: 96 KB X tile, 14 KB constants at Hd = 1536)
-  static const int wide = [] { const char* e = getenv("LMV_MLP_WIDE"); return e ? atoi(e) : 1; }();
   const bool narrow = C >= 32 && C <= 192 && C % 32 == 0;
-  const bool wide_ok = wide && C == 384 && Hd <= 1536;
+  const bool wide_ok = C == 384 && Hd <= 1536;
   return (narrow || wide_ok) && Hd % 128 == 0 && Hd >= 128 && Hd <= 4096;
 }
 
@@ -457,6 +836,41 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
   const int HC = mlp_hc(a.C);
   const int kHidBytes = BM * HC * 2, kW1KbBytes = HC * BK * 2;
   p.hc = HC;
+  // LMV_MLP_PAIR=1 selects the CTA-pair kernel for the wide shape (read per call: schedules are built once, tests switch it)
+  const char* pair_env = getenv("LMV_MLP_PAIR");
+  p.pair = (HC == 64 && a.C == kPairC && pair_env && atoi(pair_env) != 0) ? 1 : 0;
+  if (p.pair) {
+    // CTA-pair kernel: 256 rows per cluster, each CTA loads half of every weight box
+    p.tiles = (a.R + 2 * BM - 1) / (2 * BM);
+    p.kb1 = kPairKb; p.chunks = a.Hd / kPairHC; p.nparts2 = 2; p.n2 = kPairN2; p.slot2_bytes = 0; p.const_bytes = 0;
+    p.nx = 1; p.nh = 2; p.n1slots = kPairSlots; p.n2slots = 0; p.w1_kpb = kPairKb; p.w1_boxes = 1; p.res_smem = 0;
+    op->smem_bytes = kPairSmemBytes;
+    p.b1 = a.b1; p.cs1 = a.cs1; p.b2 = a.b2;
+    p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1; p.ln_eps = a.ln_eps; p.ln_inv_k = 1.0f / (float)a.C;
+    p.resid = a.resid ? a.resid : a.x;
+    p.out = a.out;
+    op->grid = 2 * std::min(p.tiles, device_sm_count() / 2);
+    int rc;
+    {
+      uint64_t dims[2] = {(uint64_t)a.C, (uint64_t)a.R};
+      uint64_t strides[1] = {(uint64_t)a.C * 2};
+      uint32_t box[2] = {BK, BM};
+      if ((rc = encode_tmap_bf16(&op->tmX, a.x, 2, dims, strides, box, 128))) return rc;
+    }
+    {   // (k inside a K-block, hidden row, K-block): this CTA's 32 hidden rows of all six K-blocks in one box
+      uint64_t dims[3] = {(uint64_t)BK, (uint64_t)a.Hd, (uint64_t)kPairKb};
+      uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)BK * 2};
+      uint32_t box[3] = {BK, (uint32_t)(kPairHC / 2), (uint32_t)kPairKb};
+      if ((rc = encode_tmap_bf16(&op->tmW1, a.W1, 3, dims, strides, box, 128))) return rc;
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)a.Hd, (uint64_t)a.C};
+      uint64_t strides[1] = {(uint64_t)a.Hd * 2};
+      uint32_t box[2] = {BK, (uint32_t)(kPairN2 / 2)};
+      if ((rc = encode_tmap_bf16(&op->tmW2, a.W2, 2, dims, strides, box, 128))) return rc;
+    }
+    return LMV_OK;
+  }
   p.kb1 = (a.C + BK - 1) / BK;
   p.chunks = a.Hd / HC;
   p.nparts2 = a.C <= 256 ? 1 : 2;
@@ -528,12 +942,24 @@ int mlp_fused_run(const MlpOp& op, cudaStream_t stream) {
   LMV_CUDA_OK(g_attr_once.run([] {
     const cudaError_t e0 = cudaFuncSetAttribute(mlp_fused_tcgen05<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     const cudaError_t e1 = cudaFuncSetAttribute(mlp_fused_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    return e0 != cudaSuccess ? e0 : e1;
+    const cudaError_t e2 = cudaFuncSetAttribute(mlp_pair_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    return e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
   }));
-  auto fn = op.p.hc == 128 ? mlp_fused_tcgen05<128> : mlp_fused_tcgen05<64>;
+  auto fn = op.p.pair ? mlp_pair_tcgen05 : (op.p.hc == 128 ? mlp_fused_tcgen05<128> : mlp_fused_tcgen05<64>);
   LMV_CUDA_OK(launch_kernel(fn, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmX, op.tmW1, op.tmW2, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }
 
 }  // namespace lmv
+
+#ifdef LMV_MLP_TRACE
+extern "C" int lmv_debug_mlp_flags(int flags) { return cudaMemcpyToSymbol(lmv::g_mlp_debug, &flags, sizeof(int)) != cudaSuccess; }
+extern "C" int lmv_debug_mlp_trace(unsigned long long* host, int n) {
+  static unsigned long long zero[148 * 8];
+  if (n > 148 * 8) n = 148 * 8;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(host, lmv::g_mlp_trace, sizeof(unsigned long long) * n) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(lmv::g_mlp_trace, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif
