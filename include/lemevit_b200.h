@@ -74,8 +74,9 @@ void lmv_plan_destroy(lmv_plan* plan);
 int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
 /* schedule options (A/B switches; every schedule is rebuilt afterwards).  Known names:
  *   "fused_mlp" (default 1): run `x + mlp(norm2(x))` as ONE kernel (lmv_mlp_fused) where the shape allows it;
- *   "fused_mlp_wide" (default 0): also the C = 384 MLP of the stage-3 'S' blocks (64-column hidden chunks; with LMV_MLP_PAIR=1 in the
- *       environment the cta_group::2 CTA-pair kernel) — correct and tested, but not faster than the two GEMMs yet;
+ *   "fused_mlp_wide" (default 1; LMV_FUSED_MLP_WIDE in the environment overrides the default): also the C = 384 MLP of the stage-3
+ *       'S' blocks — on the cta_group::2 CTA-pair kernel (two CTAs of a cluster share M = 256 MMAs and each loads half of every
+ *       weight box), or with LMV_MLP_PAIR=0 on the single-CTA wide kernel;
  *   "direct_stem" (default 1): first stem convolution as a direct kernel (lmv_stem_conv1) instead of im2col + GEMM;
  *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self);
  *   "fused_dca" (default 1): 'C' / 'D' blocks through the fused cross-attention kernels (lmv_dca_block) where the shape allows it;

@@ -162,7 +162,9 @@ struct lmv_plan {
   int chunk = 0;
   int debug_simt = 0;
   int fused_mlp = 1;
-  int fused_mlp_wide = 0;   // also fuse the C = 384 MLP of the 'S' blocks (measured: 175 us against 168 us for the two GEMMs — DESIGN.md §4)
+  // also fuse the C = 384 MLP of the 'S' blocks (LMV_FUSED_MLP_WIDE in the environment overrides the default; with LMV_MLP_PAIR=1 the
+  // cta_group::2 CTA-pair kernel runs it — DESIGN.md §4)
+  int fused_mlp_wide = [] { const char* e = getenv("LMV_FUSED_MLP_WIDE"); return e ? atoi(e) : 1; }();
   int fused_self_attn = 1;
   int fused_dca = 1;
   int dca_pipe = 0;      // pipelined schedule of the fused cross-attention kernel: measured 5-10 % SLOWER than one tile at a time

@@ -428,37 +428,47 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
 // ------------------------------------------------------------------------------------------------
 // Pair variant of the wide MLP (C = 384): two CTAs of a cluster (one TPC) work on 256 rows with cta_group::2 MMAs (M = 256).
-// Each CTA keeps ITS 128 rows of X, of the hidden tiles and of both accumulators, but only HALF of every weight box (the B
-// operand of a pair MMA is split along N: rank r holds rows [r N/2, (r+1) N/2)), so the same 96 KB ring holds two hidden chunks
-// of lookahead instead of one and the L2 -> SM weight traffic per row halves — the single-CTA wide variant is bound by the bytes
-// it can keep in flight (~2k cycles of L2 latency under load x 48 B/clk needed).
+// Each CTA keeps ITS 128 rows of X, of the hidden tile and of both accumulators, but only HALF of every weight box (the B operand
+// of a pair MMA is split along N: rank r holds rows [r N/2, (r+1) N/2)), so the L2 -> SM weight traffic per row halves and the
+// ring holds a whole 128-column hidden chunk per slot — the single-CTA wide variant is bound by the weight bytes it can keep in
+// flight (~2k cycles of L2 latency under load against the 48 B/clk it needs).
+//   TMEM             acc2 [0, 384), ONE fc1 accumulator [384, 512): hidden chunks of 128 columns.  The epilogue drains acc1 into
+//                    registers right away, so fc1(g+1) only waits for that drain, and the pipe runs fc2(g-1) meanwhile:
+//                    issue order fc1(0), { fc1(g+1), fc2(g) }.  Chunks of 64 with two accumulators were measured slower: every
+//                    chunk costs ~2.7k cycles of hand-shakes across the pair regardless of its width.  Handing the hidden tile
+//                    to fc2 in two 64-column halves was slower too (the single hidden buffer has to wait for fc2(g-1) anyway).
 //   leader (rank 0)  warp 2 issues every MMA; its mbarriers collect the TMA bytes of both CTAs (x_full, w_full), the arrivals of
 //                    its own epilogue warps and ONE forwarded arrival per event from the peer (acc1_empty, hid_full, acc2_empty)
 //   both CTAs        producers load their halves (completing on the leader's barriers), epilogue warps work on their own rows
 //                    and only ever arrive on their OWN CTA's barriers; tcgen05.commit multicasts to the barrier at the same
 //                    offset in both CTAs (w_empty, x_empty, acc1_full, hid_empty, acc2_full)
 //   peer (rank 1)    warps 2 and 3 forward "all 16 epilogue warps have arrived" to the leader's barrier: a cluster-scope
-//                    release arrive costs the issuing warp ~700 cycles, twice per 64-column chunk in every epilogue warp when
-//                    they signalled the leader directly (measured: the epilogue, not the tensor pipe, set the pace)
-// Ring slot (24 KB per CTA): W1'(j) = one 3-D box [6 K-blocks][32 hidden rows][64]; W2(j) = two boxes [96 out rows][64 hidden].
+//                    release arrive costs the issuing warp ~700 cycles — twice per chunk in every epilogue warp when they
+//                    signalled the leader directly (measured: the epilogue, not the tensor pipe, set the pace)
+// Ring slot (48 KB per CTA): W1'(j) = one 3-D box [6 K-blocks][64 hidden rows][64]; W2(j) = four boxes [96 out rows][64 hidden]
+// ([hidden K-block][output half]).
 // ------------------------------------------------------------------------------------------------
-constexpr int kPairHC = 64;                     // hidden columns per chunk
+constexpr int kPairHC = 128;                    // hidden columns per chunk
 constexpr int kPairC = 384;
 constexpr int kPairKb = kPairC / BK;            // 6 K-blocks of X
 constexpr int kPairXBytes = kPairKb * kXBlockBytes;   // 96 KB
-constexpr int kPairHidBytes = BM * kPairHC * 2;       // 16 KB
-constexpr int kPairSlotBytes = 24 * 1024;
-constexpr int kPairSlots = 4;
-constexpr int kPairW1KbBytes = (kPairHC / 2) * BK * 2;   // 4 KB: this CTA's 32 hidden rows of one K-block
+constexpr int kPairHidBytes = BM * kPairHC * 2;       // 32 KB (two K-blocks), single buffer
+constexpr int kPairSlotBytes = 48 * 1024;
+constexpr int kPairSlots = 2;
+constexpr int kPairW1KbBytes = (kPairHC / 2) * BK * 2;   // 8 KB: this CTA's 64 hidden rows of one K-block
 constexpr int kPairN2 = kPairC / 2;             // fc2 in two N = 192 halves
-constexpr int kPairW2PartBytes = (kPairN2 / 2) * BK * 2;   // 12 KB: this CTA's 96 out rows of one half
+constexpr int kPairW2PartBytes = (kPairN2 / 2) * BK * 2;   // 12 KB: this CTA's 96 out rows of one half, one hidden K-block
 constexpr int kPairAcc1Col = 384;
-constexpr int kPairSmemBytes = 1024 + 1023 + kPairXBytes + 2 * kPairHidBytes + kPairSlots * kPairSlotBytes;
-static_assert(kPairSmemBytes <= kSmemLimit, "pair MLP shared memory");
-static_assert(kPairKb * kPairW1KbBytes == kPairSlotBytes && 2 * kPairW2PartBytes == kPairSlotBytes, "ring slot layout");
+// [alignment pad <= 1023][ctrl 1 KB][X][H][ring][constants page 2 KB — only addressable when the pad is 0, see the epilogue]
+constexpr int kPairConstBytes = 2 * kPairHC * 8;   // two buffers of (colsum, b1) per hidden column of a chunk
+constexpr int kPairSmemBytes = 1024 + kPairXBytes + kPairHidBytes + kPairSlots * kPairSlotBytes + kPairConstBytes;
+static_assert(kPairSmemBytes <= kSmemLimit && kPairSmemBytes - kPairConstBytes + 1023 <= kSmemLimit, "pair MLP shared memory");
+static_assert(kPairKb * kPairW1KbBytes == kPairSlotBytes && 4 * kPairW2PartBytes == kPairSlotBytes, "ring slot layout");
 
-// Debug build (-DLMV_MLP_TRACE): cycle account of the pair kernel's MMA issuer (leader CTAs), read back with lmv_debug_mlp_trace().
-// slots: 0 wait x_full, 1 wait acc1_empty, 2 wait w_full (fc1), 3 issue fc1, 4 wait hid_full (+ acc2_empty), 5 wait w_full (fc2), 6 issue fc2, 7 total
+// Debug build (-DLMV_MLP_TRACE): cycle account of the pair kernel's MMA issuer (leader CTAs) and of one epilogue warp, read back
+// with lmv_debug_mlp_trace().
+// issuer slots:   0 wait x_full, 1 wait acc1_empty, 2 wait w_full (fc1), 3 issue fc1, 4 wait hid_full (+ acc2_empty), 5 wait w_full (fc2), 6 issue fc2, 7 total
+// epilogue slots: 0 wait acc1_full, 1 ld + math, 2 wait hid_empty, 3 stores + arrive (+ loop), 4 output epilogue, 7 total
 #ifdef LMV_MLP_TRACE
 __device__ unsigned long long g_mlp_trace[148 * 8];
 __device__ int g_mlp_debug;   // timing experiments (lmv_debug_mlp_flags; results become wrong): 1 skip the fc1 MMAs, 2 skip the fc2 MMAs
@@ -478,8 +488,8 @@ __device__ int g_mlp_debug;   // timing experiments (lmv_debug_mlp_flags; result
 struct CtrlPair {
   uint64_t x_full, x_empty;
   uint64_t w_full[kPairSlots], w_empty[kPairSlots];
-  uint64_t acc1_full[2], acc1_empty[2];
-  uint64_t hid_full[2], hid_empty[2];
+  uint64_t acc1_full, acc1_empty;
+  uint64_t hid_full, hid_empty;
   uint64_t acc2_full, acc2_empty;
   uint32_t tmem_base;
 };
@@ -493,31 +503,36 @@ mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   CtrlPair* ctrl = reinterpret_cast<CtrlPair*>(smem);
   uint8_t* sX = smem + 1024;
   uint8_t* sH = sX + kPairXBytes;
-  uint8_t* sW = sH + 2 * kPairHidBytes;
+  uint8_t* sW = sH + kPairHidBytes;
+  // The last 2 KB of the allocation hold the epilogue constants of the current and the next hidden chunk — but only when the
+  // dynamic shared memory happens to start 1024-aligned (pad == 0: it does on every driver seen so far); otherwise those bytes are
+  // the alignment pad and the epilogue broadcasts its constants with shuffles instead.
+  float2* sConst = reinterpret_cast<float2*>(sW + kPairSlots * kPairSlotBytes);
+  const bool const_page = pad == 0;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int J = p.chunks;
   const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
   const int my_tiles = (pair < p.tiles) ? (p.tiles - 1 - pair) / npairs + 1 : 0;   // p.tiles counts 256-row pair tiles
+  const int G = my_tiles * J;                                                      // hidden chunks of this pair
   auto row0_of = [&](int it) { return ((pair + it * npairs) * 2 + (int)rank) * BM; };
   auto leader = [&](uint64_t* bar) { return mapa_u32(smem_u32(bar), 0u); };   // the leader's copy of a barrier
 
   if (threadIdx.x == 0) {
+    const uint32_t nepi = kEpiWarps + (rank == 0 ? 1 : 0);   // own epilogue warps (+ the peer's forwarder on the leader)
     mbar_init(&ctrl->x_full, 1);
     mbar_init(&ctrl->x_empty, 1);
     for (int i = 0; i < kPairSlots; ++i) {
       mbar_init(&ctrl->w_full[i], 1);
       mbar_init(&ctrl->w_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&ctrl->acc1_full[i], 1);
-      mbar_init(&ctrl->acc1_empty[i], kEpiWarps + (rank == 0 ? 1 : 0));   // own epilogue warps (+ the peer's forwarder on the leader)
-      mbar_init(&ctrl->hid_full[i], kEpiWarps + (rank == 0 ? 1 : 0));
-      mbar_init(&ctrl->hid_empty[i], 1);
-    }
+    mbar_init(&ctrl->acc1_full, 1);
+    mbar_init(&ctrl->acc1_empty, nepi);
+    mbar_init(&ctrl->hid_full, nepi);
+    mbar_init(&ctrl->hid_empty, 1);
     mbar_init(&ctrl->acc2_full, 1);
-    mbar_init(&ctrl->acc2_empty, kEpiWarps + (rank == 0 ? 1 : 0));
+    mbar_init(&ctrl->acc2_empty, nepi);
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
@@ -560,26 +575,26 @@ mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(&ctrl->w_empty[slot], wphase ^ 1u, 42);
         if (rank == 0) mbar_expect_tx(&ctrl->w_full[slot], 2u * kPairSlotBytes);
         const uint32_t bar = leader(&ctrl->w_full[slot]);
-        for (int q = 0; q < 2; ++q)
-          tma_load_2d_2sm(sW + (size_t)slot * kPairSlotBytes + (size_t)q * kPairW2PartBytes, &tmW2, bar, j * kPairHC, q * kPairN2 + (int)rank * (kPairN2 / 2));
+        for (int kb = 0; kb < kPairHC / BK; ++kb)
+          for (int q = 0; q < 2; ++q)
+            tma_load_2d_2sm(sW + (size_t)slot * kPairSlotBytes + (size_t)(kb * 2 + q) * kPairW2PartBytes, &tmW2, bar, j * kPairHC + kb * BK,
+                            q * kPairN2 + (int)rank * (kPairN2 / 2));
         next();
       };
-      for (int it = 0; it < my_tiles; ++it) {
+      for (int it = 0; it < my_tiles; ++it) {   // W1'(0), W1'(1), W2(0), W1'(2), W2(1), ..., W2(J-1)
         put_w1(0);
         for (int j = 1; j < J; ++j) { put_w1(j); put_w2(j - 1); }
         put_w2(J - 1);
       }
     }
   } else if (warp == 2) {
-    // ---------------- MMA issuer (leader CTA only): whole warp in uniform control flow, one elected lane issues ----------------
     if (rank == 0) {
+      // ---------------- MMA issuer (leader CTA only): whole warp in uniform control flow, one elected lane issues ----------------
       const uint32_t idesc1 = make_idesc_bf16(2 * BM, kPairHC);
       const uint32_t idesc2 = make_idesc_bf16(2 * BM, kPairN2);
-      const int G = my_tiles * J;
       int s = 0;
       uint32_t ph = 0;
-      int i1 = 0, i2 = 0;     // next fc1 / fc2 chunk (global over this pair's tiles)
-      const uint32_t xaddr = smem_u32(sX);
+      const uint32_t xaddr = smem_u32(sX), haddr = smem_u32(sH);
       auto wait_warp = [&](uint64_t* bar, uint32_t parity) { mbar_wait_cluster(bar, parity); __syncwarp(); };
       TR_INIT
       DBG_INIT
@@ -588,13 +603,12 @@ mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         TR(6)
         if (j == 0) wait_warp(&ctrl->x_full, (uint32_t)(g / J) & 1u);   // both CTAs' X tiles have landed
         TR(0)
-        const uint32_t buf = (uint32_t)g & 1u, use = (uint32_t)g >> 1;
-        wait_warp(&ctrl->acc1_empty[buf], (use & 1u) ^ 1u);
+        wait_warp(&ctrl->acc1_empty, ((uint32_t)g & 1u) ^ 1u);          // both CTAs' epilogues have drained acc1(g-1)
         TR(1)
         wait_warp(&ctrl->w_full[s], ph);
         TR(2)
         tc_fence_after();
-        const uint32_t d = tmem_base + kPairAcc1Col + buf * kPairHC;
+        const uint32_t d = tmem_base + kPairAcc1Col;
         const uint32_t wbase = smem_u32(sW + (size_t)s * kPairSlotBytes);
 #pragma unroll
         for (int kb = 0; kb < kPairKb; ++kb) {
@@ -606,74 +620,74 @@ mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         umma_commit_warp_2sm(&ctrl->w_empty[s]);
         if (++s == kPairSlots) { s = 0; ph ^= 1u; }
-        umma_commit_warp_2sm(&ctrl->acc1_full[buf]);
+        umma_commit_warp_2sm(&ctrl->acc1_full);
         if (j == J - 1) umma_commit_warp_2sm(&ctrl->x_empty);   // the X tiles are free once the last fc1 of the tile retires
       };
       auto fc2 = [&](int g) {
         const int j = g % J;
-        const uint32_t tile_it = (uint32_t)(g / J);
-        const uint32_t hb = (uint32_t)g & 1u, use = (uint32_t)g >> 1;
         TR(3)
-        wait_warp(&ctrl->hid_full[hb], use & 1u);
-        if (j == 0) wait_warp(&ctrl->acc2_empty, (tile_it & 1u) ^ 1u);
+        wait_warp(&ctrl->hid_full, (uint32_t)g & 1u);
+        if (j == 0) wait_warp(&ctrl->acc2_empty, ((uint32_t)(g / J) & 1u) ^ 1u);
         TR(4)
         wait_warp(&ctrl->w_full[s], ph);
         TR(5)
         tc_fence_after();
-        const uint64_t da = make_kmajor_desc<128>(smem_u32(sH + (size_t)hb * kPairHidBytes));
         const uint32_t wbase = smem_u32(sW + (size_t)s * kPairSlotBytes);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint64_t db = make_kmajor_desc<128>(wbase + (uint32_t)q * kPairW2PartBytes);
-          const uint32_t d = tmem_base + (uint32_t)(q * kPairN2);
+        for (int kb = 0; kb < kPairHC / BK; ++kb) {
+          const uint64_t da = make_kmajor_desc<128>(haddr + (uint32_t)kb * kXBlockBytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            if (!DBG(2)) umma_bf16_ss_warp_2sm(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | k) != 0));
+          for (int q = 0; q < 2; ++q) {
+            const uint64_t db = make_kmajor_desc<128>(wbase + (uint32_t)(kb * 2 + q) * kPairW2PartBytes);
+            const uint32_t d = tmem_base + (uint32_t)(q * kPairN2);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              if (!DBG(2)) umma_bf16_ss_warp_2sm(d, da + 2ull * k, db + 2ull * k, idesc2, (uint32_t)((j | kb | k) != 0));
+          }
         }
         umma_commit_warp_2sm(&ctrl->w_empty[s]);
         if (++s == kPairSlots) { s = 0; ph ^= 1u; }
-        umma_commit_warp_2sm(&ctrl->hid_empty[hb]);
+        umma_commit_warp_2sm(&ctrl->hid_empty);
         if (j == J - 1) umma_commit_warp_2sm(&ctrl->acc2_full);
       };
-      while (i2 < G) {
-        // fc1 runs one chunk ahead of fc2 (two accumulators); a single X buffer: never run ahead into the next tile
-        while (i1 < G && i1 < i2 + 2 && i1 / J == i2 / J) fc1(i1++);
-        fc2(i2++);
+      // fc1 runs one chunk ahead of fc2 inside a tile (the ring's order); a single X buffer: never run ahead into the next tile
+      for (int g = 0; g < G; ++g) {
+        if (g % J == 0) fc1(g);
+        if ((g + 1) % J != 0) fc1(g + 1);
+        fc2(g);
       }
       TR(6)
       TR_FLUSH
     } else {
       // peer CTA: forward hid_full (all 16 local epilogue warps have written their part of H_g) to the leader
-      const uint32_t dst[2] = {leader(&ctrl->hid_full[0]), leader(&ctrl->hid_full[1])};
-      const int G = my_tiles * J;
+      const uint32_t dst = leader(&ctrl->hid_full);
       for (int g = 0; g < G; ++g) {
-        mbar_wait(&ctrl->hid_full[g & 1], ((uint32_t)g >> 1) & 1u, 70);
+        mbar_wait(&ctrl->hid_full, (uint32_t)g & 1u, 70);
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(dst[g & 1]);
+        if (lane == 0) mbar_arrive_cluster(dst);
       }
     }
   } else if (warp == 3) {
     if (rank == 1) {
-      // peer CTA: forward acc1_empty (per chunk) and acc2_empty (per tile) to the leader
-      const uint32_t dst1[2] = {leader(&ctrl->acc1_empty[0]), leader(&ctrl->acc1_empty[1])};
-      const uint32_t dst2 = leader(&ctrl->acc2_empty);
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int j = 0; j < J; ++j) {
-          const uint32_t g = (uint32_t)(it * J + j);
-          mbar_wait(&ctrl->acc1_empty[g & 1u], (g >> 1) & 1u, 71);
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(dst1[g & 1u]);
-        }
-        mbar_wait(&ctrl->acc2_empty, (uint32_t)it & 1u, 72);
+      // peer CTA: forward acc1_empty (per chunk) and acc2_empty (per tile) to the leader, in the order the epilogue warps arrive:
+      // the output epilogue of a tile is deferred behind the first chunk of the next one
+      const uint32_t dst1 = leader(&ctrl->acc1_empty), dst2 = leader(&ctrl->acc2_empty);
+      auto forward = [&](uint64_t* bar, uint32_t parity, uint32_t dst) {
+        mbar_wait(bar, parity, 71);
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(dst2);
-      }
+        if (lane == 0) mbar_arrive_cluster(dst);
+      };
+      for (int it = 0; it < my_tiles; ++it)
+        for (int j = 0; j < J; ++j) {
+          forward(&ctrl->acc1_empty, (uint32_t)(it * J + j) & 1u, dst1);
+          if (j == 0 && it > 0) forward(&ctrl->acc2_empty, (uint32_t)(it - 1) & 1u, dst2);
+        }
+      if (my_tiles > 0) forward(&ctrl->acc2_empty, (uint32_t)(my_tiles - 1) & 1u, dst2);
     }
   } else if (warp >= kFirstEpiWarp) {
     // ---------------- epilogue warps (both CTAs, on their own 128 rows) ----------------
     const int q = warp & 3;                        // TMEM lane quarter
-    const int e = (warp - kFirstEpiWarp) >> 2;     // 0..3
-    constexpr int HCW = kPairHC / 4;               // 16 hidden columns per warp and chunk
+    const int e = (warp - kFirstEpiWarp) >> 2;     // 0..3: this warp's 32 of the chunk's 128 hidden columns
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int rloc = q * 32 + lane;                // row inside this CTA's tile == TMEM lane
     float2 nst[4];
@@ -689,71 +703,25 @@ mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
     };
     if (p.ln_stats && my_tiles > 0) load_stats(0);
-    // Epilogue constants of this warp's 16 hidden columns of a chunk, one register per lane: lanes 0..15 hold colsum(W1') of column
-    // (lane), lanes 16..31 hold b1 of column (lane - 16); one coalesced load per chunk, requested a whole chunk ahead (there is no
-    // shared memory left for a constants page, and an L1 miss in the chunk's critical path costs more than 32 shuffles).
+    // Epilogue constants of this warp's 32 hidden columns of a chunk, one register pair per lane: (colsum(W1'), b1) of column
+    // (lane); one coalesced load per chunk, requested a whole chunk ahead.  Every warp writes them to the constants page (buffer
+    // g & 1; the four warps that share the columns write identical bytes, so nobody waits for anybody) and reads them back as
+    // broadcast 16-byte loads; without the page they are broadcast with shuffles, whose throughput (one warp per clock and SM)
+    // then limits the chunk.  Buffer reuse is safe: a warp starts chunk g+2 only after acc1_full(g+2), i.e. after fc1(g+2) was
+    // issued, i.e. after every warp drained acc1(g+1) — which it does after finishing the math of chunk g.
+    // (warp-uniform 16-byte loads through L1, even prefetched, were measured 20% slower than the shuffles.)
     auto load_consts = [&](int j) {
-      const int col = j * kPairHC + e * HCW + (lane & 15);
-      return lane < 16 ? (p.cs1 ? __ldg(p.cs1 + col) : 0.f) : __ldg(p.b1 + col);
+      const int col = j * kPairHC + e * 32 + lane;
+      return make_float2(p.cs1 ? __ldg(p.cs1 + col) : 0.f, __ldg(p.b1 + col));
     };
-    float cnext = my_tiles > 0 ? load_consts(0) : 0.f;
+    float2 cnext = my_tiles > 0 ? load_consts(0) : make_float2(0.f, 0.f);
     TR_INIT
-    for (int it = 0; it < my_tiles; ++it) {
-      const int row = row0_of(it) + rloc;
+    // ---- output epilogue of tile iteration `oit`: acc2 + b2 + residual -> out.  It runs AFTER the first hidden chunk of the next tile
+    // was handed to fc2, so the wait for the last fc2 of the tile and the output stores hide behind fc1 of the next tile.
+    auto output_epilogue = [&](int oit) {
+      const int row = row0_of(oit) + rloc;
       const bool rok = row < p.R;
-      float own_r = 1.f, own_n = 0.f;
-      if (p.ln_stats) {
-        const float s1 = (nst[0].x + nst[1].x) + (nst[2].x + nst[3].x), s2 = (nst[0].y + nst[1].y) + (nst[2].y + nst[3].y);
-        const float mu = s1 * p.ln_inv_k;
-        const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mu * mu), 0.f);
-        own_r = rsqrtf(var + p.ln_eps);
-        own_n = -own_r * mu;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
-        if (it + 1 < my_tiles) load_stats(it + 1);
-      }
-      const float2 r2 = make_float2(own_r, own_r), n2v = make_float2(own_n, own_n);
-      for (int j = 0; j < J; ++j) {
-        const uint32_t g = (uint32_t)(it * J + j);
-        const uint32_t buf = g & 1u, use1 = g >> 1;
-        const uint32_t hb = g & 1u, useh = g >> 1;
-        const float ccur = cnext;
-        cnext = load_consts(j + 1 < J ? j + 1 : 0);
-        TR(3)
-        mbar_wait(&ctrl->acc1_full[buf], use1 & 1u, 60);
-        TR(0)
-        tc_fence_after();
-        uint32_t v[HCW];
-        tmem_ld_x16(lane_addr + kPairAcc1Col + buf * kPairHC + (uint32_t)(e * HCW), v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->acc1_empty[buf]);   // accumulator drained (own CTA's barrier; the peer's is forwarded)
-        uint32_t pk[HCW / 2];
-#pragma unroll
-        for (int i = 0; i < HCW / 2; ++i) {
-          const float2 cs = make_float2(__shfl_sync(0xffffffffu, ccur, 2 * i), __shfl_sync(0xffffffffu, ccur, 2 * i + 1));
-          const float2 bb = make_float2(__shfl_sync(0xffffffffu, ccur, 16 + 2 * i), __shfl_sync(0xffffffffu, ccur, 17 + 2 * i));
-          float2 a = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-          a = ffma2(r2, a, ffma2(n2v, cs, bb));
-          a = gelu_fast2(a);
-          pk[i] = pack_bf16x2(a.x, a.y);
-        }
-        TR(1)
-        mbar_wait(&ctrl->hid_empty[hb], (useh & 1u) ^ 1u, 61);   // the fc2 that last read this buffer has retired
-        TR(2)
-        uint8_t* hrow = sH + (size_t)hb * kPairHidBytes + (size_t)rloc * 128;
-#pragma unroll
-        for (int i = 0; i < HCW / 8; ++i) {
-          const int ch = ((e * HCW) >> 3) + i;
-          *reinterpret_cast<uint4*>(hrow + ((ch ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->hid_full[hb]);
-      }
-      // ---- output epilogue of this tile: acc2 + b2 + residual -> out ----
-      {
+      const int it = oit;
         TR(3)
         bool waited = false;
         for (int c0 = e * 32; c0 < kPairC; c0 += 128) {
@@ -794,8 +762,76 @@ mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctrl->acc2_empty);
         TR(4)
+    };
+    for (int it = 0; it < my_tiles; ++it) {
+      const int row = row0_of(it) + rloc;
+      const bool rok = row < p.R;
+      float own_r = 1.f, own_n = 0.f;
+      if (p.ln_stats) {
+        const float s1 = (nst[0].x + nst[1].x) + (nst[2].x + nst[3].x), s2 = (nst[0].y + nst[1].y) + (nst[2].y + nst[3].y);
+        const float mu = s1 * p.ln_inv_k;
+        const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mu * mu), 0.f);
+        own_r = rsqrtf(var + p.ln_eps);
+        own_n = -own_r * mu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
+        if (it + 1 < my_tiles) load_stats(it + 1);
+      }
+      const float2 r2 = make_float2(own_r, own_r), n2v = make_float2(own_n, own_n);
+      for (int j = 0; j < J; ++j) {
+        const uint32_t g = (uint32_t)(it * J + j);
+        const float2 ccur = cnext;
+        cnext = load_consts(j + 1 < J ? j + 1 : 0);
+        TR(3)
+        mbar_wait(&ctrl->acc1_full, g & 1u, 60);
+        TR(0)
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_x32(lane_addr + kPairAcc1Col + (uint32_t)(e * 32), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->acc1_empty);   // accumulator drained (own CTA's barrier; the peer's is forwarded)
+        uint32_t pk[16];
+        if (const_page) {
+          float2* cpage = sConst + (g & 1u) * kPairHC + e * 32;
+          cpage[lane] = ccur;
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 c = *reinterpret_cast<const float4*>(cpage + 2 * i);   // (cs, b1) of columns 2i, 2i+1 — broadcast read
+            float2 a = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            a = ffma2(r2, a, ffma2(n2v, make_float2(c.x, c.z), make_float2(c.y, c.w)));
+            a = gelu_fast2(a);
+            pk[i] = pack_bf16x2(a.x, a.y);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 cs = make_float2(__shfl_sync(0xffffffffu, ccur.x, 2 * i), __shfl_sync(0xffffffffu, ccur.x, 2 * i + 1));
+            const float2 bb = make_float2(__shfl_sync(0xffffffffu, ccur.y, 2 * i), __shfl_sync(0xffffffffu, ccur.y, 2 * i + 1));
+            float2 a = make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            a = ffma2(r2, a, ffma2(n2v, cs, bb));
+            a = gelu_fast2(a);
+            pk[i] = pack_bf16x2(a.x, a.y);
+          }
+        }
+        TR(1)
+        mbar_wait(&ctrl->hid_empty, (g & 1u) ^ 1u, 61);   // fc2(g-1), the last reader of the hidden tile, has retired
+        TR(2)
+        uint8_t* hrow = sH + (size_t)(e >> 1) * kXBlockBytes + (size_t)rloc * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ch = (e & 1) * 4 + i;
+          *reinterpret_cast<uint4*>(hrow + ((ch ^ (rloc & 7)) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctrl->hid_full);
+        if (j == 0 && it > 0) output_epilogue(it - 1);   // deferred output epilogue of the previous tile
       }
     }
+    if (my_tiles > 0) output_epilogue(my_tiles - 1);
 #ifdef LMV_MLP_TRACE
     if (warp == kFirstEpiWarp && rank == 0) { tr[7] = (unsigned long long)(clock64() - tr_t0); if (lane == 0) for (int i_ = 0; i_ < 8; ++i_) g_mlp_trace[(size_t)(blockIdx.x + 1) * 8 + i_] += tr[i_]; }
 #endif
@@ -836,9 +872,9 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
   const int HC = mlp_hc(a.C);
   const int kHidBytes = BM * HC * 2, kW1KbBytes = HC * BK * 2;
   p.hc = HC;
-  // LMV_MLP_PAIR=1 selects the CTA-pair kernel for the wide shape (read per call: schedules are built once, tests switch it)
+  // the wide shape runs on the CTA-pair kernel unless LMV_MLP_PAIR=0 (read per call: schedules are built once, tests switch it)
   const char* pair_env = getenv("LMV_MLP_PAIR");
-  p.pair = (HC == 64 && a.C == kPairC && pair_env && atoi(pair_env) != 0) ? 1 : 0;
+  p.pair = (HC == 64 && a.C == kPairC && !(pair_env && atoi(pair_env) == 0)) ? 1 : 0;
   if (p.pair) {
     // CTA-pair kernel: 256 rows per cluster, each CTA loads half of every weight box
     p.tiles = (a.R + 2 * BM - 1) / (2 * BM);
@@ -857,7 +893,7 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
       uint32_t box[2] = {BK, BM};
       if ((rc = encode_tmap_bf16(&op->tmX, a.x, 2, dims, strides, box, 128))) return rc;
     }
-    {   // (k inside a K-block, hidden row, K-block): this CTA's 32 hidden rows of all six K-blocks in one box
+    {   // (k inside a K-block, hidden row, K-block): this CTA's 64 hidden rows of all six K-blocks in one box
       uint64_t dims[3] = {(uint64_t)BK, (uint64_t)a.Hd, (uint64_t)kPairKb};
       uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)BK * 2};
       uint32_t box[3] = {BK, (uint32_t)(kPairHC / 2), (uint32_t)kPairKb};

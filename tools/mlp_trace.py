@@ -32,7 +32,7 @@ for cta in range(0, 148, 2):
     if v[7]:
         n += 1
         tot = [a + b for a, b in zip(tot, v)]
-chunks = Hd // 64 * ((R + 255) // 256) / max(n, 1)
+chunks = Hd // 128 * ((R + 255) // 256) / max(n, 1)
 print(f"{n} issuers, {chunks:.1f} chunks each:", {nm: round(t / n / 1e3, 1) for nm, t in zip(names, tot)}, "kcycles;",
       {nm: round(t / n / chunks) for nm, t in zip(names, tot)}, "cycles per chunk")
 
