@@ -25,6 +25,7 @@ namespace lmv {
 namespace {
 
 constexpr int kD = 32;
+constexpr bool kPolyExp = true;   // every fourth pair of exponentials of the exp pass on the FMA pipe (exp2_poly2)
 constexpr int kQTile = 128;
 constexpr int kMaxKeys = 224;
 constexpr int kSCols = 224;              // TMEM columns reserved per S accumulator
@@ -66,6 +67,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+
+// 2^x for x <= 0 on the FMA / ALU pipes, two values at a time (the exp pass is MUFU-bound: every fourth pair goes here instead of
+// through ex2.approx).  Cody-Waite: n = round(x) via the 1.5 * 2^23 trick, 2^(x - n) by a cubic on [-0.5, 0.5] (max relative error
+// 2.2e-4, an eighth of the bf16 rounding P gets anyway), 2^n added straight into the exponent field.  Arguments below -126
+// (masked keys are -inf) give ~1e-38 instead of 0: 38 orders of magnitude below the row maximum's 1.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.f;
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
+  const float2 r = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 q = ffma2(r, make_float2(0.05286743491888046f, 0.05286743491888046f), make_float2(0.2421518862247467f, 0.2421518862247467f));
+  q = ffma2(q, r, make_float2(0.6935867667198181f, 0.6935867667198181f));
+  q = ffma2(q, r, make_float2(0.9999627470970154f, 0.9999627470970154f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)), __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
 
 __device__ __forceinline__ uint64_t make_mnmajor_sw64_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -418,15 +436,21 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const float2 scc = hide ? make_float2(0.f, 0.f) : sc2, nmc = hide ? make_float2(-INFINITY, -INFINITY) : nm2;
           uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
+          for (int j = 0; j < 16; j += 4) {   // eight scores: six exponentials on MUFU, one pair on the FMA pipe
             float2 a0 = ffma2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), scc, nmc);
             float2 a1 = ffma2(make_float2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), scc, nmc);
+            float2 a2 = ffma2(make_float2(__uint_as_float(v[2 * j + 4]), __uint_as_float(v[2 * j + 5])), scc, nmc);
+            float2 a3 = ffma2(make_float2(__uint_as_float(v[2 * j + 6]), __uint_as_float(v[2 * j + 7])), scc, nmc);
             a0.x = ex2_approx(a0.x); a0.y = ex2_approx(a0.y);
             a1.x = ex2_approx(a1.x); a1.y = ex2_approx(a1.y);
-            s0 = fadd2(s0, a0);
-            s1 = fadd2(s1, a1);
+            a2.x = ex2_approx(a2.x); a2.y = ex2_approx(a2.y);
+            a3 = kPolyExp ? exp2_poly2(a3) : make_float2(ex2_approx(a3.x), ex2_approx(a3.y));
+            s0 = fadd2(s0, fadd2(a0, a2));
+            s1 = fadd2(s1, fadd2(a1, a3));
             pk[j] = pack_bf16x2(a0.x, a0.y);
             pk[j + 1] = pack_bf16x2(a1.x, a1.y);
+            pk[j + 2] = pack_bf16x2(a2.x, a2.y);
+            pk[j + 3] = pack_bf16x2(a3.x, a3.y);
           }
           // P[r, c0 .. c0+31] -> tile (c0 / 64), 16-byte chunks ((c0 % 64) / 8) .. +3, XOR-swizzled with (r % 8)
           uint8_t* tile_p = pg + (size_t)(c0 >> 6) * kPTileBytes;

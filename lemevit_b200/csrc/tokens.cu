@@ -408,10 +408,13 @@ stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp]
 #pragma unroll
     for (int c = 0; c < C1 / 8; ++c) {
       uint4 u;
-      u.x = pack_bf16x2(gelu_fast(acc[q][2 * c].x), gelu_fast(acc[q][2 * c].y));
-      u.y = pack_bf16x2(gelu_fast(acc[q][2 * c].z), gelu_fast(acc[q][2 * c].w));
-      u.z = pack_bf16x2(gelu_fast(acc[q][2 * c + 1].x), gelu_fast(acc[q][2 * c + 1].y));
-      u.w = pack_bf16x2(gelu_fast(acc[q][2 * c + 1].z), gelu_fast(acc[q][2 * c + 1].w));
+      // packed GELU (FFMA2 / FMUL2 + two MUFU.TANH per pair): this kernel is issue-bound, and the activation is a third of its instructions
+      const float2 g0 = gelu_fast2(make_float2(acc[q][2 * c].x, acc[q][2 * c].y)), g1 = gelu_fast2(make_float2(acc[q][2 * c].z, acc[q][2 * c].w));
+      const float2 g2 = gelu_fast2(make_float2(acc[q][2 * c + 1].x, acc[q][2 * c + 1].y)), g3 = gelu_fast2(make_float2(acc[q][2 * c + 1].z, acc[q][2 * c + 1].w));
+      u.x = pack_bf16x2(g0.x, g0.y);
+      u.y = pack_bf16x2(g1.x, g1.y);
+      u.z = pack_bf16x2(g2.x, g2.y);
+      u.w = pack_bf16x2(g3.x, g3.y);
       dst[c] = u;
     }
   }
