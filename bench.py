@@ -86,7 +86,7 @@ def parse_args():
 # kernel class (native plan profile) -> kernel symbol in the ncu summaries under profiles/
 _CLASS_SYMBOL = {"gemm_tcgen05": "gemm_bf16_tn_tcgen05", "mlp_fused_tcgen05": "mlp_fused_tcgen05", "attention_self_tcgen05": "attention_self_kernel",
                  "attention_tcgen05": "attention_tc_kernel", "attention_meta_tcgen05": "attention_meta_kernel", "posembed_layernorm": "posembed_tile_kernel",
-                 "dca_fused_tcgen05": "dca_x_kernel", "meta_branch": "meta_chain_kernel"}
+                 "dca_fused_tcgen05": "dca_x_kernel", "meta_branch": "meta_chain_kernel", "mlp_pair_tcgen05": "mlp_pair_tcgen05"}
 
 
 def ncu_traffic(kernel_class: str):

@@ -117,9 +117,9 @@ struct StageW {
 
 typedef std::function<int(cudaStream_t)> Launch;
 
-enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_SELF, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_STEM, OP_IM2COL, OP_MISC, OP_DCA, OP_META, OP_NUM_CLASSES };
+enum OpClass { OP_GEMM = 0, OP_MLP, OP_ATTN_SELF, OP_ATTN_TC, OP_ATTN_META, OP_ATTN_SIMT, OP_POSLN, OP_LN, OP_STEM, OP_IM2COL, OP_MISC, OP_DCA, OP_META, OP_MLP_PAIR, OP_NUM_CLASSES };
 static const char* const kOpClassNames[OP_NUM_CLASSES] = {"gemm_tcgen05", "mlp_fused_tcgen05", "attention_self_tcgen05", "attention_tcgen05", "attention_meta_tcgen05", "attention_simt",
-                                                          "posembed_layernorm", "layernorm", "stem_conv_direct", "im2col", "misc", "dca_fused_tcgen05", "meta_branch"};
+                                                          "posembed_layernorm", "layernorm", "stem_conv_direct", "im2col", "misc", "dca_fused_tcgen05", "meta_branch", "mlp_pair_tcgen05"};
 struct OpRec {
   Launch fn;
   std::string desc;
@@ -492,7 +492,7 @@ struct Builder {
       if (rc) return;
       char d[120];
       snprintf(d, sizeof(d), "mlp_fused R=%d C=%d Hd=%d", R, C, Hd);
-      sc->push([op](cudaStream_t s) { return mlp_fused_run(op, s); }, OP_MLP, 4.0 * R * C * (double)Hd, 4.0 * R * C, d);
+      sc->push([op](cudaStream_t s) { return mlp_fused_run(op, s); }, op.p.pair ? OP_MLP_PAIR : OP_MLP, 4.0 * R * C * (double)Hd, 4.0 * R * C, d);
       return;
     }
     ln_linear(x, stats, parts, bw.w1, bw.b1, bw.cs1, R, Hd, C, hid, 1);

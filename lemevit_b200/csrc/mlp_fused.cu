@@ -449,21 +449,26 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 // ([hidden K-block][output half]).
 // ------------------------------------------------------------------------------------------------
 constexpr int kPairHC = 128;                    // hidden columns per chunk
-constexpr int kPairC = 384;
-constexpr int kPairKb = kPairC / BK;            // 6 K-blocks of X
-constexpr int kPairXBytes = kPairKb * kXBlockBytes;   // 96 KB
-constexpr int kPairHidBytes = BM * kPairHC * 2;       // 32 KB (two K-blocks), single buffer
-constexpr int kPairSlotBytes = 48 * 1024;
 constexpr int kPairSlots = 2;
+constexpr int kPairHidBytes = BM * kPairHC * 2;       // 32 KB (two K-blocks), single buffer
 constexpr int kPairW1KbBytes = (kPairHC / 2) * BK * 2;   // 8 KB: this CTA's 64 hidden rows of one K-block
-constexpr int kPairN2 = kPairC / 2;             // fc2 in two N = 192 halves
-constexpr int kPairW2PartBytes = (kPairN2 / 2) * BK * 2;   // 12 KB: this CTA's 96 out rows of one half, one hidden K-block
 constexpr int kPairAcc1Col = 384;
-// [alignment pad <= 1023][ctrl 1 KB][X][H][ring][constants page 2 KB — only addressable when the pad is 0, see the epilogue]
 constexpr int kPairConstBytes = 2 * kPairHC * 8;   // two buffers of (colsum, b1) per hidden column of a chunk
-constexpr int kPairSmemBytes = 1024 + kPairXBytes + kPairHidBytes + kPairSlots * kPairSlotBytes + kPairConstBytes;
-static_assert(kPairSmemBytes <= kSmemLimit && kPairSmemBytes - kPairConstBytes + 1023 <= kSmemLimit, "pair MLP shared memory");
-static_assert(kPairKb * kPairW1KbBytes == kPairSlotBytes && 4 * kPairW2PartBytes == kPairSlotBytes, "ring slot layout");
+// shapes that depend on the channel count C (384: stage 3 of Base, stage 4 of Small; 320: stage 3 of Small, stage 4 of Tiny)
+template <int C>
+struct PairShape {
+  static constexpr int kKb = C / BK;                        // K-blocks of X
+  static constexpr int kXBytes = kKb * kXBlockBytes;        // 96 / 80 KB
+  static constexpr int kN2 = C / 2;                         // fc2 in two halves of N = C / 2
+  static constexpr int kW2PartBytes = (kN2 / 2) * BK * 2;   // this CTA's out rows of one half, one hidden K-block (12 / 10 KB)
+  static constexpr int kSlotBytes = kKb * kPairW1KbBytes;   // 48 / 40 KB
+  // [alignment pad <= 1023][ctrl 1 KB][X][H][ring][constants page 2 KB — only addressable when the pad is 0, see the epilogue]
+  static constexpr int kSmemBytes = 1024 + kXBytes + kPairHidBytes + kPairSlots * kSlotBytes + kPairConstBytes;
+  static_assert(C % BK == 0 && C <= kPairAcc1Col && kN2 % 16 == 0 && kN2 <= 256, "pair MLP channel count");
+  static_assert(kSmemBytes <= kSmemLimit && kSmemBytes - kPairConstBytes + 1023 <= kSmemLimit, "pair MLP shared memory");
+  static_assert(4 * kW2PartBytes == kSlotBytes && kW2PartBytes % 1024 == 0, "ring slot layout");
+};
+static bool pair_channels_ok(int C) { return C == 384 || C == 320; }
 
 // Debug build (-DLMV_MLP_TRACE): cycle account of the pair kernel's MMA issuer (leader CTAs) and of one epilogue warp, read back
 // with lmv_debug_mlp_trace().
@@ -494,9 +499,13 @@ struct CtrlPair {
   uint32_t tmem_base;
 };
 
+template <int kPairC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const MlpParams p) {
+  using Shape = PairShape<kPairC>;
+  constexpr int kPairKb = Shape::kKb, kPairXBytes = Shape::kXBytes, kPairN2 = Shape::kN2, kPairW2PartBytes = Shape::kW2PartBytes,
+                kPairSlotBytes = Shape::kSlotBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -851,8 +860,10 @@ bool mlp_fused_supported(int C, int Hd) {
   // acc2 [128 x C] + two acc1 buffers must fit the 512 TMEM columns; the X tile, two hidden buffers and both weight rings
   // must fit 227 KB of shared memory (C = 384: 96 KB X tile, 14 KB constants at Hd = 1536)
   const bool narrow = C >= 32 && C <= 192 && C % 32 == 0;
-  const bool wide_ok = C == 384 && Hd <= 1536;
-  return (narrow || wide_ok) && Hd % 128 == 0 && Hd >= 128 && Hd <= 4096;
+  const bool wide_ok = C == 384 && Hd <= 1536;                   // single-CTA wide kernel (constants page sized for Hd <= 1536)
+  const char* pair_env = getenv("LMV_MLP_PAIR");
+  const bool pair_ok = pair_channels_ok(C) && !(pair_env && atoi(pair_env) == 0);   // CTA-pair kernel
+  return (narrow || wide_ok || pair_ok) && Hd % 128 == 0 && Hd >= 128 && Hd <= 4096;
 }
 
 int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
@@ -874,13 +885,14 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
   p.hc = HC;
   // the wide shape runs on the CTA-pair kernel unless LMV_MLP_PAIR=0 (read per call: schedules are built once, tests switch it)
   const char* pair_env = getenv("LMV_MLP_PAIR");
-  p.pair = (HC == 64 && a.C == kPairC && !(pair_env && atoi(pair_env) == 0)) ? 1 : 0;
+  p.pair = (HC == 64 && pair_channels_ok(a.C) && !(pair_env && atoi(pair_env) == 0)) ? 1 : 0;
   if (p.pair) {
     // CTA-pair kernel: 256 rows per cluster, each CTA loads half of every weight box
     p.tiles = (a.R + 2 * BM - 1) / (2 * BM);
-    p.kb1 = kPairKb; p.chunks = a.Hd / kPairHC; p.nparts2 = 2; p.n2 = kPairN2; p.slot2_bytes = 0; p.const_bytes = 0;
-    p.nx = 1; p.nh = 2; p.n1slots = kPairSlots; p.n2slots = 0; p.w1_kpb = kPairKb; p.w1_boxes = 1; p.res_smem = 0;
-    op->smem_bytes = kPairSmemBytes;
+    const int kb = a.C / BK, n2 = a.C / 2;
+    p.kb1 = kb; p.chunks = a.Hd / kPairHC; p.nparts2 = 2; p.n2 = n2; p.slot2_bytes = 0; p.const_bytes = 0;
+    p.nx = 1; p.nh = 1; p.n1slots = kPairSlots; p.n2slots = 0; p.w1_kpb = kb; p.w1_boxes = 1; p.res_smem = 0;
+    op->smem_bytes = a.C == 384 ? PairShape<384>::kSmemBytes : PairShape<320>::kSmemBytes;
     p.b1 = a.b1; p.cs1 = a.cs1; p.b2 = a.b2;
     p.ln_stats = a.ln_stats; p.ln_parts = a.ln_parts > 0 ? a.ln_parts : 1; p.ln_eps = a.ln_eps; p.ln_inv_k = 1.0f / (float)a.C;
     p.resid = a.resid ? a.resid : a.x;
@@ -894,15 +906,15 @@ int mlp_fused_prepare(const MlpArgs& a, MlpOp* op) {
       if ((rc = encode_tmap_bf16(&op->tmX, a.x, 2, dims, strides, box, 128))) return rc;
     }
     {   // (k inside a K-block, hidden row, K-block): this CTA's 64 hidden rows of all six K-blocks in one box
-      uint64_t dims[3] = {(uint64_t)BK, (uint64_t)a.Hd, (uint64_t)kPairKb};
+      uint64_t dims[3] = {(uint64_t)BK, (uint64_t)a.Hd, (uint64_t)kb};
       uint64_t strides[2] = {(uint64_t)a.C * 2, (uint64_t)BK * 2};
-      uint32_t box[3] = {BK, (uint32_t)(kPairHC / 2), (uint32_t)kPairKb};
+      uint32_t box[3] = {BK, (uint32_t)(kPairHC / 2), (uint32_t)kb};
       if ((rc = encode_tmap_bf16(&op->tmW1, a.W1, 3, dims, strides, box, 128))) return rc;
     }
     {
       uint64_t dims[2] = {(uint64_t)a.Hd, (uint64_t)a.C};
       uint64_t strides[1] = {(uint64_t)a.Hd * 2};
-      uint32_t box[2] = {BK, (uint32_t)(kPairN2 / 2)};
+      uint32_t box[2] = {BK, (uint32_t)(n2 / 2)};
       if ((rc = encode_tmap_bf16(&op->tmW2, a.W2, 2, dims, strides, box, 128))) return rc;
     }
     return LMV_OK;
@@ -978,10 +990,12 @@ int mlp_fused_run(const MlpOp& op, cudaStream_t stream) {
   LMV_CUDA_OK(g_attr_once.run([] {
     const cudaError_t e0 = cudaFuncSetAttribute(mlp_fused_tcgen05<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     const cudaError_t e1 = cudaFuncSetAttribute(mlp_fused_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    const cudaError_t e2 = cudaFuncSetAttribute(mlp_pair_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    return e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
+    const cudaError_t e2 = cudaFuncSetAttribute(mlp_pair_tcgen05<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    const cudaError_t e3 = cudaFuncSetAttribute(mlp_pair_tcgen05<320>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    return e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
   }));
-  auto fn = op.p.pair ? mlp_pair_tcgen05 : (op.p.hc == 128 ? mlp_fused_tcgen05<128> : mlp_fused_tcgen05<64>);
+  auto fn = op.p.pair ? (op.p.C == 384 ? mlp_pair_tcgen05<384> : mlp_pair_tcgen05<320>)
+                      : (op.p.hc == 128 ? mlp_fused_tcgen05<128> : mlp_fused_tcgen05<64>);
   LMV_CUDA_OK(launch_kernel(fn, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmX, op.tmW1, op.tmW2, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;

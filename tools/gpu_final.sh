@@ -19,14 +19,27 @@ cap() { run ncu_$1 400 ncu --set full --metrics $M --clock-control none --import
 cap dca_d_c96 dca_x_kernel 2
 cap dca_d_c192 dca_x_kernel 6
 cap dca_c_c96 dca_x_kernel 0
-cap gemm_fc1 gemm_bf16 ${GEMM_SKIP:-30}
-cap mlp_c96 mlp_fused 0
-cap attn_self attention_self_kernel 0
+cap gemm_qkv gemm_bf16 ${GEMM_SKIP:-30}
+cap mlp_c96 mlp_fused_tcgen05 0
+cap mlp_pair_c384 mlp_pair 2
+cap attn_self attention_self_kernel 2
 cap posembed_c96 posembed_tile 0
+cap posembed_c384 posembed_tile 22
 cap meta_chain_c192 meta_chain 8
+# cycle traces (debug builds, if present): fused cross-attention roles, self-attention softmax phases, CTA-pair MLP issuer / epilogue
 if [ -f lemevit_b200/liblemevit_b200_dcatrace.so ]; then
   export LEMEVIT_B200_LIB=$PWD/lemevit_b200/liblemevit_b200_dcatrace.so
-  for a in "128 3136 96 3 D 0" "128 3136 96 3 D 2" "128 3136 96 3 C 0" "128 784 192 6 D 0"; do timeout 120 python tools/dca_trace.py $a; done > gpurun_out/dca_trace_$TAG.txt 2>&1
-  unset LEMEVIT_B200_LIB
+  for a in "128 3136 96 3 D 0" "128 3136 96 3 C 0" "128 784 192 6 D 0"; do timeout 120 python tools/dca_trace.py $a; done > gpurun_out/dca_trace_$TAG.txt 2>&1
 fi
+if [ -f lemevit_b200/liblemevit_b200_attntrace.so ]; then
+  export LEMEVIT_B200_LIB=$PWD/lemevit_b200/liblemevit_b200_attntrace.so
+  timeout 120 python tools/attn_trace.py 256 12 212 196 > gpurun_out/attn_trace_$TAG.txt 2>&1
+fi
+if [ -f lemevit_b200/liblemevit_b200_mlptrace.so ]; then
+  export LEMEVIT_B200_LIB=$PWD/lemevit_b200/liblemevit_b200_mlptrace.so
+  timeout 120 python tools/mlp_trace.py > gpurun_out/mlp_trace_$TAG.txt 2>&1
+fi
+unset LEMEVIT_B200_LIB
+# schedule A/B lines behind the numbers in DESIGN.md: stage-3 MLP as two GEMMs / single-CTA wide kernel / CTA-pair kernel
+for v in "LMV_FUSED_MLP_WIDE=0" "LMV_MLP_PAIR=0" "LMV_MLP_PAIR=1"; do echo "== $v"; env $v timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-eager-reference | tail -1 | cut -c1-200; done > gpurun_out/mlp_ab_$TAG.txt 2>&1
 true
