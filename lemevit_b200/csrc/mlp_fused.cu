@@ -730,47 +730,69 @@ mlp_pair_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     auto output_epilogue = [&](int oit) {
       const int row = row0_of(oit) + rloc;
       const bool rok = row < p.R;
-      const int it = oit;
-        TR(3)
-        bool waited = false;
-        for (int c0 = e * 32; c0 < kPairC; c0 += 128) {
-          uint4 res[4];
-          if (rok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (long long)row * kPairC + c0);
+      TR(3)
+      // this warp's output columns: c0 = 32 e + 128 k.  b2 sits one column per lane (broadcast by shuffles), the residual of chunk
+      // k+1 is requested before chunk k is processed: the three dependent trips to L2 of a straightforward loop were the largest
+      // single item of this kernel's per-tile time, and while the epilogue warps are here nobody drains the next fc1 accumulator.
+      constexpr int kChunks = (kPairC + 127) / 128;
+      float b2r[kChunks];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) res[i] = rp[i];   // plain loads: resid may alias out
-          }
-          float4 b2v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) b2v[i] = __ldg(reinterpret_cast<const float4*>(p.b2 + c0) + i);
-          if (!waited) {
-            mbar_wait(&ctrl->acc2_full, (uint32_t)it & 1u, 62);
-            tc_fence_after();
-            waited = true;
-          }
-          uint32_t v[32];
-          tmem_ld_x32(lane_addr + (uint32_t)c0, v);
-          tmem_ld_wait();
-          if (rok) {
-            uint4 o[4];
+      for (int k = 0; k < kChunks; ++k) {
+        const int c0 = e * 32 + k * 128;
+        b2r[k] = c0 < kPairC ? __ldg(p.b2 + c0 + lane) : 0.f;
+      }
+      // lane = row: every lane touches its own cache lines, and the LSU pays per line — 256-bit accesses (a full sector per lane)
+      // where the rows are 32-byte aligned, 128-bit ones otherwise
+      const bool wide_ls = ((reinterpret_cast<uintptr_t>(p.resid) | reinterpret_cast<uintptr_t>(p.out)) & 31) == 0;
+      auto load_res = [&](int c0, uint32_t (&res)[16]) {
+        if (rok && c0 < kPairC) {
+          const bf16* rp = p.resid + (long long)row * kPairC + c0;   // plain loads: resid may alias out
+          if (wide_ls) {
+            ld_global_256(rp, reinterpret_cast<uint32_t (&)[8]>(res[0]));
+            ld_global_256(rp + 16, reinterpret_cast<uint32_t (&)[8]>(res[8]));
+          } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b0 = b2v[2 * i], b1 = b2v[2 * i + 1];
-              const float2 r0 = unpack_bf16x2(res[i].x), r1 = unpack_bf16x2(res[i].y), r2_ = unpack_bf16x2(res[i].z), r3 = unpack_bf16x2(res[i].w);
-              o[i].x = pack_bf16x2(__uint_as_float(v[8 * i + 0]) + b0.x + r0.x, __uint_as_float(v[8 * i + 1]) + b0.y + r0.y);
-              o[i].y = pack_bf16x2(__uint_as_float(v[8 * i + 2]) + b0.z + r1.x, __uint_as_float(v[8 * i + 3]) + b0.w + r1.y);
-              o[i].z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + b1.x + r2_.x, __uint_as_float(v[8 * i + 5]) + b1.y + r2_.y);
-              o[i].w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + b1.z + r3.x, __uint_as_float(v[8 * i + 7]) + b1.w + r3.y);
+              const uint4 u = reinterpret_cast<const uint4*>(rp)[i];
+              res[4 * i] = u.x; res[4 * i + 1] = u.y; res[4 * i + 2] = u.z; res[4 * i + 3] = u.w;
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + (long long)row * kPairC + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = o[i];
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->acc2_empty);
-        TR(4)
+      };
+      uint32_t res[2][16];
+      load_res(e * 32, res[0]);
+      mbar_wait(&ctrl->acc2_full, (uint32_t)oit & 1u, 62);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < kChunks; ++k) {
+        const int c0 = e * 32 + k * 128;
+        if (c0 >= kPairC) break;   // (warp-uniform)
+        if (k + 1 < kChunks) load_res(c0 + 128, res[(k + 1) & 1]);
+        uint32_t v[32];
+        tmem_ld_x32(lane_addr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 rr = unpack_bf16x2(res[k & 1][i]);
+          const float b0 = __shfl_sync(0xffffffffu, b2r[k], 2 * i), b1 = __shfl_sync(0xffffffffu, b2r[k], 2 * i + 1);
+          o[i] = pack_bf16x2(__uint_as_float(v[2 * i]) + b0 + rr.x, __uint_as_float(v[2 * i + 1]) + b1 + rr.y);
+        }
+        if (rok) {
+          bf16* op = p.out + (long long)row * kPairC + c0;
+          if (wide_ls) {
+            st_global_256(op, reinterpret_cast<const uint32_t (&)[8]>(o[0]));
+            st_global_256(op + 16, reinterpret_cast<const uint32_t (&)[8]>(o[8]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctrl->acc2_empty);
+      TR(4)
     };
     for (int it = 0; it < my_tiles; ++it) {
       const int row = row0_of(it) + rloc;

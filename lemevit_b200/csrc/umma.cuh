@@ -370,6 +370,19 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 // packed fp32 (two lanes per register pair: FFMA2 / FMUL2 / FADD2 on sm_100)
+// 256-bit global accesses (sm_100: LDG / STG.256): one full 32-byte sector per lane — for lane = row access patterns, where every
+// lane touches a different cache line and the LSU pays per line, not per byte
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(ptr)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 // three-input maximum (FMNMX3 on sm_100a)
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
