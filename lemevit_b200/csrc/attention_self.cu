@@ -310,15 +310,12 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (lane == 0) mbar_arrive(&ctrl->o_empty[g]);
       if (prev_out) {
         const float inv = 1.f / (prev_ps + y_sum[prev_par * kQTile + r]);
+        uint32_t w[8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-          reinterpret_cast<uint4*>(prev_out + hcol * 16)[j] = u;
-        }
+        for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
+        bf16* dst = prev_out + hcol * 16;
+        reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);   // (one 256-bit store instead was measured 4 % slower here)
+        reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
       } else if (prev_prow >= 0) {
         // split-KV: unnormalised partial of this key block; the merge kernel rescales and sums the blocks
         float4* dst = reinterpret_cast<float4*>(p.part_o + prev_prow * kD + hcol * 16);

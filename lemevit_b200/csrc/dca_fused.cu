@@ -518,9 +518,18 @@ dca_x_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
               st2 = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, st2))));
               st2 = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, fmaf(f3.y, f3.y, st2))));
             }
-            uint4* op = reinterpret_cast<uint4*>(p.xout + grow * C + c0);
+            // lane = token stores: the LSU pays per cache line touched — one full 32-byte sector per lane and instruction where the
+            // rows are 32-byte aligned (C % 16 == 0 always holds here)
+            bf16* op = p.xout + grow * C + c0;
+            if ((reinterpret_cast<uintptr_t>(p.xout) & 31) == 0 && (C & 15) == 0) {
+              const uint32_t w0[8] = {o[0].x, o[0].y, o[0].z, o[0].w, o[1].x, o[1].y, o[1].z, o[1].w};
+              const uint32_t w1[8] = {o[2].x, o[2].y, o[2].z, o[2].w, o[3].x, o[3].y, o[3].z, o[3].w};
+              st_global_256(op, w0);
+              st_global_256(op + 16, w1);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = o[i];
+              for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = o[i];
+            }
           }
          }
         }

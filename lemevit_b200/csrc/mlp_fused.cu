@@ -333,9 +333,18 @@ mlp_fused_tcgen05(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               o[i].z = pack_bf16x2(__uint_as_float(v[8 * i + 4]) + b1.x + r2_.x, __uint_as_float(v[8 * i + 5]) + b1.y + r2_.y);
               o[i].w = pack_bf16x2(__uint_as_float(v[8 * i + 6]) + b1.z + r3.x, __uint_as_float(v[8 * i + 7]) + b1.w + r3.y);
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + (long long)row * p.C + c0);
+            // lane = row stores: the LSU pays per cache line touched, so one full 32-byte sector per lane and instruction where the
+            // rows are 32-byte aligned
+            bf16* op = p.out + (long long)row * p.C + c0;
+            if ((reinterpret_cast<uintptr_t>(p.out) & 31) == 0) {
+              const uint32_t w0[8] = {o[0].x, o[0].y, o[0].z, o[0].w, o[1].x, o[1].y, o[1].z, o[1].w};
+              const uint32_t w1[8] = {o[2].x, o[2].y, o[2].z, o[2].w, o[3].x, o[3].y, o[3].z, o[3].w};
+              st_global_256(op, w0);
+              st_global_256(op + 16, w1);
+            } else {
   #pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = o[i];
+              for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(op)[i] = o[i];
+            }
           }
         }
         if (!waited) {   // this warp owns no output columns (C < 128): still consume the phase
