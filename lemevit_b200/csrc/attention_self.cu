@@ -318,10 +318,16 @@ attention_self_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
       } else if (prev_prow >= 0) {
         // split-KV: unnormalised partial of this key block; the merge kernel rescales and sums the blocks
-        float4* dst = reinterpret_cast<float4*>(p.part_o + prev_prow * kD + hcol * 16);
+        // lane = row stores of 64 contiguous bytes: two 256-bit stores where the workspace allows it (the LSU pays per cache line)
+        float* dst = p.part_o + prev_prow * kD + hcol * 16;
+        if ((reinterpret_cast<uintptr_t>(p.part_o) & 31) == 0) {
+          st_global_256(dst, reinterpret_cast<const uint32_t (&)[8]>(v[0]));
+          st_global_256(dst + 8, reinterpret_cast<const uint32_t (&)[8]>(v[8]));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
         if (hcol == 0) p.part_ml[prev_prow] = make_float2(prev_mxs, prev_ps + y_sum[prev_par * kQTile + r]);
       }
     };

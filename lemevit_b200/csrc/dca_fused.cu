@@ -717,10 +717,16 @@ dca_x_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
           tmem_ld_x32(lane_addr + colZ + (uint32_t)c0, v);
           tmem_ld_wait();
           if (rvalid) {
-            float4* dst = reinterpret_cast<float4*>(p.part_z + pr * C + c0);
+            // lane = row stores of 128 contiguous bytes: 256-bit where the partial buffer allows it (the LSU pays per cache line)
+            float* dst = p.part_z + pr * C + c0;
+            if ((reinterpret_cast<uintptr_t>(p.part_z) & 31) == 0 && (C & 7) == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              for (int i = 0; i < 4; ++i) st_global_256(dst + 8 * i, reinterpret_cast<const uint32_t (&)[8]>(v[8 * i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
           }
         }
         tc_fence_before();

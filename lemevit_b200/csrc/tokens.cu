@@ -404,18 +404,30 @@ stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp]
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     if (q && !two) break;
-    uint4* dst = reinterpret_cast<uint4*>(out + (pix0 + q) * C1);
+    // lane = pixel stores (C1 * 2 = 64 or 96 contiguous bytes each): the LSU pays per cache line touched, so one full 32-byte sector
+    // per lane and instruction where the output is 32-byte aligned
+    bf16* dst = out + (pix0 + q) * C1;
+    const bool al32 = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
 #pragma unroll
-    for (int c = 0; c < C1 / 8; ++c) {
-      uint4 u;
-      // packed GELU (FFMA2 / FMUL2 + two MUFU.TANH per pair): this kernel is issue-bound, and the activation is a third of its instructions
-      const float2 g0 = gelu_fast2(make_float2(acc[q][2 * c].x, acc[q][2 * c].y)), g1 = gelu_fast2(make_float2(acc[q][2 * c].z, acc[q][2 * c].w));
-      const float2 g2 = gelu_fast2(make_float2(acc[q][2 * c + 1].x, acc[q][2 * c + 1].y)), g3 = gelu_fast2(make_float2(acc[q][2 * c + 1].z, acc[q][2 * c + 1].w));
-      u.x = pack_bf16x2(g0.x, g0.y);
-      u.y = pack_bf16x2(g1.x, g1.y);
-      u.z = pack_bf16x2(g2.x, g2.y);
-      u.w = pack_bf16x2(g3.x, g3.y);
-      dst[c] = u;
+    for (int c = 0; c < C1 / 16; ++c) {
+      uint32_t w[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // packed GELU (FFMA2 / FMUL2 + two MUFU.TANH per pair): this kernel is issue-bound, and the activation is a third of its instructions
+        const float4 a0 = acc[q][4 * c + 2 * h], a1 = acc[q][4 * c + 2 * h + 1];
+        const float2 g0 = gelu_fast2(make_float2(a0.x, a0.y)), g1 = gelu_fast2(make_float2(a0.z, a0.w));
+        const float2 g2 = gelu_fast2(make_float2(a1.x, a1.y)), g3 = gelu_fast2(make_float2(a1.z, a1.w));
+        w[4 * h] = pack_bf16x2(g0.x, g0.y);
+        w[4 * h + 1] = pack_bf16x2(g1.x, g1.y);
+        w[4 * h + 2] = pack_bf16x2(g2.x, g2.y);
+        w[4 * h + 3] = pack_bf16x2(g3.x, g3.y);
+      }
+      if (al32) {
+        st_global_256(dst + 16 * c, w);
+      } else {
+        reinterpret_cast<uint4*>(dst + 16 * c)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<uint4*>(dst + 16 * c)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
     }
   }
 }
