@@ -26,13 +26,18 @@ struct PosTileParams {
   const float* dw_w;   // [9][C]
   const float* dw_b;   // [C]
   bf16* out;           // [B, T, C]
-  float* stats;        // [B*T][2] or null
+  float* stats;        // [B*T][parts][2] or null
   int B, H, W, T, C;
-  int TW, TH, tiles_x, tiles_y;
+  int TW, TH, tiles_x, ntiles, n_items;
   int col_threads;     // threads that own (tile column, channel vector) pairs: a multiple of V = CS / 8
-  int cbox, ncb;       // channel box of one TMA load, number of boxes per CTA (CS = cbox * ncb)
+  int V, tx_step;      // 16-byte channel vectors of a slice; columns a thread advances by when the tile has more pairs than threads
+  int cbox, ncb, vpb;  // channel box of one TMA load, boxes per CTA (CS = cbox * ncb), 16-byte vectors per box
   int CS, parts;       // channels per CTA (blockIdx.z selects the slice) and slices per row; C = CS * parts
   int sub_bytes;       // shared-memory bytes of one channel box of the input tile (128-byte multiple: TMA destination)
+  int in_bytes;        // one input tile: ncb * sub_bytes
+  int row_pitch, col_pitch;   // bytes between tile rows / tile columns inside a channel box
+  int part_elems;      // TH * TW * V statistics partials per buffer
+  uint32_t tx_bytes;   // bytes one tile load delivers
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -41,26 +46,30 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
   f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
+__device__ __forceinline__ float2 unpack2(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
 
 // Persistent CTAs (grid.x strides over the (image, tile) items of one channel slice) with a double-buffered input tile: the TMA
 // load of item i+1 is in flight while item i is computed, and the depthwise taps are fetched once per CTA instead of once per tile.
-// Thread = (column tx of the tile, 8-channel vector v); it streams the TH + 2 input rows of its column ONCE: every input row
-// (3 x LDS.128, unpacked once) feeds the three output rows it touches through three rotating accumulators, so an output element
-// costs 3 shared loads + 36 packed FMAs instead of 9 loads + 9 unpacks + 72 FMAs (the one-shot version was issue-bound at 57 %).
+// Thread = (column tx of the tile, 8-channel vector v); it streams the input rows of its column ONCE: every input row (3 x LDS.128,
+// unpacked once) feeds the (up to) three output rows it touches through three rotating accumulators.  The row loop is peeled so
+// that no tap is computed for an output row outside the tile (first / last two input rows) and all addressing is three running
+// pointers: per input row and thread 3 LDS + 24 unpack + <= 36 packed FMAs, per output row 4 packs + one 16-byte store + ~16
+// packed-fp32 instructions for the row statistics.  (The first persistent version spent 2/3 of its issue slots on predicates and
+// 64-bit index arithmetic: profiles/r02_ncu_posembed_c384.txt.)  The FMA order per output element is bias, then taps 0..8: the
+// per-token kernel (tokens.cu) rounds identically.
 __global__ void __launch_bounds__(kThreads)
 posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (128u - (smem_u32(smem_raw) & 127u)) & 127u;
   uint8_t* smem = smem_raw + pad;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);           // full[2]
-  const int C = p.C, V = p.CS >> 3, HW = p.H * p.W;            // V: 16-byte channel vectors of this CTA's slice
+  const int C = p.C, V = p.V, HW = p.H * p.W;
   const int slice = blockIdx.z, c_off = slice * p.CS;
-  const int ntiles = p.tiles_x * p.tiles_y;
   pdl_launch_dependents();
-  pdl_wait();
 
   if (blockIdx.y == 1) {
     // ---- meta-token rows of a unified buffer: copy + statistics, one warp per row ----
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;          // blockDim need not be a multiple of 32: use the full warps only
     if (warp >= nwarps || slice != 0) return;   // slice 0 copies the whole row; the other partials of the row are zero
@@ -87,28 +96,24 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
     return;
   }
 
-  const int IW = p.TW + 2, IH = p.TH + 2;
-  const int in_bytes = p.ncb * p.sub_bytes;                              // one input tile (all channel boxes of the slice)
-  uint8_t* s_in = smem + 128;                                            // [2][in_bytes]
-  float2* s_part = reinterpret_cast<float2*>(s_in + 2 * (size_t)in_bytes);   // [2][TH*TW][V] partial statistics
-  const int part_elems = p.TH * p.TW * V;
-  const int n_items = ntiles * p.B;
+  uint8_t* s_in = smem + 128;                                                // [2][in_bytes]
+  float2* s_part = reinterpret_cast<float2*>(s_in + 2 * (size_t)p.in_bytes);  // [2][TH*TW][V] partial statistics
+  const int ntiles = p.ntiles, n_items = p.n_items;
   auto issue = [&](int item, int buf) {
     const int b = item / ntiles, t = item - b * ntiles;
     const int tile_y = t / p.tiles_x, tile_x = t - tile_y * p.tiles_x;
-    mbar_expect_tx(&bar[buf], (uint32_t)(p.ncb * IH * IW * p.cbox * 2));
+    mbar_expect_tx(&bar[buf], p.tx_bytes);
     for (int cb = 0; cb < p.ncb; ++cb)
-      tma_load_4d(s_in + (size_t)buf * in_bytes + (size_t)cb * p.sub_bytes, &tm, &bar[buf], c_off + cb * p.cbox, tile_x * p.TW - 1, tile_y * p.TH - 1, b);
+      tma_load_4d(s_in + (size_t)buf * p.in_bytes + (size_t)cb * p.sub_bytes, &tm, &bar[buf], c_off + cb * p.cbox, tile_x * p.TW - 1, tile_y * p.TH - 1, b);
   };
   if (threadIdx.x == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
     fence_mbar_init();
-    if ((int)blockIdx.x < n_items) issue(blockIdx.x, 0);
   }
-  // thread = (tile column, channel vector): its 9 x 8 depthwise taps and 8 biases live in registers as packed pairs.  When the
-  // tile has more (column, vector) pairs than the CTA has threads, a thread keeps its vector and walks columns tx0, tx0 + tx_step, ..
-  const int tx_step = p.col_threads / V;
+  // thread = (tile column, channel vector): its 9 x 8 depthwise taps and 8 biases live in registers as packed pairs (weights are
+  // constants of the plan, not outputs of the previous kernel: fetched before the grid dependency resolves).  When the tile has more
+  // (column, vector) pairs than the CTA has threads, a thread keeps its vector and walks columns tx0, tx0 + tx_step, ..
   const bool active = (int)threadIdx.x < p.col_threads;
   const int tx0 = active ? (int)threadIdx.x / V : 0, v = active ? (int)threadIdx.x - tx0 * V : 0;
   float2 w[9][4], bias[4];
@@ -124,10 +129,16 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.dw_b + c_off + v * 8) + 1);
     bias[0] = make_float2(b0.x, b0.y); bias[1] = make_float2(b0.z, b0.w); bias[2] = make_float2(b1.x, b1.y); bias[3] = make_float2(b1.z, b1.w);
   }
-  const int vpb = p.cbox >> 3;                     // 16-byte vectors per channel box
-  const int cb = v / vpb, vv = v - cb * vpb;
-  const int row_pitch = IW * p.cbox * 2, col_pitch = p.cbox * 2;
+  const int cb = v / p.vpb, vv = v - cb * p.vpb;
+  const uint32_t thr_off = (uint32_t)(cb * p.sub_bytes + vv * 16);      // this thread's vector inside an input tile, column 0
+  const uint32_t row_pitch = p.row_pitch, col_pitch = p.col_pitch;
+  const long long out_row_step = (long long)p.W * C;                    // elements between vertically adjacent tokens
+  const int part_row_step = p.TW * V;
+  const int n_tok = p.TW * p.TH;
+  const int tok_ty0 = (int)threadIdx.x / p.TW, tok_tx0 = (int)threadIdx.x - tok_ty0 * p.TW;   // first token of the statistics pass
   __syncthreads();          // barrier init visible to every waiter
+  pdl_wait();
+  if (threadIdx.x == 0 && (int)blockIdx.x < n_items) issue(blockIdx.x, 0);
 
   int it = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -137,78 +148,97 @@ posembed_tile_kernel(const __grid_constant__ CUtensorMap tm, const PosTileParams
     const int b = item / ntiles, t = item - b * ntiles;
     const int tile_y = t / p.tiles_x, tile_x = t - tile_y * p.tiles_x;
     const int x0 = tile_x * p.TW, y0 = tile_y * p.TH;
+    const int nrows = min(p.TH, p.H - y0);                 // output rows of this tile (>= 1)
+    const long long tok0 = (long long)b * p.T + (long long)y0 * p.W + x0;
     mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u, 20);
-    float2* part = s_part + (size_t)buf * part_elems;
+    float2* part = s_part + (size_t)buf * p.part_elems;
     if (active)
-     for (int tx = tx0; tx < p.TW; tx += tx_step) {
-      const int x = x0 + tx;
-      const bool xok = x < p.W;
-      const uint8_t* base = s_in + (size_t)buf * in_bytes + (size_t)cb * p.sub_bytes + (size_t)tx * col_pitch + (size_t)vv * 16;
-      const long long row0 = (long long)b * p.T + (long long)y0 * p.W + x;
-      float2 a0[4], a1[4], a2[4];    // accumulators of output rows (ir), (ir - 1), (ir - 2), rotated by the 3x unrolled loop
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { a1[j] = make_float2(0.f, 0.f); a2[j] = make_float2(0.f, 0.f); }
-      // one input row: three 16-byte vectors (kx = 0..2) feed NEW (ky = 0), MID (ky = 1) and OLD (ky = 2); OLD is then complete
-      auto step = [&](int ir, float2 (&NEW)[4], float2 (&MID)[4], float2 (&OLD)[4]) {
+      for (int tx = tx0; tx < p.TW && x0 + tx < p.W; tx += p.tx_step) {
+        const uint8_t* sp = s_in + (size_t)buf * p.in_bytes + thr_off + (uint32_t)tx * col_pitch;   // input row ir, column tx (kx = 0)
+        bf16* op = p.out + (tok0 + tx) * C + c_off + v * 8;                                          // output row ty
+        float2* pp = part + tx * V + v;
         float2 in[3][4];
+        auto load = [&]() {
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const uint4 u = *reinterpret_cast<const uint4*>(base + (size_t)ir * row_pitch + (size_t)kx * col_pitch);
-          in[kx][0] = make_float2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
-          in[kx][1] = make_float2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
-          in[kx][2] = make_float2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
-          in[kx][3] = make_float2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          NEW[j] = ffma2(in[0][j], w[0][j], bias[j]);
-          NEW[j] = ffma2(in[1][j], w[1][j], NEW[j]);
-          NEW[j] = ffma2(in[2][j], w[2][j], NEW[j]);
-          MID[j] = ffma2(in[0][j], w[3][j], MID[j]);
-          MID[j] = ffma2(in[1][j], w[4][j], MID[j]);
-          MID[j] = ffma2(in[2][j], w[5][j], MID[j]);
-          OLD[j] = ffma2(in[0][j], w[6][j], OLD[j]);
-          OLD[j] = ffma2(in[1][j], w[7][j], OLD[j]);
-          OLD[j] = ffma2(in[2][j], w[8][j], OLD[j]);
-        }
-        const int ty = ir - 2;                      // the output row that is complete now
-        if (ty >= 0) {
-          float2 st = make_float2(0.f, 0.f);
-          if (xok && y0 + ty < p.H) {
-            uint4 pk;
-            pk.x = pack_bf16x2(OLD[0].x, OLD[0].y); pk.y = pack_bf16x2(OLD[1].x, OLD[1].y);
-            pk.z = pack_bf16x2(OLD[2].x, OLD[2].y); pk.w = pack_bf16x2(OLD[3].x, OLD[3].y);
-            reinterpret_cast<uint4*>(p.out + (row0 + (long long)ty * p.W) * C + c_off)[v] = pk;
-            // statistics of the STORED (bf16-rounded) values: exactly what the consuming GEMM reads
-            float f[8];
-            unpack8(pk, f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { st.x += f[j]; st.y = fmaf(f[j], f[j], st.y); }
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint4 u = *reinterpret_cast<const uint4*>(sp + (uint32_t)kx * col_pitch);
+            in[kx][0] = unpack2(u.x); in[kx][1] = unpack2(u.y); in[kx][2] = unpack2(u.z); in[kx][3] = unpack2(u.w);
           }
-          if (p.stats) part[(ty * p.TW + tx) * V + v] = st;
+          sp += row_pitch;
+        };
+        auto top = [&](float2 (&acc)[4]) {       // ky = 0: this input row is the row above the output row
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[j] = ffma2(in[0][j], w[0][j], bias[j]);
+            acc[j] = ffma2(in[1][j], w[1][j], acc[j]);
+            acc[j] = ffma2(in[2][j], w[2][j], acc[j]);
+          }
+        };
+        auto mid = [&](float2 (&acc)[4]) {       // ky = 1
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[j] = ffma2(in[0][j], w[3][j], acc[j]);
+            acc[j] = ffma2(in[1][j], w[4][j], acc[j]);
+            acc[j] = ffma2(in[2][j], w[5][j], acc[j]);
+          }
+        };
+        auto bot = [&](float2 (&acc)[4]) {       // ky = 2: completes the output row, which is stored with its statistics
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[j] = ffma2(in[0][j], w[6][j], acc[j]);
+            acc[j] = ffma2(in[1][j], w[7][j], acc[j]);
+            acc[j] = ffma2(in[2][j], w[8][j], acc[j]);
+          }
+          uint4 pk;
+          pk.x = pack_bf16x2(acc[0].x, acc[0].y); pk.y = pack_bf16x2(acc[1].x, acc[1].y);
+          pk.z = pack_bf16x2(acc[2].x, acc[2].y); pk.w = pack_bf16x2(acc[3].x, acc[3].y);
+          *reinterpret_cast<uint4*>(op) = pk;
+          op += out_row_step;
+          if (p.stats) {
+            // statistics of the STORED (bf16-rounded) values: exactly what the consuming GEMM reads
+            const float2 f0 = unpack2(pk.x), f1 = unpack2(pk.y), f2 = unpack2(pk.z), f3 = unpack2(pk.w);
+            const float2 s = fadd2(fadd2(f0, f1), fadd2(f2, f3));
+            float2 q = fmul2(f0, f0);
+            q = ffma2(f1, f1, q); q = ffma2(f2, f2, q); q = ffma2(f3, f3, q);
+            *pp = make_float2(s.x + s.y, q.x + q.y);
+            pp += part_row_step;
+          }
+        };
+        float2 a0[4], a1[4], a2[4];
+        // input rows nrows, nrows + 1 (M: accumulator whose output row got its ky = 0 taps last, O: the one before)
+        auto tail = [&](float2 (&M)[4], float2 (&O)[4]) {
+          load();
+          if (nrows >= 2) bot(O);
+          mid(M);
+          load();
+          bot(M);
+        };
+        load(); top(a0);
+        if (nrows == 1) {
+          tail(a0, a1);
+        } else {
+          load(); top(a1); mid(a0);
+          int ir = 2;
+          while (true) {
+            if (ir >= nrows) { tail(a1, a0); break; }
+            load(); top(a2); mid(a1); bot(a0); ++ir;
+            if (ir >= nrows) { tail(a2, a1); break; }
+            load(); top(a0); mid(a2); bot(a1); ++ir;
+            if (ir >= nrows) { tail(a0, a2); break; }
+            load(); top(a1); mid(a0); bot(a2); ++ir;
+          }
         }
-      };
-      int ir = 0;
-      for (; ir + 2 < IH; ir += 3) {
-        step(ir, a0, a1, a2);
-        step(ir + 1, a2, a0, a1);
-        step(ir + 2, a1, a2, a0);
       }
-      if (ir < IH) { step(ir, a0, a1, a2); ++ir; }
-      if (ir < IH) { step(ir, a2, a0, a1); }
-    }
     __syncthreads();
     if (p.stats) {
-      for (int tok = threadIdx.x; tok < p.TW * p.TH; tok += blockDim.x) {
-        const int ty = tok / p.TW, txx = tok - ty * p.TW;
-        const int x = x0 + txx, y = y0 + ty;
-        if (x >= p.W || y >= p.H) continue;
+      int ty = tok_ty0, txx = tok_tx0;
+      for (int tok = threadIdx.x; tok < n_tok; tok += blockDim.x) {
+        if (tok != (int)threadIdx.x) { ty = tok / p.TW; txx = tok - ty * p.TW; }
+        if (x0 + txx >= p.W || ty >= nrows) continue;
         float s1 = 0.f, s2 = 0.f;
-        for (int q = 0; q < V; ++q) {
-          const float2 pq = part[tok * V + q];
-          s1 += pq.x; s2 += pq.y;
-        }
-        const long long row = (long long)b * p.T + (long long)y * p.W + x;
+        const float2* pq = part + tok * V;
+        for (int q = 0; q < V; ++q) { s1 += pq[q].x; s2 += pq[q].y; }
+        const long long row = tok0 + (long long)ty * p.W + txx;
         *reinterpret_cast<float2*>(p.stats + 2 * (row * p.parts + slice)) = make_float2(s1, s2);
       }
     }
@@ -271,8 +301,14 @@ int posembed_tile_run(const PosEmbedOp& op, cudaStream_t s) {
   PosTileParams p;
   p.tokens = a.tokens; p.dw_w = a.dw_w; p.dw_b = a.dw_b; p.out = a.resid_out; p.stats = a.stats_out;
   p.H = a.H; p.W = a.W; p.T = a.T; p.C = a.C;
-  p.TW = op.TW; p.TH = op.TH; p.tiles_x = op.tiles_x; p.tiles_y = op.tiles_y; p.cbox = op.cbox; p.ncb = op.ncb;
+  p.TW = op.TW; p.TH = op.TH; p.tiles_x = op.tiles_x; p.cbox = op.cbox; p.ncb = op.ncb;
   p.sub_bytes = op.sub_bytes; p.parts = op.parts; p.CS = a.C / op.parts; p.B = a.B; p.col_threads = op.col_threads;
+  p.ntiles = op.tiles_x * op.tiles_y; p.n_items = p.ntiles * a.B;
+  p.V = p.CS / 8; p.tx_step = op.col_threads / p.V; p.vpb = op.cbox / 8;
+  p.in_bytes = op.ncb * op.sub_bytes;
+  p.col_pitch = op.cbox * 2; p.row_pitch = (op.TW + 2) * p.col_pitch;
+  p.part_elems = op.TH * op.TW * p.V;
+  p.tx_bytes = (uint32_t)(op.ncb * (op.TH + 2) * (op.TW + 2) * op.cbox * 2);
   // persistent CTAs: as many as can be resident (shared memory / registers allow 2-3 per SM), striding over the (image, tile) items;
   // blockIdx.y == 1: the CTAs that pass the meta-token rows of a unified buffer through
   const int n_items = op.tiles_x * op.tiles_y * a.B;

@@ -187,6 +187,27 @@ def test_dca_block_batch_invariance_and_peaked_softmax():
     assert torch.equal(x1[0], xout[4]) and torch.equal(c1[0], c_out[4])
 
 
+@pytest.mark.parametrize("kind,B,N,C,heads", [("D", 5, 300, 96, 3), ("D", 3, 784, 192, 6), ("C", 7, 1000, 96, 3), ("D", 2, 200, 64, 2), ("D", 1, 256, 160, 5)])
+def test_dca_block_images_per_cta(kind, B, N, C, heads, monkeypatch):
+    """The meta-token kernels run 1, 2 or 4 images per CTA (one weight fragment feeds the MMAs of all of them); the per-image
+    arithmetic is the same sequence, so the results are bit-identical, odd batches (last CTA runs its image twice) included."""
+    torch.manual_seed(11 * B + C)
+    xt = G.bf(torch.randn(B, N, C, device="cuda") * 1.3)
+    c = G.bf(torch.randn(B, 16, C, device="cuda"))
+    W = _dca_weights(kind, C, 4 * C)
+    sc, sx = C ** -0.5, math.log(16) / math.log(N) * C ** -0.5
+    ref_x, ref_c = G.ref_dca_block(kind, xt, c, W, heads, sx, sc)
+    outs = []
+    for im in (1, 2, 4):
+        monkeypatch.setenv("LMV_META_IM", str(im))
+        xout, _, c_out, _ = G.dca_block(kind, xt, c, W, heads, sx, sc)
+        torch.cuda.synchronize()
+        assert G.rel_err(c_out, ref_c) < TOL
+        outs.append((xout, c_out))
+    for xo, co in outs[1:]:
+        assert torch.equal(co, outs[0][1]) and (kind == "C" or torch.equal(xo, outs[0][0]))
+
+
 MLP_SHAPES = [(1000, 96, 384), (777, 192, 768), (300, 64, 256), (260, 160, 640), (130, 128, 512), (129, 192, 1280),
               (40000, 96, 384), (25000, 192, 768),
               # wide variant (256 < C <= 384: 64-column hidden chunks, fc2 in two halves, 3-D W1' boxes) — the stage-3 'S' blocks
