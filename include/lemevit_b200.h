@@ -33,6 +33,11 @@ extern "C" {
 
 #define LMV_DTYPE_BF16 0
 #define LMV_DTYPE_F32 1
+/* input images only (x_dtype of the lmv_forward_* calls and lmv_stem_conv1): raw 8-bit pixels, normalised inside the first stem
+ * convolution as bf16((float(u8) - mean[c]) / std[c]) — bit-identical to `x.float().sub_(mean).div_(std).to(bfloat16)`, the GPU side
+ * of the timm prefetcher the reference trains and validates with (main.py:399-428) — so the fp32 / bf16 image never exists in HBM. */
+#define LMV_DTYPE_U8 2       /* [B, 3, H, W] planar (timm fast_collate)          */
+#define LMV_DTYPE_U8_NHWC 3  /* [B, H, W, 3] interleaved (a decoded image as is) */
 
 #define LMV_MAX_STAGES 8
 
@@ -81,12 +86,16 @@ int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
  *   "fused_self_attn" (default 1): image + meta token self-attention of an 'S' block in ONE persistent kernel (lmv_attention_self);
  *   "fused_dca" (default 1): 'C' / 'D' blocks through the fused cross-attention kernels (lmv_dca_block) where the shape allows it;
  *   "dca_pipe" (default 0): the pipelined schedule of the fused cross-attention kernel where tensor memory allows it (A/B switch;
- *   measured slower than the one-tile-at-a-time schedule on B200). */
+ *   measured slower than the one-tile-at-a-time schedule on B200);
+ *   "implicit_conv" (default 1): strided convolutions as implicit GEMMs (0: im2col kernel + GEMM). */
 int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
 /* test hook (block-level parity against the reference's forward hooks): after block `block` of stage `stage` every forward
  * copies the block's outputs to x_tokens_out [B, N, C] bf16 (token-major) and c_out [B, queries_len, C] bf16 (either may be
  * null); stage < 0 turns the tap off.  The buffers must hold the batch of the forwards that follow. */
 int lmv_plan_set_tap(lmv_plan* plan, int stage, int block, void* x_tokens_out, void* c_out);
+/* per-channel mean / std of the 8-bit input path, in pixel units (0..255); default: ImageNet mean / std x 255, what the
+ * reference's default_cfg (`_cfg()`, models/lemevit.py:866) resolves to in timm's loader.  Needs 3 input channels. */
+int lmv_plan_set_input_norm(lmv_plan* plan, const float* mean3, const float* std3);
 /* bring-up switch: 1 routes every GEMM / attention through the plain SIMT cross-check kernels. */
 int lmv_plan_set_debug_simt(lmv_plan* plan, int enable);
 size_t lmv_workspace_bytes(const lmv_plan* plan, int batch, int H, int W);
@@ -108,8 +117,9 @@ int lmv_plan_get_profile(lmv_plan* plan, lmv_profile_entry* out, int max_entries
 /* human-readable per-launch-shape table of the same data (tuning aid); returns the untruncated length */
 int lmv_plan_profile_report(lmv_plan* plan, char* buf, int buf_bytes);
 
-/* replaces LeMeViT.forward (models/lemevit.py:831-836): x[B,in_chans,H,W] NCHW (bf16 or f32)
- * -> logits[B,num_classes] (bf16 or f32, per logits_dtype). */
+/* replaces LeMeViT.forward (models/lemevit.py:831-836): x[B,in_chans,H,W] NCHW (bf16 or f32), or raw 8-bit pixels
+ * (LMV_DTYPE_U8 / LMV_DTYPE_U8_NHWC, normalised in the stem: lmv_plan_set_input_norm) -> logits[B,num_classes] (bf16 or f32,
+ * per logits_dtype). */
 int lmv_forward_cls(lmv_plan* plan, const void* x, int x_dtype, int batch, int H, int W, void* workspace,
                     size_t workspace_bytes, void* logits, int logits_dtype, void* stream);
 /* replaces LeMeViT.forward_features(x, c) (models/lemevit.py:809-829) and, with `logits`, the head on top of it (:831-836):
@@ -213,11 +223,19 @@ int lmv_dca_block(int kind, const void* xt, const float* stats1, int parts1, voi
  * out[B*Ho*Wo, Kp] bf16 with k = ci*9 + ky*3 + kx, zero padded to Kp = round_up(9*Cin, 8); the conv
  * itself (+ folded BN + GELU, :700-701) is then lmv_linear on the tcgen05 GEMM. */
 int lmv_stem_im2col(const void* x, int x_dtype, void* out, int B, int Cin, int H, int W, void* stream);
-/* First stem convolution without the im2col detour: x NCHW [B, 3, H, W] (f32 | bf16) -> conv3x3 / stride 2 / pad 1 with the
+/* First stem convolution without the im2col detour: x NCHW [B, 3, H, W] (f32 | bf16; LMV_DTYPE_U8 / LMV_DTYPE_U8_NHWC pixels are
+ * normalised with the ImageNet mean / std, see lmv_plan_set_input_norm for the plan-level knob) -> conv3x3 / stride 2 / pad 1 with the
  * BatchNorm-folded weights w bf16 [C1][Kp = 32] (k = ci*9 + ky*3 + kx, lemevit_b200/pack.py) + bias -> GELU -> out token-major
  * [B, ceil(H/2)*ceil(W/2), C1] bf16 (models/lemevit.py:699-701).  Cin must be 3, C1 32 or 48. */
 int lmv_stem_conv1(const void* x, int x_dtype, const void* w, const float* bias, void* out, int B, int Cin, int C1, int H, int W,
                    void* stream);
+/* conv 3x3 / stride 2 / pad 1 (+ bias) on token-major bf16 activations in[B, T, Cin] (first H*W rows of every image, row = y*W + x)
+ * as an implicit GEMM on the tcgen05 kernel (strided TMA boxes gather the patch rows, nothing is materialised): the second stem
+ * convolution and the stage downsample convolutions with their BatchNorm folded (models/lemevit.py:702-703,715-716).
+ * w bf16 [Cout][9*Cin] with k = (ky*3 + kx)*Cin + ci, out bf16 token-major; out_rows_per_image: 0 = dense [B*Ho*Wo, Cout], else the
+ * rows of image b start at row b * out_rows_per_image (a unified [B, N + M, C] buffer).  Needs ceil(W/2) <= 128 and Cin % 8 == 0. */
+int lmv_conv3x3s2(const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int T, int Cin, int Cout,
+                  int out_rows_per_image, void* stream);
 /* im2col for conv 3x3/s2/p1 on NHWC bf16 tokens [B, T, C] (first H*W rows): out[B*Ho*Wo, 9*C] */
 int lmv_im2col_3x3s2(const void* in, void* out, int B, int H, int W, int T, int C, void* stream);
 /* classification tail (models/lemevit.py:815-827): feat[b] = bn_scale*mean_n(x[b]) + bn_shift + mean_m(LN(c[b])) */

@@ -13,7 +13,7 @@ from . import build as _build
 
 LMV_OK = 0
 LMV_ERR_INVALID, LMV_ERR_UNSUPPORTED, LMV_ERR_CUDA, LMV_ERR_OOM = -1, -2, -3, -4
-DTYPE_BF16, DTYPE_F32 = 0, 1
+DTYPE_BF16, DTYPE_F32, DTYPE_U8, DTYPE_U8_NHWC = 0, 1, 2, 3
 MAX_STAGES = 8
 
 
@@ -52,6 +52,8 @@ SIGNATURES = {
     "lmv_plan_destroy": (None, [_vp]),
     "lmv_plan_set_chunk": (_i, [_vp, _i]),
     "lmv_plan_set_debug_simt": (_i, [_vp, _i]),
+    "lmv_conv3x3s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "lmv_plan_set_input_norm": (_i, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "lmv_plan_set_tap": (_i, [_vp, _i, _i, _vp, _vp]),
     "lmv_plan_set_option": (_i, [_vp, C.c_char_p, _i]),
     "lmv_plan_set_profile": (_i, [_vp, _i]),

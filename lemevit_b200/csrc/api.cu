@@ -43,7 +43,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle_bytes) {
+                     const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(LMV_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  A fresh thread (nn.DataParallel
@@ -58,7 +58,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   for (int i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstrides[i - 1] = strides_bytes[i - 1];
   }
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
@@ -169,6 +169,10 @@ struct lmv_plan {
   int fused_dca = 1;
   int dca_pipe = 0;      // pipelined schedule of the fused cross-attention kernel: measured 5-10 % SLOWER than one tile at a time
   int direct_stem = 1;
+  int implicit_conv = 1;   // strided convolutions as implicit GEMMs (0: im2col kernel + GEMM)
+  // 8-bit input path (LMV_DTYPE_U8 / LMV_DTYPE_U8_NHWC): per-channel mean / std in pixel units, lmv_plan_set_input_norm
+  float in_mean[3] = {0.485f * 255.f, 0.456f * 255.f, 0.406f * 255.f};
+  float in_std[3] = {0.229f * 255.f, 0.224f * 255.f, 0.225f * 255.f};
   int profile = 0;
   int tap_stage = -1, tap_block = -1;       // test hook: copy (x, c) after this block to tap_x / tap_c
   void *tap_x = nullptr, *tap_c = nullptr;
@@ -439,8 +443,8 @@ struct Builder {
     rc = gemm_prepare(a, &op);
     if (rc) return;
     char d[160];
-    snprintf(d, sizeof(d), "gemm M=%d N=%d K=%d BN=%d%s%s%s%s", a.M, a.N, a.K, op.p.BN, a.ln_stats ? " ln" : "", a.act ? " gelu" : "",
-             a.residual ? " res" : "", a.stats_out ? " stats" : "");
+    snprintf(d, sizeof(d), "gemm M=%d N=%d K=%d BN=%d%s%s%s%s%s", a.M, a.N, a.K, op.p.BN, a.ln_stats ? " ln" : "", a.act ? " gelu" : "",
+             a.residual ? " res" : "", a.stats_out ? " stats" : "", a.conv_C > 0 ? " conv3x3s2" : "");
     sc->push([op](cudaStream_t s) { return gemm_run(op, s); }, OP_GEMM, fl, by, d);
   }
   void linear(const bf16* A, int lda, const bf16* Wt, const float* bias, int M, int N, int K, bf16* out, int ldc,
@@ -450,6 +454,25 @@ struct Builder {
     a.bias = bias; a.act = gelu; a.residual = resid; a.out = out; a.ldc = ldc;
     a.grp_rows = grp_rows; a.grp_stride = grp_stride;
     gemm(a);
+  }
+  // conv3x3 / stride 2 / pad 1 (+ folded BatchNorm) on token-major activations in [B, T, Cin] (first H * W rows per image) as an
+  // implicit GEMM: the A tiles are gathered by strided TMA boxes straight from the activation (gemm.cu), no patch matrix.
+  // Falls back to im2col + GEMM (patches: scratch for B * Ho * Wo * 9 * Cin bf16) where the implicit form does not apply.
+  void conv3x3s2(const bf16* in, int B, int H, int W, int T, int Cin, const bf16* Wt, const float* bias, int Cout, bf16* out,
+                 int grp_rows, int grp_stride, bf16* patches) {
+    if (rc) return;
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    if (!simt && plan->implicit_conv && gemm_conv_supported(H, W, Cin)) {
+      GemmArgs a;
+      a.A = in; a.lda = 0; a.W = Wt; a.ldw = 9 * Cin; a.M = B * Ho * Wo; a.N = Cout; a.K = 9 * Cin;
+      a.bias = bias; a.out = out; a.ldc = Cout; a.grp_rows = grp_rows; a.grp_stride = grp_stride;
+      a.conv_B = B; a.conv_H = H; a.conv_W = W; a.conv_T = T; a.conv_C = Cin;
+      gemm(a);
+      return;
+    }
+    Im2colArgs ia{in, patches, B, H, W, T, Cin};
+    sc->push([ia](cudaStream_t s) { return im2col_run(ia, s); }, OP_IM2COL, 0.0, 2.0 * B * Cin * ((double)H * W + 9.0 * Ho * Wo));
+    linear(patches, 9 * Cin, Wt, bias, B * Ho * Wo, Cout, 9 * Cin, out, Cout, 0, nullptr, grp_rows, grp_stride);
   }
   // LayerNorm(eps 1e-6, affine folded into Wt/bias at pack time) -> Linear, the norm folded into the epilogue:
   // A holds the raw rows, ln_stats their (sum, sum^2), colsum the column sums of Wt.
@@ -649,29 +672,30 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
 
   // ---- stem (models/lemevit.py:698-704): conv3x3/s2 + BN + GELU + conv3x3/s2 + BN, both on the GEMM
   {
+    const bool x_u8 = x_dtype == LMV_DTYPE_U8 || x_dtype == LMV_DTYPE_U8_NHWC;
+    const double x_bytes = (double)B * c.in_chans * H * W * (x_dtype == LMV_DTYPE_F32 ? 4 : x_u8 ? 1 : 2);
+    if (x_u8 && (b.simt || !plan->direct_stem || !stem_conv1_supported(c.in_chans, C0 / 2)))
+      return fail(LMV_ERR_UNSUPPORTED, "8-bit input needs the direct stem kernel (3 input channels, embed_dim[0] / 2 in {32, 48}, direct_stem = 1)");
     if (!b.simt && plan->direct_stem && stem_conv1_supported(c.in_chans, C0 / 2)) {
       StemArgs sa{nullptr, x_dtype, stem1, B, c.in_chans, H, W};
+      for (int i = 0; i < 3; ++i) { sa.mean[i] = plan->in_mean[i]; sa.std[i] = plan->in_std[i]; }
       const bf16* w1 = plan->stem1_w;
       const float* b1 = plan->stem1_b;
       const int C1 = C0 / 2;
       sc->push([sa, io, w1, b1, C1](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_conv1_run(a, w1, b1, C1, s); }, OP_STEM,
-               2.0 * B * g.H1 * g.W1 * C1 * 27.0,
-               (double)B * c.in_chans * H * W * (x_dtype == LMV_DTYPE_F32 ? 4 : 2) + 2.0 * B * g.H1 * g.W1 * C1, "stem_conv1_direct");
+               2.0 * B * g.H1 * g.W1 * C1 * 27.0, x_bytes + 2.0 * B * g.H1 * g.W1 * C1, "stem_conv1_direct");
     } else {
       StemArgs sa{nullptr, x_dtype, patches, B, c.in_chans, H, W};
       sc->push([sa, io](cudaStream_t s) { StemArgs a = sa; a.x = io->x; return stem_im2col_run(a, s); }, OP_IM2COL, 0.0,
-               (double)B * c.in_chans * H * W * (x_dtype == LMV_DTYPE_F32 ? 4 : 2) + 2.0 * B * g.H1 * g.W1 * kp0(c));
+               x_bytes + 2.0 * B * g.H1 * g.W1 * kp0(c));
       b.linear(patches, kp0(c), plan->stem1_w, plan->stem1_b, B * g.H1 * g.W1, C0 / 2, kp0(c), stem1, C0 / 2, /*gelu=*/1);
     }
-    Im2colArgs ia{stem1, patches, B, g.H1, g.W1, g.H1 * g.W1, C0 / 2};
-    sc->push([ia](cudaStream_t s) { return im2col_run(ia, s); }, OP_IM2COL, 0.0,
-             2.0 * B * (C0 / 2) * ((double)g.H1 * g.W1 + 9.0 * g.N[0]));
   }
   int cur = 0, ccur = 0;
   {
     const bool uni = g.unified[0];
-    b.linear(patches, 9 * (C0 / 2), plan->stem2_w, plan->stem2_b, B * g.N[0], C0, 9 * (C0 / 2), xbuf[cur], C0, 0, nullptr,
-             uni ? g.N[0] : 0, uni ? g.T[0] : 0);
+    b.conv3x3s2(stem1, B, g.H1, g.W1, g.H1 * g.W1, C0 / 2, plan->stem2_w, plan->stem2_b, C0, xbuf[cur], uni ? g.N[0] : 0, uni ? g.T[0] : 0,
+                patches);
   }
 
   for (int i = 0; i < S && !b.rc; ++i) {
@@ -685,11 +709,8 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
       const int Cp = c.embed_dim[i - 1];
       if (g.unified[i - 1]) c_prev_unified = xbuf[cur];
       if (c.attn_type[i - 1] != 'C') {
-        Im2colArgs ia{xbuf[cur], patches, B, g.H[i - 1], g.W[i - 1], g.T[i - 1], Cp};
-        sc->push([ia](cudaStream_t s) { return im2col_run(ia, s); }, OP_IM2COL, 0.0,
-                 2.0 * B * Cp * ((double)g.N[i - 1] + 9.0 * N));
-        b.linear(patches, 9 * Cp, sw.ds_w, sw.ds_b, B * N, C, 9 * Cp, xbuf[cur ^ 1], C, 0, nullptr, uni ? N : 0,
-                 uni ? T : 0);
+        b.conv3x3s2(xbuf[cur], B, g.H[i - 1], g.W[i - 1], g.T[i - 1], Cp, sw.ds_w, sw.ds_b, C, xbuf[cur ^ 1], uni ? N : 0, uni ? T : 0,
+                    patches);
         cur ^= 1;
       }
     }
@@ -920,11 +941,11 @@ static int run_forward(lmv_plan* plan, const void* x, int x_dtype, int B, int H,
                        void* logits, void* const* outs, int n_outs, int out_dtype, cudaStream_t stream,
                        const void* c_in = nullptr, void* feat = nullptr) {
   LMV_REQUIRE(plan && x && B > 0, "forward: null plan/input or empty batch");
-  LMV_REQUIRE(x_dtype == LMV_DTYPE_BF16 || x_dtype == LMV_DTYPE_F32, "forward: x dtype");
+  LMV_REQUIRE(x_dtype == LMV_DTYPE_BF16 || x_dtype == LMV_DTYPE_F32 || x_dtype == LMV_DTYPE_U8 || x_dtype == LMV_DTYPE_U8_NHWC, "forward: x dtype");
   LMV_REQUIRE(out_dtype == LMV_DTYPE_BF16 || out_dtype == LMV_DTYPE_F32, "forward: output dtype");
   const lmv_config& c = plan->cfg;
   const int chunk = (plan->chunk > 0 && plan->chunk < B) ? plan->chunk : B;
-  const size_t xe = x_dtype == LMV_DTYPE_F32 ? 4 : 2, oe = out_dtype == LMV_DTYPE_F32 ? 4 : 2;
+  const size_t xe = x_dtype == LMV_DTYPE_F32 ? 4 : (x_dtype == LMV_DTYPE_BF16 ? 2 : 1), oe = out_dtype == LMV_DTYPE_F32 ? 4 : 2;
   Geo g;
   int rc = geometry(c, H, W, &g);
   if (rc) return rc;
@@ -1064,6 +1085,7 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   else if (n == "fused_mlp_wide") plan->fused_mlp_wide = value ? 1 : 0;
   else if (n == "fused_self_attn") plan->fused_self_attn = value ? 1 : 0;
   else if (n == "direct_stem") plan->direct_stem = value ? 1 : 0;
+  else if (n == "implicit_conv") plan->implicit_conv = value ? 1 : 0;
   else if (n == "fused_dca") plan->fused_dca = value ? 1 : 0;
   else if (n == "dca_pipe") plan->dca_pipe = value ? 1 : 0;
   else return fail(LMV_ERR_INVALID, "set_option: unknown option " + n);
@@ -1076,6 +1098,17 @@ int lmv_plan_set_tap(lmv_plan* plan, int stage, int block, void* x_tokens_out, v
   if (rc) return rc;
   plan->tap_stage = stage; plan->tap_block = block; plan->tap_x = x_tokens_out; plan->tap_c = c_out;
   plan->cache.clear();
+  return LMV_OK;
+}
+int lmv_plan_set_input_norm(lmv_plan* plan, const float* mean3, const float* std3) {
+  if (!plan || !mean3 || !std3) return fail(LMV_ERR_INVALID, "set_input_norm: null argument");
+  if (plan->cfg.in_chans != 3) return fail(LMV_ERR_UNSUPPORTED, "set_input_norm: the 8-bit input path needs 3 input channels");
+  for (int i = 0; i < 3; ++i)
+    if (!(std3[i] > 0.f) || !std::isfinite(mean3[i]) || !std::isfinite(std3[i])) return fail(LMV_ERR_INVALID, "set_input_norm: std must be positive and finite");
+  int rc = harvest_profile(plan);
+  if (rc) return rc;
+  for (int i = 0; i < 3; ++i) { plan->in_mean[i] = mean3[i]; plan->in_std[i] = std3[i]; }
+  plan->cache.clear();   // the stem launch carries the constants by value
   return LMV_OK;
 }
 int lmv_plan_set_debug_simt(lmv_plan* plan, int enable) {
@@ -1313,6 +1346,22 @@ int lmv_stem_conv1(const void* x, int x_dtype, const void* w, const float* bias,
   if (!x || !w || !bias || !out) return fail(LMV_ERR_INVALID, "stem_conv1: null pointer");
   StemArgs a{x, x_dtype, static_cast<bf16*>(out), B, Cin, H, W};
   return stem_conv1_run(a, static_cast<const bf16*>(w), bias, C1, static_cast<cudaStream_t>(stream));
+}
+
+int lmv_conv3x3s2(const void* in, const void* w, const float* bias, void* out, int B, int H, int W, int T, int Cin, int Cout,
+                  int out_rows_per_image, void* stream) {
+  if (!in || !w || !out) return fail(LMV_ERR_INVALID, "conv3x3s2: null pointer");
+  if (!gemm_conv_supported(H, W, Cin)) return fail(LMV_ERR_UNSUPPORTED, "conv3x3s2: needs an output width <= 128 and Cin % 8 == 0");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  GemmArgs a;
+  a.A = static_cast<const bf16*>(in); a.W = static_cast<const bf16*>(w); a.ldw = 9 * Cin; a.M = B * Ho * Wo; a.N = Cout; a.K = 9 * Cin;
+  a.bias = bias; a.out = out; a.ldc = Cout;
+  if (out_rows_per_image > 0) { a.grp_rows = Ho * Wo; a.grp_stride = out_rows_per_image; }
+  a.conv_B = B; a.conv_H = H; a.conv_W = W; a.conv_T = T; a.conv_C = Cin;
+  GemmOp op;
+  int rc = gemm_prepare(a, &op);
+  if (rc) return rc;
+  return gemm_run(op, static_cast<cudaStream_t>(stream));
 }
 
 int lmv_im2col_3x3s2(const void* in, void* out, int B, int H, int W, int T, int C, void* stream) {

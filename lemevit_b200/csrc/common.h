@@ -39,8 +39,10 @@ int fail(int code, const std::string& msg);  // records msg, returns code
 
 // Encode a tiled bf16 tensor map.  dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 // swizzle_bytes in {0, 32, 64, 128}.  Returns 0 on success.
+// elem_strides (optional, innermost first): traversal stride per dimension; dimension i then delivers ceil(box[i] / elem_strides[i])
+// elements (the strided gather of the implicit-GEMM convolutions).
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box, int swizzle_bytes);
+                     const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides = nullptr);
 
 int device_sm_count();   // SM count of the CURRENT device (cached per device)
 
@@ -111,6 +113,11 @@ struct GemmArgs {
   // optional row remap of the OUTPUT (and residual): row r -> (r / grp_rows) * grp_stride + r % grp_rows
   int grp_rows = 0, grp_stride = 0;
   int force_bn = 0;                  // test hook: override the tile-N heuristic
+  // Implicit-GEMM convolution 3x3 / stride 2 / pad 1 (conv_C > 0): A is not a matrix but the token-major activation
+  // [conv_B, conv_T, conv_C] (first conv_H * conv_W rows of every image, row = y * W + x); the GEMM rows are the output pixels
+  // (b, oy, ox), M = conv_B * ceil(H/2) * ceil(W/2), K = 9 * conv_C with k = (ky * 3 + kx) * C + ci — the layout of the
+  // materialised patch matrix (im2col_3x3s2_kernel) this replaces, so W [N, 9C] is used as packed.  lda is ignored.
+  int conv_B = 0, conv_H = 0, conv_W = 0, conv_T = 0, conv_C = 0;
   // LayerNorm folded into the GEMM (LN(y) W'^T = r (y W'^T - mu colsum(W'))): A holds the RAW rows y,
   // ln_stats[row] = (sum_k y, sum_k y^2) of A row `row`, ln_colsum[n] = sum_k W'[n,k] (of the bf16 weights).
   const float* ln_stats = nullptr;   // [M][2] or null
@@ -136,16 +143,24 @@ struct GemmParams {
   int ln_parts;
   float* stats_out;
   int prefetch_res;
+  // implicit-GEMM convolution (conv != 0): an M tile is `tile_rows` <= 128 output pixels = conv_bb whole images (maps of <= 64
+  // pixels) or conv_bh output rows of one image (conv_tpi such tiles per image); K blocks walk (tap, 64-channel slice)
+  int conv, conv_cpt, conv_bb, conv_bh, conv_tpi, conv_Ho, conv_Wo, conv_HoWo;
+  int tile_rows;        // GEMM rows per M tile (128 unless conv)
+  uint32_t tx_bytes;    // bytes one pipeline stage receives (A box + W box)
+  int tma_out;   // the fast-path epilogue leaves through TMA tile stores (tmC) instead of per-lane global stores
 };
 
 struct GemmOp {
   CUtensorMap tmA, tmB, tmR;   // tmR: residual tile, only used for L2 prefetch
+  CUtensorMap tmC;             // output, 32 x 32 boxes (64-byte rows, 64B swizzle): p.tma_out
   GemmParams p;
   int grid = 0;
   int smem_bytes = 0;
 };
 
 int gemm_stats_parts(int N, int force_bn = 0);   // partial-sum slots per row that stats_out receives
+bool gemm_conv_supported(int H, int W, int C);   // implicit-GEMM conv3x3/s2/p1 on [B, T, C] tokens (GemmArgs::conv_*)
 int gemm_prepare(const GemmArgs& a, GemmOp* op);
 int gemm_run(const GemmOp& op, cudaStream_t stream);
 int gemm_simt_run(const GemmArgs& a, cudaStream_t stream);  // bring-up cross-check kernel (tests only)

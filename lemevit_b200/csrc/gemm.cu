@@ -31,6 +31,7 @@ constexpr int kMaxStages = 8;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kStageF32 = 32 * 32 * 4;   // per-warp transpose buffer: 32 rows x 32 fp32
+constexpr int kStageOut = 2 * 32 * 64;   // per-warp output staging of the TMA-store epilogue: two 32-row x 64-byte (32 bf16) boxes
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -141,12 +142,13 @@ constexpr int kEpiLn = 1, kEpiGelu = 2, kEpiRes = 4, kEpiStats = 8;
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   SmemCtrl* ctrl = reinterpret_cast<SmemCtrl*>(smem);
-  uint8_t* tiles = smem + 1024 + kEpiWarps * kStageF32;   // [ctrl 1 KB][8 x 4 KB transpose buffers][stage ring]
+  // [ctrl 1 KB][8 x 4 KB transpose buffers][8 x 4 KB output staging (TMA-store epilogue only)][stage ring]
+  uint8_t* tiles = smem + 1024 + kEpiWarps * kStageF32 + (p.tma_out ? kEpiWarps * kStageOut : 0);
   const int a_bytes = BM * BK * 2;
   const int stage_bytes = a_bytes + p.BN * BK * 2;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the role branches stay uniform
@@ -164,6 +166,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) tma_prefetch_desc(&tmC);
   }
   if (warp == 1) {
     tmem_alloc(&ctrl->tmem_base, 512);
@@ -187,14 +190,31 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
         // pull the residual tile into L2 while the mainloop of this tile runs: the epilogue reads it ~2 tiles later
         if (p.prefetch_res) tma_prefetch_l2_2d(&tmR, n_blk * p.BN, m_blk * BM);
+        // implicit convolution: the tile's first image / output row; K block kb = (tap, 64-channel slice)
+        int cb0 = 0, cy0 = 0;
+        if (p.conv) {
+          if (p.conv_bb > 1) { cb0 = m_blk * p.conv_bb; }
+          else { cb0 = m_blk / p.conv_tpi; cy0 = (m_blk - cb0 * p.conv_tpi) * p.conv_bh; }
+        }
+        int tap = 0, cs = 0;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           TR(1)
           mbar_wait(&ctrl->empty[stage], phase ^ 1u, 1);
           TR(0)
           uint8_t* sa = tiles + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&ctrl->full[stage], (uint32_t)stage_bytes);
-          tma_load_2d(sa, &tmA, &ctrl->full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + a_bytes, &tmB, &ctrl->full[stage], kb * BK, n_blk * p.BN);
+          mbar_expect_tx(&ctrl->full[stage], p.tx_bytes);
+          if (p.conv) {
+            // A: input pixels (2 oy + ky - 1, 2 ox + kx - 1) of the tile's output pixels: a stride-2 box whose out-of-range
+            // coordinates (the padding ring, channels beyond C in the last slice of a tap) arrive as zeros; W: the same slice of
+            // tap `tap` from the [N][9][C] view of the packed weights (zero beyond C as well, so the padded k contribute nothing)
+            const int ky = tap / 3, kx = tap - 3 * ky;
+            tma_load_4d(sa, &tmA, &ctrl->full[stage], cs * BK, kx - 1, 2 * cy0 + ky - 1, cb0);
+            tma_load_3d(sa + a_bytes, &tmB, &ctrl->full[stage], cs * BK, tap, n_blk * p.BN);
+            if (++cs == p.conv_cpt) { cs = 0; ++tap; }
+          } else {
+            tma_load_2d(sa, &tmA, &ctrl->full[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sa + a_bytes, &tmB, &ctrl->full[stage], kb * BK, n_blk * p.BN);
+          }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -251,6 +271,13 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool vec_ok = (p.ldc % 8 == 0);
     const bool fast_ok = vec_ok && !p.out_fp32;
     float* stg = reinterpret_cast<float*>(smem + 1024 + (size_t)(warp - 2) * kStageF32);
+    // TMA-store epilogue: the bf16 results of a chunk are staged as a 32-row x 64-byte box (64B swizzle: the 16-byte slot of
+    // (row, j) is j ^ ((row >> 1) & 3), so the eight rows x four slots a warp writes per pass cover 512 contiguous bytes once) and
+    // leave through one cp.async.bulk.tensor store per chunk.  The warp's global stores otherwise queue in the LSU in front of its
+    // next bias / colsum / residual loads (profiles/r02_gemm_role_trace.txt: 44 % of the epilogue time sat in the load-issue phase).
+    const bool tma_out = p.tma_out != 0;
+    uint8_t* ostg = smem + 1024 + kEpiWarps * kStageF32 + (size_t)(warp - 2) * kStageOut;
+    int obuf = 0;
     const int lr = lane >> 2, lc = (lane & 3) * 8;   // transposed domain: this lane owns rows it*8 + lr, columns lc .. lc+7
     int as = 0;
     uint32_t aphase = 0;
@@ -260,7 +287,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
     for (int k = 0; k < 4; ++k) nst[k] = make_float2(0.f, 0.f);
     auto load_stats = [&](int tile) {
-      const int row = (tile / p.tiles_n) * BM + q * 32 + lane;
+      const int row = (tile / p.tiles_n) * BM + q * 32 + lane;   // (LayerNorm fold: never an implicit convolution)
       if (row < p.M) {
         const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + (long long)row * p.ln_parts;
 #pragma unroll
@@ -272,6 +299,18 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     TR_INIT
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
+      // dense GEMM row of the tile's first row and the number of rows it really has (implicit convolutions: short tiles)
+      int row_base = m_blk * BM, row_valid = min(BM, p.M - row_base);
+      if (p.conv) {
+        if (p.conv_bb > 1) {
+          row_base = m_blk * p.tile_rows;
+          row_valid = min(p.tile_rows, p.M - row_base);
+        } else {
+          const int cb = m_blk / p.conv_tpi, cy0 = (m_blk - cb * p.conv_tpi) * p.conv_bh;
+          row_base = cb * p.conv_HoWo + cy0 * p.conv_Wo;
+          row_valid = min(p.conv_bh, p.conv_Ho - cy0) * p.conv_Wo;
+        }
+      }
       long long orow_t[4];
       bool rok_t[4];
       float lnr[4], lnn[4];   // LayerNorm fold: v = r * acc + (-r * mu) * colsum[n] + bias[n]
@@ -286,8 +325,8 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int rr = m_blk * BM + q * 32 + it * 8 + lr;
-        rok_t[it] = rr < p.M;
+        const int rr = row_base + q * 32 + it * 8 + lr;
+        rok_t[it] = q * 32 + it * 8 + lr < row_valid;
         orow_t[it] = (p.grp_rows > 0) ? (long long)(rr / p.grp_rows) * p.grp_stride + (rr % p.grp_rows) : (long long)rr;
         lnr[it] = f_ln ? __shfl_sync(0xffffffffu, own_r, it * 8 + lr) : 1.f;
         lnn[it] = f_ln ? __shfl_sync(0xffffffffu, own_n, it * 8 + lr) : 0.f;
@@ -334,10 +373,10 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tmem_ld_wait();
         TR(1)
         if (!fast) {
-          const int row = m_blk * BM + q * 32 + lane;
+          const int row = row_base + q * 32 + lane;
           long long orow = row;
           if (p.grp_rows > 0) orow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows);
-          epilogue_chunk(p, r, row, orow, col0, vec_ok, own_r, own_n);
+          epilogue_chunk(p, r, q * 32 + lane < row_valid ? row : p.M, orow, col0, vec_ok, own_r, own_n);
           loaded = false;
           continue;
         }
@@ -410,7 +449,24 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
             st2[it] = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, st2[it]))));
             st2[it] = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, fmaf(f3.y, f3.y, st2[it]))));
           }
-          if (rok_t[it]) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow_t[it] * (long long)p.ldc + col0 + lc) = w;
+          if (tma_out) {
+            if (it == 0) {   // the box staged two chunks ago must have been read out before its buffer is overwritten
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+            }
+            *reinterpret_cast<uint4*>(ostg + obuf * (kStageOut / 2) + rl * 64 + (((lane & 3) ^ ((rl >> 1) & 3)) << 4)) = w;
+          } else if (rok_t[it]) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + orow_t[it] * (long long)p.ldc + col0 + lc) = w;
+          }
+        }
+        if (tma_out) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, ostg + obuf * (kStageOut / 2), col0, row_base + q * 32);   // rows >= M are clipped
+            tma_store_commit();
+          }
+          obuf ^= 1;
         }
         TR(3)   // transposed reads + math + global stores
       }
@@ -439,6 +495,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (as == 0) aphase ^= 1u;
       TR(5)   // accumulator release + statistics partials
     }
+    if (tma_out && lane == 0) tma_store_wait<0>();   // every tile store has been performed before the CTA (and its staging memory) goes away
     TR_FLUSH
   }
   tc_fence_before();
@@ -495,10 +552,16 @@ int gemm_stats_parts(int N, int force_bn) {
   return 2 * ((N + bn - 1) / bn);
 }
 
+bool gemm_conv_supported(int H, int W, int C) {
+  const int Wo = (W + 1) / 2;
+  return H >= 1 && W >= 1 && Wo <= 128 && C >= 8 && C % 8 == 0;
+}
+
 int gemm_prepare(const GemmArgs& a, GemmOp* op) {
+  const bool conv = a.conv_C > 0;
   LMV_REQUIRE(a.A && a.W && a.out, "gemm: null pointer");
   LMV_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: empty problem");
-  LMV_REQUIRE(a.K % 8 == 0 && a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: K, lda, ldw must be multiples of 8 (16-byte TMA strides)");
+  LMV_REQUIRE(a.K % 8 == 0 && (conv || a.lda % 8 == 0) && a.ldw % 8 == 0, "gemm: K, lda, ldw must be multiples of 8 (16-byte TMA strides)");
   LMV_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0, "gemm: operands must be 16-byte aligned");
   LMV_REQUIRE((reinterpret_cast<uintptr_t>(a.out) & 15) == 0, "gemm: output must be 16-byte aligned");
   LMV_REQUIRE(a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
@@ -509,8 +572,41 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   p.tiles_m = (a.M + BM - 1) / BM;
   p.tiles_n = (a.N + p.BN - 1) / p.BN;
   p.k_blocks = (a.K + BK - 1) / BK;
+  p.conv = 0; p.conv_cpt = 0; p.conv_bb = 0; p.conv_bh = 0; p.conv_tpi = 0; p.conv_Ho = 0; p.conv_Wo = 0; p.conv_HoWo = 0;
+  p.tile_rows = BM;
   const int stage_bytes = BM * BK * 2 + p.BN * BK * 2;
-  p.num_stages = std::min(kMaxStages, (kSmemLimit - 2048 - kEpiWarps * kStageF32) / stage_bytes);
+  p.tx_bytes = (uint32_t)stage_bytes;
+  if (conv) {
+    const int Ho = (a.conv_H + 1) / 2, Wo = (a.conv_W + 1) / 2, HoWo = Ho * Wo;
+    LMV_REQUIRE(gemm_conv_supported(a.conv_H, a.conv_W, a.conv_C), "gemm(conv): needs an output width <= 128 and C % 8 == 0");
+    LMV_REQUIRE(a.M == a.conv_B * HoWo && a.K == 9 * a.conv_C && a.ldw == a.K && a.conv_T >= a.conv_H * a.conv_W, "gemm(conv): inconsistent shape");
+    LMV_REQUIRE(!a.ln_stats && !a.stats_out && !a.residual, "gemm(conv): bias / activation epilogue only");
+    p.conv = 1;
+    p.conv_cpt = (a.conv_C + BK - 1) / BK;
+    p.k_blocks = 9 * p.conv_cpt;
+    p.conv_Ho = Ho; p.conv_Wo = Wo; p.conv_HoWo = HoWo;
+    if (HoWo <= BM / 2) {           // several whole images per tile
+      p.conv_bb = BM / HoWo; p.conv_bh = Ho; p.conv_tpi = 1;
+      p.tile_rows = p.conv_bb * HoWo;
+      p.tiles_m = (a.conv_B + p.conv_bb - 1) / p.conv_bb;
+    } else {                        // equal-height groups of output rows of one image
+      const int max_bh = std::max(1, BM / Wo);
+      p.conv_tpi = (Ho + max_bh - 1) / max_bh;
+      p.conv_bh = (Ho + p.conv_tpi - 1) / p.conv_tpi;
+      p.conv_bb = 1;
+      p.tile_rows = p.conv_bh * Wo;
+      p.tiles_m = a.conv_B * p.conv_tpi;
+    }
+    p.tx_bytes = (uint32_t)(p.tile_rows * BK * 2 + p.BN * BK * 2);
+  }
+  // TMA-store epilogue (8 x 4 KB of output staging) whenever the output is a dense-enough bf16 matrix and the staging does not
+  // cost the ring a stage it needs (BN = 256 tiles keep 4 stages and the per-lane stores); LMV_GEMM_TMA_OUT=0/1 overrides.
+  const int stages_plain = std::min(kMaxStages, (kSmemLimit - 2048 - kEpiWarps * kStageF32) / stage_bytes);
+  const int stages_tma = std::min(kMaxStages, (kSmemLimit - 2048 - kEpiWarps * (kStageF32 + kStageOut)) / stage_bytes);
+  bool tma_out = !conv && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && stages_tma >= 2 && stages_tma >= std::min(stages_plain, 4);
+  if (const char* e = getenv("LMV_GEMM_TMA_OUT")) tma_out = tma_out && e[0] != '0';
+  p.tma_out = tma_out ? 1 : 0;
+  p.num_stages = tma_out ? stages_tma : stages_plain;
   p.bias = a.bias; p.residual = a.residual; p.out = a.out;
   p.ldc = a.ldc; p.out_fp32 = a.out_fp32; p.act = a.act;
   p.grp_rows = a.grp_rows; p.grp_stride = a.grp_stride;
@@ -522,25 +618,49 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   p.stats_out = a.stats_out;
   LMV_REQUIRE(a.stats_out == nullptr || (a.N % 32 == 0 && a.ldc % 8 == 0 && !a.out_fp32),
               "gemm: stats_out needs N % 32 == 0, ldc % 8 == 0 and a bf16 output");
-  op->smem_bytes = 2048 + kEpiWarps * kStageF32 + p.num_stages * stage_bytes;
+  op->smem_bytes = 2048 + kEpiWarps * (kStageF32 + (p.tma_out ? kStageOut : 0)) + p.num_stages * stage_bytes;
   op->grid = std::min(p.tiles_m * p.tiles_n, device_sm_count());
-  {
-    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
-    uint64_t strides[1] = {(uint64_t)a.lda * 2};
-    uint32_t box[2] = {BK, BM};
-    int rc = encode_tmap_bf16(&op->tmA, a.A, 2, dims, strides, box, 128);
+  if (conv) {
+    // activation [B][T rows of C] seen as {C, W, H, B}; the box walks W and H with stride 2 from (kx - 1, 2 oy0 + ky - 1)
+    const int C = a.conv_C;
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)a.conv_W, (uint64_t)a.conv_H, (uint64_t)a.conv_B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)a.conv_W * C * 2, (uint64_t)a.conv_T * C * 2};
+    uint32_t box[4] = {BK, (uint32_t)(2 * p.conv_Wo), (uint32_t)(2 * p.conv_bh), (uint32_t)p.conv_bb};
+    uint32_t estr[4] = {1, 2, 2, 1};
+    int rc = encode_tmap_bf16(&op->tmA, a.A, 4, dims, strides, box, 128, estr);
     if (rc) return rc;
+    uint64_t wdims[3] = {(uint64_t)C, 9, (uint64_t)a.N};
+    uint64_t wstrides[2] = {(uint64_t)C * 2, (uint64_t)9 * C * 2};
+    uint32_t wbox[3] = {BK, 1, (uint32_t)p.BN};
+    rc = encode_tmap_bf16(&op->tmB, a.W, 3, wdims, wstrides, wbox, 128);
+    if (rc) return rc;
+  } else {
+    {
+      uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+      uint64_t strides[1] = {(uint64_t)a.lda * 2};
+      uint32_t box[2] = {BK, BM};
+      int rc = encode_tmap_bf16(&op->tmA, a.A, 2, dims, strides, box, 128);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+      uint64_t strides[1] = {(uint64_t)a.ldw * 2};
+      uint32_t box[2] = {BK, (uint32_t)p.BN};
+      int rc = encode_tmap_bf16(&op->tmB, a.W, 2, dims, strides, box, 128);
+      if (rc) return rc;
+    }
   }
-  {
-    uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
-    uint64_t strides[1] = {(uint64_t)a.ldw * 2};
-    uint32_t box[2] = {BK, (uint32_t)p.BN};
-    int rc = encode_tmap_bf16(&op->tmB, a.W, 2, dims, strides, box, 128);
+  op->tmC = op->tmA;
+  if (p.tma_out) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
+    uint64_t strides[1] = {(uint64_t)a.ldc * 2};
+    uint32_t box[2] = {32, 32};
+    int rc = encode_tmap_bf16(&op->tmC, a.out, 2, dims, strides, box, 64);
     if (rc) return rc;
   }
   op->tmR = op->tmA;
   p.prefetch_res = 0;
-  if (a.residual && a.grp_rows == 0 && a.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0) {
+  if (!conv && a.residual && a.grp_rows == 0 && a.ldc % 8 == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0) {
     uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M};
     uint64_t strides[1] = {(uint64_t)a.ldc * 2};
     uint32_t box[2] = {(uint32_t)std::min(p.BN, ((a.N + 7) / 8) * 8), BM};
@@ -550,7 +670,7 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   return LMV_OK;
 }
 
-using GemmKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+using GemmKernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
 // the epilogue combinations the LeMeViT schedule uses get their own instantiation; everything else runs the run-time one
 static const struct { int flags; GemmKernel fn; } kGemmVariants[] = {
     {0, gemm_bf16_tn_tcgen05<0>},                                   // bias only (convolutions as GEMM, c-path q/kv)
@@ -577,7 +697,7 @@ int gemm_run(const GemmOp& op, cudaStream_t stream) {
   if (gp.act == 0 || gp.act == 1)
     for (const auto& v : kGemmVariants)
       if (v.flags == flags) { fn = v.fn; break; }
-  LMV_CUDA_OK(launch_kernel(fn, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmA, op.tmB, op.tmR, op.p));
+  LMV_CUDA_OK(launch_kernel(fn, dim3(op.grid), dim3(kThreads), (size_t)(op.smem_bytes), stream, op.tmA, op.tmB, op.tmR, op.tmC, op.p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;
 }

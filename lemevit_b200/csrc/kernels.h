@@ -65,10 +65,12 @@ size_t attention_meta_workspace(const AttnArgs& a);
 int attention_meta_run(const AttnArgs& a, void* workspace, size_t workspace_bytes, cudaStream_t s);
 
 struct StemArgs {
-  const void* x;  // NCHW, f32 or bf16
+  const void* x;  // NCHW, f32 or bf16; stem_conv1 only: 8-bit pixels, LMV_DTYPE_U8 [B,3,H,W] / LMV_DTYPE_U8_NHWC [B,H,W,3]
   int x_dtype;
   bf16* out;      // patches [B*Ho*Wo, Kp], Kp = round_up(9*Cin, 8), k = ci*9 + ky*3 + kx
   int B, Cin, H, W;
+  float mean[3] = {0.485f * 255.f, 0.456f * 255.f, 0.406f * 255.f};   // 8-bit input: bf16((u8 - mean[c]) / std[c])
+  float std[3] = {0.229f * 255.f, 0.224f * 255.f, 0.225f * 255.f};
 };
 int stem_im2col_run(const StemArgs& a, cudaStream_t s);
 // direct first stem convolution + folded BN + GELU: a.out receives token-major [B, Ho*Wo, C1] (no im2col detour)

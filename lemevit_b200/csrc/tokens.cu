@@ -350,19 +350,31 @@ stem_im2col_kernel(const T* __restrict__ x, bf16* __restrict__ out, int B, int C
 // results leave as one contiguous 2*C1-byte run (neighbouring threads -> neighbouring runs).
 // ------------------------------------------------------------------------------------------------
 
-template <typename T, int C1>
+struct StemNorm { float mean[3], std[3]; };
+
+// LAYOUT 0: x[B, 3, H, W] of T (float | bf16 | uint8_t); 1: x[B, H, W, 3] uint8_t.  8-bit pixels go through a 3 x 256-entry table of
+// bf16((v - mean[c]) / std[c]) built once per CTA with IEEE subtraction / division: the same bits as the torch expression
+// x.float().sub_(mean).div_(std).to(bfloat16), without a cvt / sub / div per tap.
+template <typename T, int C1, int LAYOUT>
 __global__ void __launch_bounds__(128)
 stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp], k = ci*9 + ky*3 + kx*/, const float* __restrict__ bias,
-                  bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int Kp) {
+                  bf16* __restrict__ out, int B, int H, int W, int Ho, int Wo, int Kp, StemNorm nrm) {
+  constexpr bool kU8 = sizeof(T) == 1;
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float4 sw[27 * (C1 / 4)];     // [k][C1]
   __shared__ float4 sb[C1 / 4];
+  __shared__ float lut[kU8 ? 3 * 256 : 1];
   for (int i = threadIdx.x; i < 27 * C1; i += blockDim.x) {
     const int k = i / C1, c = i - k * C1;
     reinterpret_cast<float*>(sw)[i] = __bfloat162float(w[c * Kp + k]);
   }
   for (int i = threadIdx.x; i < C1; i += blockDim.x) reinterpret_cast<float*>(sb)[i] = bias[i];
+  if (kU8)
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+      const int c = i >> 8;
+      lut[i] = __bfloat162float(__float2bfloat16(__fdiv_rn(__fsub_rn((float)(i & 255), nrm.mean[c]), nrm.std[c])));
+    }
   __syncthreads();
   // two output pixels per thread: every broadcast weight vector read from shared memory feeds 8 FMAs instead of 4
   const long long total = (long long)B * Ho * Wo;
@@ -381,8 +393,16 @@ stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp]
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-          in[q][ci * 9 + ky * 3 + kx] =
-              (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ld_as_float<T>(x + (((long long)b * 3 + ci) * H + iy) * W + ix) : 0.f;
+          float v = 0.f;     // the zero padding pads the NORMALISED image
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            if constexpr (kU8) {
+              const long long idx = LAYOUT == 1 ? (((long long)b * H + iy) * W + ix) * 3 + ci : (((long long)b * 3 + ci) * H + iy) * W + ix;
+              v = lut[ci * 256 + (int)__ldg(reinterpret_cast<const unsigned char*>(x) + idx)];
+            } else {
+              v = ld_as_float<T>(x + (((long long)b * 3 + ci) * H + iy) * W + ix);
+            }
+          }
+          in[q][ci * 9 + ky * 3 + kx] = v;
         }
   }
   float4 acc[2][C1 / 4];
@@ -640,15 +660,25 @@ int stem_conv1_run(const StemArgs& a, const bf16* w, const float* bias, int C1, 
   const long long total = (long long)a.B * Ho * Wo;
   if (total == 0) return LMV_OK;
   const unsigned grid = blocks_for((total + 1) / 2, 128);   // two output pixels per thread
-  if (a.x_dtype == LMV_DTYPE_F32) {
-    if (C1 == 32) LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<float, 32>, dim3(grid), dim3(128), (size_t)(0), s, (const float*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
-    else LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<float, 48>, dim3(grid), dim3(128), (size_t)(0), s, (const float*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
-  } else {
-    if (C1 == 32) LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<bf16, 32>, dim3(grid), dim3(128), (size_t)(0), s, (const bf16*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
-    else LMV_CUDA_OK(launch_kernel(stem_conv1_kernel<bf16, 48>, dim3(grid), dim3(128), (size_t)(0), s, (const bf16*)a.x, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp));
+  StemNorm nrm;
+  for (int i = 0; i < 3; ++i) { nrm.mean[i] = a.mean[i]; nrm.std[i] = a.std[i]; }
+  auto go = [&](auto kern, auto* xp) -> int {
+    LMV_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(128), (size_t)(0), s, xp, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp, nrm));
+    LMV_CUDA_OK(cudaGetLastError());
+    return LMV_OK;
+  };
+  switch (a.x_dtype) {
+    case LMV_DTYPE_F32:
+      return C1 == 32 ? go(stem_conv1_kernel<float, 32, 0>, (const float*)a.x) : go(stem_conv1_kernel<float, 48, 0>, (const float*)a.x);
+    case LMV_DTYPE_BF16:
+      return C1 == 32 ? go(stem_conv1_kernel<bf16, 32, 0>, (const bf16*)a.x) : go(stem_conv1_kernel<bf16, 48, 0>, (const bf16*)a.x);
+    case LMV_DTYPE_U8:
+      return C1 == 32 ? go(stem_conv1_kernel<uint8_t, 32, 0>, (const uint8_t*)a.x) : go(stem_conv1_kernel<uint8_t, 48, 0>, (const uint8_t*)a.x);
+    case LMV_DTYPE_U8_NHWC:
+      return C1 == 32 ? go(stem_conv1_kernel<uint8_t, 32, 1>, (const uint8_t*)a.x) : go(stem_conv1_kernel<uint8_t, 48, 1>, (const uint8_t*)a.x);
+    default:
+      return fail(LMV_ERR_INVALID, "stem_conv1: x dtype");
   }
-  LMV_CUDA_OK(cudaGetLastError());
-  return LMV_OK;
 }
 
 int im2col_run(const Im2colArgs& a, cudaStream_t s) {

@@ -142,12 +142,38 @@ class Engine:
         return self._ws
 
     def _prep_input(self, x: torch.Tensor) -> torch.Tensor:
+        """Float input: contiguous NCHW (bf16 / fp32; anything else is cast to bf16).  uint8 input (raw pixels, normalised inside
+        the stem kernel, see set_input_norm): [B, 3, H, W] planar (timm fast_collate), the same in channels_last memory, or
+        [B, H, W, 3] interleaved — the latter two are handed to the kernel as they lie in memory, seen through an NCHW view."""
         require_cuda(x)
+        if x.dtype == torch.uint8:
+            if x.dim() != 4 or self.in_chans != 3 or 3 not in (x.shape[1], x.shape[3]):
+                raise RuntimeError(f"expected 8-bit input [B, 3, H, W] or [B, H, W, 3] (in_chans = {self.in_chans}), got {tuple(x.shape)}")
+            if x.shape[1] != 3:                                   # [B, H, W, 3]
+                return x.contiguous().permute(0, 3, 1, 2)
+            if x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last):
+                return x
+            return x.contiguous()
         if x.dim() != 4 or x.shape[1] != self.in_chans:
             raise RuntimeError(f"expected input [B, {self.in_chans}, H, W], got {tuple(x.shape)}")
         if x.dtype not in _TORCH2LMV:
             x = x.to(torch.bfloat16)
         return x.contiguous()      # NCHW; channels_last inputs are re-laid out here (benchmark.py --channels-last)
+
+    @staticmethod
+    def _x_code(x: torch.Tensor) -> int:
+        """LMV_DTYPE_* of a tensor that went through _prep_input."""
+        if x.dtype == torch.uint8:
+            return _native.DTYPE_U8 if x.is_contiguous() else _native.DTYPE_U8_NHWC
+        return _TORCH2LMV[x.dtype]
+
+    def set_input_norm(self, mean, std):
+        """Per-channel mean / std (pixel units, 0..255) of the 8-bit input path: the stem computes
+        bf16((float(u8) - mean[c]) / std[c]) per tap, the bits of ``x.float().sub_(mean).div_(std).to(torch.bfloat16)``."""
+        m = (C.c_float * 3)(*[float(v) for v in mean])
+        s = (C.c_float * 3)(*[float(v) for v in std])
+        _native.check(self.lib.lmv_plan_set_input_norm(self._plan, m, s))
+        self._invalidate_graphs()
 
     def launch_count(self, B: int, H: int, W: int) -> int:
         if not self.backbone and self.lanes > 1 and B >= self.lane_min_batch and B % self.lanes == 0:
@@ -202,7 +228,7 @@ class Engine:
 
             def launch(xi, ci, fi, oi, nb, ws, stream):
                 _native.check(self.lib.lmv_forward_cls_features(
-                    self._plan, xi.data_ptr(), _TORCH2LMV[x.dtype], nb, H, W, ci.data_ptr() if ci is not None else None,
+                    self._plan, xi.data_ptr(), self._x_code(x), nb, H, W, ci.data_ptr() if ci is not None else None,
                     ws.data_ptr(), ws.numel(), fi.data_ptr() if fi is not None else None,
                     oi.data_ptr() if oi is not None else None, _TORCH2LMV[oi.dtype] if oi is not None else _native.DTYPE_BF16,
                     stream.cuda_stream))
@@ -252,7 +278,7 @@ class Engine:
                 outs = [torch.empty(s, dtype=out_dtype, device=self.device) for s in self.out_shapes(B, H, W)]
             ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _native.check(self.lib.lmv_forward_features(self._plan, x.data_ptr(), _TORCH2LMV[x.dtype], B, H, W,
+            _native.check(self.lib.lmv_forward_features(self._plan, x.data_ptr(), self._x_code(x), B, H, W,
                                                         ws.data_ptr(), ws.numel(), ptrs, len(outs),
                                                         _TORCH2LMV[outs[0].dtype], stream))
         return list(outs)
@@ -271,7 +297,7 @@ class Engine:
         raises once the engine was closed or the graph evicted — it never runs on memory that has been given back."""
         self._check_open()
         x = self._prep_input(x)
-        key = (tuple(x.shape), x.dtype, out_dtype)
+        key = (tuple(x.shape), x.dtype, self._x_code(x), out_dtype)
         if key not in self._graphs:
             B, _, H, W = x.shape
             static_x = x.clone()

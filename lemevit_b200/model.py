@@ -268,8 +268,23 @@ class LeMeViT(nn.Module):
                          mlp_ratios=self.mlp_ratios, attn_type=self.attn_type, head_dim=self.head_dim,
                          queries_len=self.queries_len, num_classes=self.num_classes, in_chans=self.in_chans,
                          backbone=self.backbone_mode, device=device, chunk=self.native_chunk)
+            norm = self.__dict__.get("_input_norm")
+            if norm is not None:
+                eng.set_input_norm(*norm)
             self._engines[key] = (eng, sig)
         return eng
+
+    def set_input_norm(self, mean, std):
+        """Mean / std (per channel, pixel units 0..255) applied to ``torch.uint8`` inputs inside the first stem convolution:
+        ``model(x_u8)`` == ``model(((x_u8.float() - mean) / std).to(bfloat16))`` with x_u8 ``[B, 3, H, W]`` (planar or
+        channels_last) or ``[B, H, W, 3]``.  This is the GPU half of the timm prefetcher the reference's training and validation
+        loaders run (main.py:399-428, mean / std x 255 of ``default_cfg``); default: the ImageNet constants of ``_cfg()``."""
+        mean, std = [float(v) for v in mean], [float(v) for v in std]
+        if len(mean) != 3 or len(std) != 3:
+            raise ValueError("set_input_norm: three channels expected")
+        self.__dict__["_input_norm"] = (mean, std)
+        for eng, _ in list(self.__dict__.get("_engines", {}).values()):
+            eng.set_input_norm(mean, std)
 
     def __deepcopy__(self, memo):
         # ModelEmaV2 deep-copies the model (reference main.py:316): copy parameters, never the native handles

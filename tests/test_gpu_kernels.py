@@ -445,6 +445,46 @@ def test_conv3x3s2_via_im2col_gemm(B, H, W, C, Co, extra):
     assert G.rel_err(out, ref) < TOL
 
 
+CONV_CASES = [
+    # (B, H, W, Cin, Cout, extra rows per input image, output rows per image (0 = dense))
+    (3, 112, 112, 48, 96, 0, 0),      # stem conv 2 (Base): 56-wide output rows, 2 per tile, K blocks padded 48 -> 64
+    (2, 56, 56, 96, 192, 0, 0),       # stage 2 downsample: 96 = 64 + 32 channels per tap
+    (3, 28, 28, 192, 384, 0, 212),    # stage 3 downsample into a unified [B, 196 + 16, C] buffer
+    (5, 14, 14, 384, 512, 16, 65),    # stage 4 downsample: two whole 7x7 images per tile (odd batch), unified input and output
+    (2, 7, 9, 64, 128, 0, 0),         # odd sizes: right / bottom padding, maps smaller than a tile
+    (1, 33, 45, 32, 64, 3, 0),        # rows that do not divide into equal tiles
+    (2, 64, 256, 24, 32, 0, 0),       # 128-wide output rows (512 x 512 input of the stem), one per tile; Cin < 64
+    (7, 2, 2, 8, 32, 0, 0),           # 1 x 1 output maps, many images per tile
+]
+
+
+@pytest.mark.parametrize("B,H,W,C,Co,extra,out_rows", CONV_CASES)
+def test_conv3x3s2_implicit_gemm(B, H, W, C, Co, extra, out_rows):
+    """conv3x3 / stride 2 / pad 1 as an implicit GEMM (strided TMA boxes gather the patch rows; reference: nn.Conv2d(.., 3, 2, 1) +
+    folded BatchNorm, models/lemevit.py:702-703,715-716) against torch.conv2d, and bit-identical to the im2col + GEMM route."""
+    T = H * W + extra
+    tok = _rand(B, T, C)
+    w = torch.randn(Co, C, 3, 3, device="cuda") * (9 * C) ** -0.5
+    b = torch.randn(Co, device="cuda") * 0.1
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    wp = G.bf(w.permute(0, 2, 3, 1).reshape(Co, 9 * C))
+    rows = out_rows if out_rows else Ho * Wo
+    out = torch.full((B, rows, Co), 7.0, dtype=torch.bfloat16, device="cuda")
+    G.ok(G.lib().lmv_conv3x3s2(G.ptr(tok), G.ptr(wp), G.ptr(b), G.ptr(out), B, H, W, T, C, Co, out_rows, G.stream()))
+    x = tok[:, :H * W].float().transpose(1, 2).reshape(B, C, H, W)
+    ref = torch.nn.functional.conv2d(x, G.bf(w).float(), b, stride=2, padding=1).permute(0, 2, 3, 1).reshape(B, Ho * Wo, Co)
+    got = out[:, :Ho * Wo]
+    assert G.rel_err(got, ref) < TOL, G.describe_mismatch(got.float().reshape(-1, Co), ref.reshape(-1, Co), TOL)
+    assert (out[:, Ho * Wo:] == 7.0).all(), "rows behind the image tokens of a unified buffer must stay untouched"
+    patches = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.bfloat16, device="cuda")
+    G.ok(G.lib().lmv_im2col_3x3s2(G.ptr(tok), G.ptr(patches), B, H, W, T, C, G.stream()))
+    via = G.linear(patches, wp, b).reshape(B, Ho * Wo, Co)
+    if C % 16 == 0:   # the K = 16 groups of the MMA instructions then hold the same products in both routes
+        assert torch.equal(via, got), "the implicit GEMM accumulates the same products in the same order"
+    else:
+        assert G.rel_err(got, via.float()) < 2e-3
+
+
 # ---- attention ----------------------------------------------------------------------------------------
 ATTN_CASES = [
     # (B, heads, Lq, Lk)   — S blocks (196/49, and 16x16 meta), D x-branch (N x 16), D/C c-branch (16 x N)

@@ -375,3 +375,43 @@ def test_cpu_input_fails_loudly():
     cfg, sd, m = _build("lemevit_micro", 0)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("layout", ["nchw", "channels_last", "nhwc"])
+def test_uint8_input_is_normalised_inside_the_stem(layout):
+    """8-bit pixels (timm fast_collate NCHW, the same in channels_last memory, or a decoded NHWC image) normalised inside the first
+    stem convolution (reference loader: main.py:399-428) give the bits of normalising in torch and feeding bf16."""
+    cfg, sd, m = _build("lemevit_tiny", 5)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (5, 3, 97, 130), generator=g, dtype=torch.uint8).cuda()     # odd sizes: padded borders on every side
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda").mul(255).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda").mul(255).view(1, 3, 1, 1)
+    ref_in = u8.float().sub_(mean).div_(std).to(torch.bfloat16)
+    y_ref = m(ref_in)
+    x = {"nchw": u8, "channels_last": u8.contiguous(memory_format=torch.channels_last), "nhwc": u8.permute(0, 2, 3, 1).contiguous()}[layout]
+    y = m(x)
+    assert torch.equal(y, y_ref)
+    # a different normalisation reaches the kernel (and cached schedules / graphs are dropped)
+    m.set_input_norm([127.5] * 3, [64.0] * 3)
+    y2 = m(x)
+    assert torch.equal(y2, m(((u8.float() - 127.5) / 64.0).to(torch.bfloat16)))
+    assert not torch.equal(y2, y)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 4, 32, 32, dtype=torch.uint8, device="cuda"))
+
+
+@pytest.mark.parametrize("name,B,res", [("lemevit_tiny", 3, 224), ("lemevit_base", 2, 224)])
+def test_implicit_conv_schedule_is_bit_identical_to_im2col(name, B, res):
+    """The strided convolutions as implicit GEMMs (default) and through the materialised patch matrix give the same logits bit for
+    bit (same products, same accumulation order), with one launch less per convolution."""
+    cfg, sd, m = _build(name, 6)
+    x = Wt.make_input(B, res, res, 6).cuda().to(torch.bfloat16)
+    eng = m.native_engine(x.device)
+    y = m(x)
+    n_impl = eng.launch_count(B, res, res)
+    eng.set_option("implicit_conv", 0)
+    y_im2col = m(x)
+    n_im2col = eng.launch_count(B, res, res)
+    eng.set_option("implicit_conv", 1)
+    assert n_impl == n_im2col - 4
+    assert torch.equal(y, y_im2col)
