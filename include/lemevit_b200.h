@@ -87,7 +87,8 @@ int lmv_plan_set_chunk(lmv_plan* plan, int images_per_chunk);
  *   "fused_dca" (default 1): 'C' / 'D' blocks through the fused cross-attention kernels (lmv_dca_block) where the shape allows it;
  *   "dca_pipe" (default 0): the pipelined schedule of the fused cross-attention kernel where tensor memory allows it (A/B switch;
  *   measured slower than the one-tile-at-a-time schedule on B200);
- *   "implicit_conv" (default 1): strided convolutions as implicit GEMMs (0: im2col kernel + GEMM). */
+ *   "implicit_conv" (default 1): strided convolutions as implicit GEMMs (0: im2col kernel + GEMM);
+ *   "stem_tc" (default 1): the direct first stem convolution on the tcgen05 kernel (0: the CUDA-core kernel). */
 int lmv_plan_set_option(lmv_plan* plan, const char* name, int value);
 /* test hook (block-level parity against the reference's forward hooks): after block `block` of stage `stage` every forward
  * copies the block's outputs to x_tokens_out [B, N, C] bf16 (token-major) and c_out [B, queries_len, C] bf16 (either may be

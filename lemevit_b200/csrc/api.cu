@@ -170,6 +170,7 @@ struct lmv_plan {
   int dca_pipe = 0;      // pipelined schedule of the fused cross-attention kernel: measured 5-10 % SLOWER than one tile at a time
   int direct_stem = 1;
   int implicit_conv = 1;   // strided convolutions as implicit GEMMs (0: im2col kernel + GEMM)
+  int stem_tc = 1;         // first stem convolution on the tcgen05 kernel (0: the CUDA-core direct kernel)
   // 8-bit input path (LMV_DTYPE_U8 / LMV_DTYPE_U8_NHWC): per-channel mean / std in pixel units, lmv_plan_set_input_norm
   float in_mean[3] = {0.485f * 255.f, 0.456f * 255.f, 0.406f * 255.f};
   float in_std[3] = {0.229f * 255.f, 0.224f * 255.f, 0.225f * 255.f};
@@ -679,6 +680,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
     if (!b.simt && plan->direct_stem && stem_conv1_supported(c.in_chans, C0 / 2)) {
       StemArgs sa{nullptr, x_dtype, stem1, B, c.in_chans, H, W};
       for (int i = 0; i < 3; ++i) { sa.mean[i] = plan->in_mean[i]; sa.std[i] = plan->in_std[i]; }
+      sa.tensor_core = plan->stem_tc;
       const bf16* w1 = plan->stem1_w;
       const float* b1 = plan->stem1_b;
       const int C1 = C0 / 2;
@@ -1086,6 +1088,7 @@ int lmv_plan_set_option(lmv_plan* plan, const char* name, int value) {
   else if (n == "fused_self_attn") plan->fused_self_attn = value ? 1 : 0;
   else if (n == "direct_stem") plan->direct_stem = value ? 1 : 0;
   else if (n == "implicit_conv") plan->implicit_conv = value ? 1 : 0;
+  else if (n == "stem_tc") plan->stem_tc = value ? 1 : 0;
   else if (n == "fused_dca") plan->fused_dca = value ? 1 : 0;
   else if (n == "dca_pipe") plan->dca_pipe = value ? 1 : 0;
   else return fail(LMV_ERR_INVALID, "set_option: unknown option " + n);
@@ -1345,6 +1348,7 @@ int lmv_stem_conv1(const void* x, int x_dtype, const void* w, const float* bias,
                    void* stream) {
   if (!x || !w || !bias || !out) return fail(LMV_ERR_INVALID, "stem_conv1: null pointer");
   StemArgs a{x, x_dtype, static_cast<bf16*>(out), B, Cin, H, W};
+  if (const char* e = getenv("LMV_STEM_TC")) a.tensor_core = e[0] != '0';   // unit tests run both kernels
   return stem_conv1_run(a, static_cast<const bf16*>(w), bias, C1, static_cast<cudaStream_t>(stream));
 }
 

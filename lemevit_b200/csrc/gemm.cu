@@ -40,6 +40,7 @@ struct SmemCtrl {
   uint64_t empty[kMaxStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t w_full;      // resident W (p.w_res): all its K blocks have landed
   uint32_t tmem_base;
 };
 
@@ -147,10 +148,11 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   SmemCtrl* ctrl = reinterpret_cast<SmemCtrl*>(smem);
-  // [ctrl 1 KB][8 x 4 KB transpose buffers][8 x 4 KB output staging (TMA-store epilogue only)][stage ring]
-  uint8_t* tiles = smem + 1024 + kEpiWarps * kStageF32 + (p.tma_out ? kEpiWarps * kStageOut : 0);
-  const int a_bytes = BM * BK * 2;
-  const int stage_bytes = a_bytes + p.BN * BK * 2;
+  // [ctrl 1 KB][8 x 4 KB transpose buffers][8 x 4 KB output staging (TMA-store epilogue)][resident W: k_blocks x BN x 128 B (w_res)][stage ring]
+  uint8_t* wres = smem + 1024 + kEpiWarps * kStageF32 + (p.tma_out ? kEpiWarps * kStageOut : 0);
+  const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2;
+  uint8_t* tiles = wres + (p.w_res ? (size_t)p.k_blocks * w_bytes : 0);
+  const int stage_bytes = p.stage_bytes;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the role branches stay uniform
   const int lane = threadIdx.x & 31;
 
@@ -163,6 +165,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&ctrl->acc_full[i], 1);
       mbar_init(&ctrl->acc_empty[i], kEpiWarps);  // one elected lane per epilogue warp
     }
+    mbar_init(&ctrl->w_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -186,6 +189,15 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       TR_INIT
+      if (p.w_res && (int)blockIdx.x < num_tiles) {
+        // one N tile and a W small enough to stay: every K block of it is loaded once per CTA (the strided convolution of the
+        // stem otherwise streams as many W bytes as A bytes per tile through the L2 -> SM path that bounds it)
+        mbar_expect_tx(&ctrl->w_full, (uint32_t)(p.k_blocks * w_bytes));
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (p.conv) tma_load_3d(wres + (size_t)kb * w_bytes, &tmB, &ctrl->w_full, (kb % p.conv_cpt) * BK, kb / p.conv_cpt, 0);
+          else tma_load_2d(wres + (size_t)kb * w_bytes, &tmB, &ctrl->w_full, kb * BK, 0);
+        }
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_blk = t / p.tiles_n, n_blk = t % p.tiles_n;
         // pull the residual tile into L2 while the mainloop of this tile runs: the epilogue reads it ~2 tiles later
@@ -209,11 +221,11 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // tap `tap` from the [N][9][C] view of the packed weights (zero beyond C as well, so the padded k contribute nothing)
             const int ky = tap / 3, kx = tap - 3 * ky;
             tma_load_4d(sa, &tmA, &ctrl->full[stage], cs * BK, kx - 1, 2 * cy0 + ky - 1, cb0);
-            tma_load_3d(sa + a_bytes, &tmB, &ctrl->full[stage], cs * BK, tap, n_blk * p.BN);
+            if (!p.w_res) tma_load_3d(sa + a_bytes, &tmB, &ctrl->full[stage], cs * BK, tap, n_blk * p.BN);
             if (++cs == p.conv_cpt) { cs = 0; ++tap; }
           } else {
             tma_load_2d(sa, &tmA, &ctrl->full[stage], kb * BK, m_blk * BM);
-            tma_load_2d(sa + a_bytes, &tmB, &ctrl->full[stage], kb * BK, n_blk * p.BN);
+            if (!p.w_res) tma_load_2d(sa + a_bytes, &tmB, &ctrl->full[stage], kb * BK, n_blk * p.BN);
           }
           if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
         }
@@ -229,6 +241,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       TR_INIT
+      if (p.w_res && (int)blockIdx.x < num_tiles) mbar_wait(&ctrl->w_full, 0u, 5);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         TR(2)
         mbar_wait(&ctrl->acc_empty[as], aphase ^ 1u, 2);
@@ -242,7 +255,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
           const uint64_t da = make_kmajor_desc<128>(sa);
-          const uint64_t db = make_kmajor_desc<128>(sa + a_bytes);
+          const uint64_t db = make_kmajor_desc<128>(p.w_res ? smem_u32(wres + (size_t)kb * w_bytes) : sa + a_bytes);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // +32 bytes per K=16 step inside the 128B swizzle span: start-address field += 2
@@ -599,14 +612,31 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
     }
     p.tx_bytes = (uint32_t)(p.tile_rows * BK * 2 + p.BN * BK * 2);
   }
-  // TMA-store epilogue (8 x 4 KB of output staging) whenever the output is a dense-enough bf16 matrix and the staging does not
-  // cost the ring a stage it needs (BN = 256 tiles keep 4 stages and the per-lane stores); LMV_GEMM_TMA_OUT=0/1 overrides.
-  const int stages_plain = std::min(kMaxStages, (kSmemLimit - 2048 - kEpiWarps * kStageF32) / stage_bytes);
-  const int stages_tma = std::min(kMaxStages, (kSmemLimit - 2048 - kEpiWarps * (kStageF32 + kStageOut)) / stage_bytes);
-  bool tma_out = !conv && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && stages_tma >= 2 && stages_tma >= std::min(stages_plain, 4);
-  if (const char* e = getenv("LMV_GEMM_TMA_OUT")) tma_out = tma_out && e[0] != '0';
+  // Shared-memory plan.  Fixed: 2 KB (control + alignment slack) + 8 x 4 KB transpose buffers.  Optional, each only where it does
+  // not cost the ring a stage it needs (fewer than min(plain, 4)):
+  //   w_res       one N tile and all K blocks of W resident beside a ring of A-only slots (>= 4 of them);
+  //   tma_out     8 x 4 KB output staging of the TMA-store epilogue (dense bf16 output, full 128-row tiles).
+  // LMV_GEMM_WRES / LMV_GEMM_TMA_OUT = 0 switch one off (A/B runs).  (Measured and dropped: the per-column epilogue constants staged
+  // in shared memory one tile ahead behind a named barrier — qkv 70.8 -> 73.9 us.)
+  auto env_on = [](const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); };
+  const int fixed = 2048 + kEpiWarps * kStageF32;
+  const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2;
+  const int stages_plain = std::min(kMaxStages, (kSmemLimit - fixed) / stage_bytes);
+  const int want = std::min(stages_plain, 4);
+  int extra = 0;
+  p.w_res = 0; p.stage_bytes = stage_bytes;
+  if (p.tiles_n == 1 && env_on("LMV_GEMM_WRES") && (kSmemLimit - fixed - p.k_blocks * w_bytes) / a_bytes >= 4 && p.tiles_m > device_sm_count()) {
+    p.w_res = 1;
+    p.stage_bytes = a_bytes;
+    p.tx_bytes -= (uint32_t)w_bytes;
+    extra += p.k_blocks * w_bytes;
+  }
+  auto stages_with = [&](int more) { return std::min(kMaxStages, (kSmemLimit - fixed - extra - more) / p.stage_bytes); };
+  bool tma_out = !conv && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && env_on("LMV_GEMM_TMA_OUT") &&
+                 stages_with(kEpiWarps * kStageOut) >= (p.w_res ? 4 : want) && stages_with(kEpiWarps * kStageOut) >= 2;
   p.tma_out = tma_out ? 1 : 0;
-  p.num_stages = tma_out ? stages_tma : stages_plain;
+  if (tma_out) extra += kEpiWarps * kStageOut;
+  p.num_stages = stages_with(0);
   p.bias = a.bias; p.residual = a.residual; p.out = a.out;
   p.ldc = a.ldc; p.out_fp32 = a.out_fp32; p.act = a.act;
   p.grp_rows = a.grp_rows; p.grp_stride = a.grp_stride;
@@ -618,7 +648,7 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   p.stats_out = a.stats_out;
   LMV_REQUIRE(a.stats_out == nullptr || (a.N % 32 == 0 && a.ldc % 8 == 0 && !a.out_fp32),
               "gemm: stats_out needs N % 32 == 0, ldc % 8 == 0 and a bf16 output");
-  op->smem_bytes = 2048 + kEpiWarps * (kStageF32 + (p.tma_out ? kStageOut : 0)) + p.num_stages * stage_bytes;
+  op->smem_bytes = fixed + extra + p.num_stages * p.stage_bytes;
   op->grid = std::min(p.tiles_m * p.tiles_n, device_sm_count());
   if (conv) {
     // activation [B][T rows of C] seen as {C, W, H, B}; the box walks W and H with stride 2 from (kx - 1, 2 oy0 + ky - 1)

@@ -71,6 +71,7 @@ struct StemArgs {
   int B, Cin, H, W;
   float mean[3] = {0.485f * 255.f, 0.456f * 255.f, 0.406f * 255.f};   // 8-bit input: bf16((u8 - mean[c]) / std[c])
   float std[3] = {0.229f * 255.f, 0.224f * 255.f, 0.225f * 255.f};
+  int tensor_core = 1;   // stem_conv1: tcgen05 implicit-GEMM kernel (0: the CUDA-core kernel, A/B switch "stem_tc")
 };
 int stem_im2col_run(const StemArgs& a, cudaStream_t s);
 // direct first stem convolution + folded BN + GELU: a.out receives token-major [B, Ho*Wo, C1] (no im2col detour)

@@ -453,6 +453,173 @@ stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp]
 }
 
 // ------------------------------------------------------------------------------------------------
+// first stem convolution on the tensor cores: the same op as stem_conv1_kernel (conv3x3 / s2 / p1 + folded BN + GELU,
+// models/lemevit.py:699-701), as an implicit GEMM with K = 27 -> 32.  The CUDA-core kernel above spends 2/3 of its issue slots on
+// the 27 x C1 FMAs of a pixel; here they are two tcgen05.mma (M = 128 pixels, N = C1, K = 16) per tile.
+//   warps 0..3  gather: thread = output pixel; its 27 inputs (NCHW f32 | bf16 | 8-bit through the normalisation table) become one
+//               64-byte K-major row of the A tile (64B swizzle: 16-byte slot j of row r sits at j ^ ((r >> 1) & 3)), double-buffered
+//   warp 8      issues the two MMAs of a tile into one of two 64-column TMEM accumulators; the weights [C1][32] bf16 (pack.py's
+//               layout is already K-major) sit in shared memory for the whole kernel
+//   warps 4..7  epilogue (TMEM lane quarter = warp & 3): tcgen05.ld -> + bias -> GELU -> bf16 -> 256-bit stores, thread = pixel
+// Persistent CTAs, several per SM (the gather is a latency chain, 128 columns of TMEM per CTA).
+// ------------------------------------------------------------------------------------------------
+constexpr int kStemTcThreads = 9 * 32;
+
+template <typename T, int C1, int LAYOUT>
+__global__ void __launch_bounds__(kStemTcThreads, 2)
+stem_conv1_tc_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][32]*/, const float* __restrict__ bias, bf16* __restrict__ out,
+                     int B, int H, int W, int Ho, int Wo, StemNorm nrm) {
+  constexpr bool kU8 = sizeof(T) == 1;
+  __shared__ __align__(1024) uint8_t sA[2][128 * 64];
+  __shared__ __align__(1024) uint8_t sW[C1 * 64];
+  __shared__ __align__(16) float sBias[C1];
+  __shared__ float lut[kU8 ? 3 * 256 : 1];
+  __shared__ uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 4);       // one elected lane per gather warp
+      mbar_init(&a_empty[i], 1);      // tcgen05.commit
+      mbar_init(&acc_full[i], 1);     // tcgen05.commit
+      mbar_init(&acc_empty[i], 4);    // one elected lane per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(&tmem_slot, 128);
+    tmem_relinquish();
+  }
+  // constants of the plan (not outputs of the previous kernel): weights, bias, normalisation table
+  for (int i = threadIdx.x; i < C1 * 4; i += blockDim.x) {
+    const int n = i >> 2, j = i & 3;
+    *reinterpret_cast<uint4*>(sW + n * 64 + ((j ^ ((n >> 1) & 3)) << 4)) = __ldg(reinterpret_cast<const uint4*>(w + n * 32) + j);
+  }
+  for (int i = threadIdx.x; i < C1; i += blockDim.x) sBias[i] = bias[i];
+  if (kU8)
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+      const int c = i >> 8;
+      lut[i] = __bfloat162float(__float2bfloat16(__fdiv_rn(__fsub_rn((float)(i & 255), nrm.mean[c]), nrm.std[c])));
+    }
+  fence_proxy_async_smem();     // sW is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = tmem_slot;
+  const long long total = (long long)B * Ho * Wo;
+  const int num_tiles = (int)((total + 127) / 128);
+
+  if (warp < 4) {
+    // ---------------- gather ----------------
+    const int r = threadIdx.x;       // row of the tile
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const long long pix = (long long)t * 128 + r;
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      if (pix < total) {
+        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        float in[28];
+        in[27] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+              float v = 0.f;     // the zero padding pads the NORMALISED image
+              if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                if constexpr (kU8) {
+                  const long long idx = LAYOUT == 1 ? (((long long)b * H + iy) * W + ix) * 3 + ci : (((long long)b * 3 + ci) * H + iy) * W + ix;
+                  v = lut[ci * 256 + (int)__ldg(reinterpret_cast<const unsigned char*>(x) + idx)];
+                } else {
+                  v = ld_as_float<T>(x + (((long long)b * 3 + ci) * H + iy) * W + ix);
+                }
+              }
+              in[ci * 9 + ky * 3 + kx] = v;
+            }
+#pragma unroll
+        for (int i = 0; i < 14; ++i) pk[i] = pack_bf16x2(in[2 * i], in[2 * i + 1]);
+      }
+      mbar_wait(&a_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u, 11);
+      uint8_t* row = sA[buf] + r * 64;
+      const int sw = (r >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[buf]);
+    }
+  } else if (warp == 8) {
+    // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues) ----------------
+    const uint32_t idesc = make_idesc_bf16(128, C1);
+    const uint64_t db = make_kmajor_desc<64>(smem_u32(sW));
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&acc_empty[buf], ph ^ 1u, 12);
+      mbar_wait(&a_full[buf], ph, 13);
+      tc_fence_after();
+      const uint64_t da = make_kmajor_desc<64>(smem_u32(sA[buf]));
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 64);
+      umma_bf16_ss_warp(d_tmem, da, db, idesc, 0u);
+      umma_bf16_ss_warp(d_tmem, da + 2ull, db + 2ull, idesc, 1u);     // +32 bytes: k = 16..31 inside the 64-byte swizzle span
+      umma_commit_warp(&a_empty[buf]);
+      umma_commit_warp(&acc_full[buf]);
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int q = warp & 3;
+    const bool al32 = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u, 14);
+      tc_fence_after();
+      const long long pix = (long long)t * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
+      uint32_t acc[C1 / 16][16];
+#pragma unroll
+      for (int c = 0; c < C1 / 16; ++c) tmem_ld_x16(taddr + (uint32_t)(c * 16), acc[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (pix < total) {
+        bf16* dst = out + pix * C1;
+#pragma unroll
+        for (int c = 0; c < C1 / 16; ++c) {
+          uint32_t wv[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bq = *reinterpret_cast<const float4*>(sBias + c * 16 + 4 * j);
+            const float2 g0 = gelu_fast2(make_float2(__uint_as_float(acc[c][4 * j]) + bq.x, __uint_as_float(acc[c][4 * j + 1]) + bq.y));
+            const float2 g1 = gelu_fast2(make_float2(__uint_as_float(acc[c][4 * j + 2]) + bq.z, __uint_as_float(acc[c][4 * j + 3]) + bq.w));
+            wv[2 * j] = pack_bf16x2(g0.x, g0.y);
+            wv[2 * j + 1] = pack_bf16x2(g1.x, g1.y);
+          }
+          if (al32) {
+            st_global_256(dst + 16 * c, wv);
+          } else {
+            reinterpret_cast<uint4*>(dst + 16 * c)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            reinterpret_cast<uint4*>(dst + 16 * c)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
 // im2col for conv3x3 stride 2 pad 1 on token-major activations: out[(b,oy,ox), tap*C + ci]
 // reference: stem conv 2 and downsample convs (models/lemevit.py:702,715)
 // ------------------------------------------------------------------------------------------------
@@ -659,26 +826,27 @@ int stem_conv1_run(const StemArgs& a, const bf16* w, const float* bias, int C1, 
   const int Ho = (a.H + 1) / 2, Wo = (a.W + 1) / 2, Kp = ((a.Cin * 9 + 7) / 8) * 8;
   const long long total = (long long)a.B * Ho * Wo;
   if (total == 0) return LMV_OK;
-  const unsigned grid = blocks_for((total + 1) / 2, 128);   // two output pixels per thread
   StemNorm nrm;
   for (int i = 0; i < 3; ++i) { nrm.mean[i] = a.mean[i]; nrm.std[i] = a.std[i]; }
-  auto go = [&](auto kern, auto* xp) -> int {
-    LMV_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(128), (size_t)(0), s, xp, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp, nrm));
+  const bool use_tc = a.tensor_core && Kp == 32;
+  const unsigned grid = use_tc ? (unsigned)std::min<long long>((total + 127) / 128, 2LL * device_sm_count())   /* two resident CTAs per SM */
+                               : blocks_for((total + 1) / 2, 128);   // CUDA-core kernel: two output pixels per thread
+  auto go = [&](auto kern_tc, auto kern, auto* xp) -> int {
+    if (use_tc) LMV_CUDA_OK(launch_kernel(kern_tc, dim3(grid), dim3(kStemTcThreads), (size_t)(0), s, xp, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, nrm));
+    else LMV_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(128), (size_t)(0), s, xp, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, Kp, nrm));
     LMV_CUDA_OK(cudaGetLastError());
     return LMV_OK;
   };
+#define LMV_STEM_GO(T, L, ptr) (C1 == 32 ? go(stem_conv1_tc_kernel<T, 32, L>, stem_conv1_kernel<T, 32, L>, ptr) \
+                                          : go(stem_conv1_tc_kernel<T, 48, L>, stem_conv1_kernel<T, 48, L>, ptr))
   switch (a.x_dtype) {
-    case LMV_DTYPE_F32:
-      return C1 == 32 ? go(stem_conv1_kernel<float, 32, 0>, (const float*)a.x) : go(stem_conv1_kernel<float, 48, 0>, (const float*)a.x);
-    case LMV_DTYPE_BF16:
-      return C1 == 32 ? go(stem_conv1_kernel<bf16, 32, 0>, (const bf16*)a.x) : go(stem_conv1_kernel<bf16, 48, 0>, (const bf16*)a.x);
-    case LMV_DTYPE_U8:
-      return C1 == 32 ? go(stem_conv1_kernel<uint8_t, 32, 0>, (const uint8_t*)a.x) : go(stem_conv1_kernel<uint8_t, 48, 0>, (const uint8_t*)a.x);
-    case LMV_DTYPE_U8_NHWC:
-      return C1 == 32 ? go(stem_conv1_kernel<uint8_t, 32, 1>, (const uint8_t*)a.x) : go(stem_conv1_kernel<uint8_t, 48, 1>, (const uint8_t*)a.x);
-    default:
-      return fail(LMV_ERR_INVALID, "stem_conv1: x dtype");
+    case LMV_DTYPE_F32: return LMV_STEM_GO(float, 0, (const float*)a.x);
+    case LMV_DTYPE_BF16: return LMV_STEM_GO(bf16, 0, (const bf16*)a.x);
+    case LMV_DTYPE_U8: return LMV_STEM_GO(uint8_t, 0, (const uint8_t*)a.x);
+    case LMV_DTYPE_U8_NHWC: return LMV_STEM_GO(uint8_t, 1, (const uint8_t*)a.x);
+    default: return fail(LMV_ERR_INVALID, "stem_conv1: x dtype");
   }
+#undef LMV_STEM_GO
 }
 
 int im2col_run(const Im2colArgs& a, cudaStream_t s) {

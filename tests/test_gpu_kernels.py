@@ -416,17 +416,22 @@ def test_stem_conv_via_im2col_gemm(dtype):
     assert G.rel_err(out, ref) < TOL
 
 
+@pytest.mark.parametrize("tc", ["1", "0"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,H,W,C1", [(2, 224, 224, 48), (3, 64, 96, 32), (1, 33, 47, 48)])
-def test_stem_conv1_direct(dtype, B, H, W, C1):
+@pytest.mark.parametrize("B,H,W,C1", [(2, 224, 224, 48), (3, 64, 96, 32), (1, 33, 47, 48), (37, 224, 224, 48)])
+def test_stem_conv1_direct(dtype, B, H, W, C1, tc, monkeypatch):
+    """First stem convolution + folded BN + GELU without an im2col detour: the tcgen05 kernel (implicit GEMM, K = 27 -> 32; several
+    tiles per persistent CTA at B = 37) and the CUDA-core kernel, against conv2d + exact GELU in fp32."""
+    monkeypatch.setenv("LMV_STEM_TC", tc)
     x = torch.randn(B, 3, H, W, device="cuda").to(dtype)
     w = torch.randn(C1, 3, 3, 3, device="cuda") * 0.3
     bias = torch.randn(C1, device="cuda") * 0.2
     out, wp = G.stem_conv1(x, w, bias)
     wr = wp[:, :27].float().reshape(C1, 3, 3, 3)
-    ref = torch.nn.functional.gelu(torch.nn.functional.conv2d(x.float(), wr, bias, stride=2, padding=1))
+    xr = G.bf(x).float() if tc == "1" else x.float()      # the tensor-core operand is bf16
+    ref = torch.nn.functional.gelu(torch.nn.functional.conv2d(xr, wr, bias, stride=2, padding=1))
     ref = ref.permute(0, 2, 3, 1).reshape(B, -1, C1)
-    assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999
+    assert G.rel_err(out, ref) < TOL and G.cosine(out, ref) > 0.9999, G.describe_mismatch(out.float().reshape(-1, C1), ref.reshape(-1, C1), TOL)
 
 
 @pytest.mark.parametrize("B,H,W,C,Co,extra", [(2, 28, 28, 48, 96, 0), (2, 14, 14, 192, 384, 16), (1, 7, 9, 64, 128, 0)])
