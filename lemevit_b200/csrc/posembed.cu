@@ -313,8 +313,11 @@ int posembed_tile_run(const PosEmbedOp& op, cudaStream_t s) {
   // blockIdx.y == 1: the CTAs that pass the meta-token rows of a unified buffer through
   const int n_items = op.tiles_x * op.tiles_y * a.B;
   const int per_sm = std::max(1, std::min(3, (200 * 1024) / std::max(op.smem, 1)));
-  // (two waves when the channels are sliced: measured faster than one wave of longer-lived CTAs at C = 384)
-  dim3 grid(std::min(n_items, std::max(1, (op.parts > 1 ? 2 : 1) * per_sm * device_sm_count() / op.parts)), a.T > a.H * a.W ? 2 : 1, op.parts);
+  // CTAs per resident slot, measured per shape at Base b256: unsliced (C = 96) and two slices (C = 192) are fastest with one
+  // wave of long-lived CTAs, four slices (C = 384, 512: 7-row tiles, 1-2 items per CTA anyway) with three.
+  int waves = op.parts >= 4 ? 3 : 1;
+  if (const char* e = getenv("LMV_POS_WAVES")) waves = std::max(1, atoi(e));   // A/B knob
+  dim3 grid(std::min(n_items, std::max(1, waves * per_sm * device_sm_count() / op.parts)), a.T > a.H * a.W ? 2 : 1, op.parts);
   LMV_CUDA_OK(launch_kernel(posembed_tile_kernel, dim3(grid), dim3(op.threads), (size_t)(op.smem), s, op.tm, p));
   LMV_CUDA_OK(cudaGetLastError());
   return LMV_OK;

@@ -3,6 +3,7 @@
 // tail and the NCHW export of the backbone feature maps.  All activations are token-major
 // [B, T, C] bf16 (NHWC); the reference's NCHW<->token rearranges (models/lemevit.py:548,579) vanish.
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.h"
 #include "umma.cuh"
@@ -456,20 +457,23 @@ stem_conv1_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][Kp]
 // first stem convolution on the tensor cores: the same op as stem_conv1_kernel (conv3x3 / s2 / p1 + folded BN + GELU,
 // models/lemevit.py:699-701), as an implicit GEMM with K = 27 -> 32.  The CUDA-core kernel above spends 2/3 of its issue slots on
 // the 27 x C1 FMAs of a pixel; here they are two tcgen05.mma (M = 128 pixels, N = C1, K = 16) per tile.
-//   warps 0..3  gather: thread = output pixel; its 27 inputs (NCHW f32 | bf16 | 8-bit through the normalisation table) become one
-//               64-byte K-major row of the A tile (64B swizzle: 16-byte slot j of row r sits at j ^ ((r >> 1) & 3)), double-buffered
-//   warp 8      issues the two MMAs of a tile into one of two 64-column TMEM accumulators; the weights [C1][32] bf16 (pack.py's
+//   warps 0..3  thread = pixel, for the gather AND the epilogue, software-pipelined: the 27 loads of tile i + 1 (NCHW f32 | bf16 |
+//               8-bit pixels) are issued, then the epilogue of tile i runs (tcgen05.ld of the thread's TMEM lane -> + bias ->
+//               GELU -> bf16 -> 256-bit stores) and hides their latency — the gather is a chain of cold image rows — and only then
+//               are they packed into one 64-byte K-major row of the A tile (64B swizzle: 16-byte slot j of row r sits at
+//               j ^ ((r >> 1) & 3); 8-bit pixels go through the normalisation table here) and handed to the issuer
+//   warp 4      issues the two MMAs of a tile into one of two 64-column TMEM accumulators; the weights [C1][32] bf16 (pack.py's
 //               layout is already K-major) sit in shared memory for the whole kernel
-//   warps 4..7  epilogue (TMEM lane quarter = warp & 3): tcgen05.ld -> + bias -> GELU -> bf16 -> 256-bit stores, thread = pixel
-// Persistent CTAs, several per SM (the gather is a latency chain, 128 columns of TMEM per CTA).
+// Persistent CTAs of 160 threads, three per SM (128 columns of TMEM each).
 // ------------------------------------------------------------------------------------------------
-constexpr int kStemTcThreads = 9 * 32;
+constexpr int kStemTcThreads = 5 * 32;
 
 template <typename T, int C1, int LAYOUT>
-__global__ void __launch_bounds__(kStemTcThreads, 2)
+__global__ void __launch_bounds__(kStemTcThreads, 3)
 stem_conv1_tc_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][32]*/, const float* __restrict__ bias, bf16* __restrict__ out,
                      int B, int H, int W, int Ho, int Wo, StemNorm nrm) {
   constexpr bool kU8 = sizeof(T) == 1;
+  using Raw = typename std::conditional<kU8, uint8_t, float>::type;      // what a tap is held as between its load and its use
   __shared__ __align__(1024) uint8_t sA[2][128 * 64];
   __shared__ __align__(1024) uint8_t sW[C1 * 64];
   __shared__ __align__(16) float sBias[C1];
@@ -480,14 +484,14 @@ stem_conv1_tc_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 4);       // one elected lane per gather warp
+      mbar_init(&a_full[i], 4);       // one elected lane per pixel warp
       mbar_init(&a_empty[i], 1);      // tcgen05.commit
       mbar_init(&acc_full[i], 1);     // tcgen05.commit
-      mbar_init(&acc_empty[i], 4);    // one elected lane per epilogue warp
+      mbar_init(&acc_empty[i], 4);    // one elected lane per pixel warp
     }
     fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == 4) {
     tmem_alloc(&tmem_slot, 128);
     tmem_relinquish();
   }
@@ -512,50 +516,107 @@ stem_conv1_tc_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][
   const int num_tiles = (int)((total + 127) / 128);
 
   if (warp < 4) {
-    // ---------------- gather ----------------
-    const int r = threadIdx.x;       // row of the tile
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const long long pix = (long long)t * 128 + r;
-      uint32_t pk[16];
+    const int r = threadIdx.x;       // row of the tile = TMEM lane
+    const int HoWo = Ho * Wo, npix = (int)total;      // (< 2^31 output pixels: checked by the launcher)
+    const bool al32 = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+    // raw taps of a tile's pixel: loads only, nothing here waits for them (out-of-image taps: `zero`, the padding of the
+    // NORMALISED image; for 8-bit input a 28th table entry would do, a flag bit per tap is cheaper)
+    auto load_raw = [&](int t, Raw (&raw)[27], uint32_t& inside) {
+      const int pix = t * 128 + r;
+      inside = 0u;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = 0u;
-      if (pix < total) {
-        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-        float in[28];
-        in[27] = 0.f;
+      for (int i = 0; i < 27; ++i) raw[i] = Raw(0);
+      if (t >= num_tiles || pix >= npix) return;
+      const int b = pix / HoWo, rem = pix - b * HoWo, oy = rem / Wo, ox = rem - oy * Wo;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
+      for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-              float v = 0.f;     // the zero padding pads the NORMALISED image
-              if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-                if constexpr (kU8) {
-                  const long long idx = LAYOUT == 1 ? (((long long)b * H + iy) * W + ix) * 3 + ci : (((long long)b * 3 + ci) * H + iy) * W + ix;
-                  v = lut[ci * 256 + (int)__ldg(reinterpret_cast<const unsigned char*>(x) + idx)];
-                } else {
-                  v = ld_as_float<T>(x + (((long long)b * 3 + ci) * H + iy) * W + ix);
-                }
+          for (int kx = 0; kx < 3; ++kx) {
+            const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1, k = ci * 9 + ky * 3 + kx;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+              inside |= 1u << k;
+              if constexpr (kU8) {
+                const long long idx = LAYOUT == 1 ? (((long long)b * H + iy) * W + ix) * 3 + ci : (((long long)b * 3 + ci) * H + iy) * W + ix;
+                raw[k] = __ldg(reinterpret_cast<const unsigned char*>(x) + idx);
+              } else {
+                raw[k] = ld_as_float<T>(x + (((long long)b * 3 + ci) * H + iy) * W + ix);
               }
-              in[ci * 9 + ky * 3 + kx] = v;
             }
+          }
+    };
+    // pack the taps into the thread's K-major row of A tile `buf` and hand the tile to the issuer
+    auto store_row = [&](const Raw (&raw)[27], uint32_t inside, int buf, uint32_t empty_parity) {
+      float in[28];
+      in[27] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 14; ++i) pk[i] = pack_bf16x2(in[2 * i], in[2 * i + 1]);
+      for (int k = 0; k < 27; ++k) {
+        if constexpr (kU8) in[k] = ((inside >> k) & 1u) ? lut[(k / 9) * 256 + (int)raw[k]] : 0.f;
+        else in[k] = raw[k];
       }
-      mbar_wait(&a_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u, 11);
+      uint32_t pk[14];
+#pragma unroll
+      for (int i = 0; i < 14; ++i) pk[i] = pack_bf16x2(in[2 * i], in[2 * i + 1]);
+      mbar_wait(&a_empty[buf], empty_parity, 11);
       uint8_t* row = sA[buf] + r * 64;
       const int sw = (r >> 1) & 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(row + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      *reinterpret_cast<uint4*>(row + ((2 ^ sw) << 4)) = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+      *reinterpret_cast<uint4*>(row + ((3 ^ sw) << 4)) = make_uint4(pk[12], pk[13], 0u, 0u);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[buf]);
+    };
+    Raw raw[27];
+    uint32_t inside;
+    if ((int)blockIdx.x < num_tiles) {
+      load_raw(blockIdx.x, raw, inside);
+      store_row(raw, inside, 0, 1u);
     }
-  } else if (warp == 8) {
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int tn = t + gridDim.x;
+      load_raw(tn, raw, inside);                     // in flight during the epilogue below
+      // ---- epilogue of tile t
+      mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u, 14);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
+      uint32_t acc[C1 / 16][16];
+#pragma unroll
+      for (int c = 0; c < C1 / 16; ++c) tmem_ld_x16(taddr + (uint32_t)(c * 16), acc[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      const int pix = t * 128 + r;
+      if (pix < npix) {
+        bf16* dst = out + (long long)pix * C1;
+#pragma unroll
+        for (int c = 0; c < C1 / 16; ++c) {
+          uint32_t wv[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bq = *reinterpret_cast<const float4*>(sBias + c * 16 + 4 * j);
+            const float2 g0 = gelu_fast2(fadd2(make_float2(__uint_as_float(acc[c][4 * j]), __uint_as_float(acc[c][4 * j + 1])), make_float2(bq.x, bq.y)));
+            const float2 g1 = gelu_fast2(fadd2(make_float2(__uint_as_float(acc[c][4 * j + 2]), __uint_as_float(acc[c][4 * j + 3])), make_float2(bq.z, bq.w)));
+            wv[2 * j] = pack_bf16x2(g0.x, g0.y);
+            wv[2 * j + 1] = pack_bf16x2(g1.x, g1.y);
+          }
+          if (al32) {
+            st_global_256(dst + 16 * c, wv);
+          } else {
+            reinterpret_cast<uint4*>(dst + 16 * c)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+            reinterpret_cast<uint4*>(dst + 16 * c)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+          }
+        }
+      }
+      // ---- tile t + stride: its taps have arrived by now
+      if (tn < num_tiles) store_row(raw, inside, buf ^ 1, ((uint32_t)((it + 1) >> 1) & 1u) ^ 1u);
+    }
+  } else {
     // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues) ----------------
     const uint32_t idesc = make_idesc_bf16(128, C1);
     const uint64_t db = make_kmajor_desc<64>(smem_u32(sW));
@@ -573,50 +634,10 @@ stem_conv1_tc_kernel(const T* __restrict__ x, const bf16* __restrict__ w /*[C1][
       umma_commit_warp(&a_empty[buf]);
       umma_commit_warp(&acc_full[buf]);
     }
-  } else {
-    // ---------------- epilogue ----------------
-    const int q = warp & 3;
-    const bool al32 = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-      const int buf = it & 1;
-      mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u, 14);
-      tc_fence_after();
-      const long long pix = (long long)t * 128 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64);
-      uint32_t acc[C1 / 16][16];
-#pragma unroll
-      for (int c = 0; c < C1 / 16; ++c) tmem_ld_x16(taddr + (uint32_t)(c * 16), acc[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (pix < total) {
-        bf16* dst = out + pix * C1;
-#pragma unroll
-        for (int c = 0; c < C1 / 16; ++c) {
-          uint32_t wv[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bq = *reinterpret_cast<const float4*>(sBias + c * 16 + 4 * j);
-            const float2 g0 = gelu_fast2(make_float2(__uint_as_float(acc[c][4 * j]) + bq.x, __uint_as_float(acc[c][4 * j + 1]) + bq.y));
-            const float2 g1 = gelu_fast2(make_float2(__uint_as_float(acc[c][4 * j + 2]) + bq.z, __uint_as_float(acc[c][4 * j + 3]) + bq.w));
-            wv[2 * j] = pack_bf16x2(g0.x, g0.y);
-            wv[2 * j + 1] = pack_bf16x2(g1.x, g1.y);
-          }
-          if (al32) {
-            st_global_256(dst + 16 * c, wv);
-          } else {
-            reinterpret_cast<uint4*>(dst + 16 * c)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-            reinterpret_cast<uint4*>(dst + 16 * c)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-          }
-        }
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 128);
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -828,8 +849,8 @@ int stem_conv1_run(const StemArgs& a, const bf16* w, const float* bias, int C1, 
   if (total == 0) return LMV_OK;
   StemNorm nrm;
   for (int i = 0; i < 3; ++i) { nrm.mean[i] = a.mean[i]; nrm.std[i] = a.std[i]; }
-  const bool use_tc = a.tensor_core && Kp == 32;
-  const unsigned grid = use_tc ? (unsigned)std::min<long long>((total + 127) / 128, 2LL * device_sm_count())   /* two resident CTAs per SM */
+  const bool use_tc = a.tensor_core && Kp == 32 && total < (1ll << 31) - 256;
+  const unsigned grid = use_tc ? (unsigned)std::min<long long>((total + 127) / 128, 3LL * device_sm_count())   /* three resident CTAs per SM */
                                : blocks_for((total + 1) / 2, 128);   // CUDA-core kernel: two output pixels per thread
   auto go = [&](auto kern_tc, auto kern, auto* xp) -> int {
     if (use_tc) LMV_CUDA_OK(launch_kernel(kern_tc, dim3(grid), dim3(kStemTcThreads), (size_t)(0), s, xp, w, bias, a.out, a.B, a.H, a.W, Ho, Wo, nrm));

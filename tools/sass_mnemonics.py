@@ -34,7 +34,8 @@ def demangle(n):
         return n
 print(f"# SASS mnemonics per kernel of {os.path.basename(lib)} (cuobjdump -sass); UTCHMMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG = TMA load,")
 print("# UTCBAR = tcgen05.commit, HMMA = warp-level mma.sync (meta-token kernels only), R2UR = register -> uniform-register moves")
-print(f"{'kernel':58s} {'regs':>5s} {'UTCHMMA':>8s} {'LDTM':>6s} {'STTM':>6s} {'UTMALDG':>8s} {'UTCBAR':>7s} {'HMMA':>6s} {'MUFU':>6s} {'R2UR':>6s}")
+print("# UTMASTG = TMA tile store (GEMM epilogue)")
+print(f"{'kernel':58s} {'regs':>5s} {'UTCHMMA':>8s} {'LDTM':>6s} {'STTM':>6s} {'UTMALDG':>8s} {'UTMASTG':>8s} {'UTCBAR':>7s} {'HMMA':>6s} {'MUFU':>6s} {'R2UR':>6s}")
 for k, c in counts.items():
     d = demangle(k)
-    print(f"{d[:58]:58s} {regs.get(k, 0):5d} {c['UTCHMMA']:8d} {c['LDTM']:6d} {c['STTM']:6d} {c['UTMALDG']:8d} {c['UTCBAR']:7d} {c['HMMA']:6d} {c['MUFU']:6d} {c['R2UR']:6d}")
+    print(f"{d[:58]:58s} {regs.get(k, 0):5d} {c['UTCHMMA']:8d} {c['LDTM']:6d} {c['STTM']:6d} {c['UTMALDG']:8d} {c['UTMASTG']:8d} {c['UTCBAR']:7d} {c['HMMA']:6d} {c['MUFU']:6d} {c['R2UR']:6d}")
