@@ -882,6 +882,7 @@ static int build_schedule(lmv_plan* plan, int B, int H, int W, uint8_t* ws, int 
         sc->push([ga, io](cudaStream_t s) { GemmArgs a = ga; a.out = io->logits; return gemm_simt_run(a, s); }, OP_MISC, hfl, 0);
       } else {
         ga.out = feat;  // placeholder for validation; replaced at launch
+        ga.out_patched = 1;   // (so the epilogue must store through the pointer, not through a TMA map of the placeholder)
         GemmOp op;
         rc = gemm_prepare(ga, &op);
         if (rc) return rc;

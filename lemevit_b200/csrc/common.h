@@ -113,6 +113,7 @@ struct GemmArgs {
   // optional row remap of the OUTPUT (and residual): row r -> (r / grp_rows) * grp_stride + r % grp_rows
   int grp_rows = 0, grp_stride = 0;
   int force_bn = 0;                  // test hook: override the tile-N heuristic
+  int out_patched = 0;               // `out` is replaced at launch time (GemmOp::p.out): nothing may bake its address into a tensor map
   // Implicit-GEMM convolution 3x3 / stride 2 / pad 1 (conv_C > 0): A is not a matrix but the token-major activation
   // [conv_B, conv_T, conv_C] (first conv_H * conv_W rows of every image, row = y * W + x); the GEMM rows are the output pixels
   // (b, oy, ox), M = conv_B * ceil(H/2) * ceil(W/2), K = 9 * conv_C with k = (ky * 3 + kx) * C + ci — the layout of the

@@ -632,7 +632,7 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
     extra += p.k_blocks * w_bytes;
   }
   auto stages_with = [&](int more) { return std::min(kMaxStages, (kSmemLimit - fixed - extra - more) / p.stage_bytes); };
-  bool tma_out = !conv && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && env_on("LMV_GEMM_TMA_OUT") &&
+  bool tma_out = !conv && !a.out_patched && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && env_on("LMV_GEMM_TMA_OUT") &&
                  stages_with(kEpiWarps * kStageOut) >= (p.w_res ? 4 : want) && stages_with(kEpiWarps * kStageOut) >= 2;
   p.tma_out = tma_out ? 1 : 0;
   if (tma_out) extra += kEpiWarps * kStageOut;

@@ -415,3 +415,29 @@ def test_implicit_conv_schedule_is_bit_identical_to_im2col(name, B, res):
     eng.set_option("implicit_conv", 1)
     assert n_impl == n_im2col - 4
     assert torch.equal(y, y_im2col)
+
+
+@pytest.mark.parametrize("num_classes", [64, 96, 1000])
+def test_head_writes_the_callers_logits_buffer(num_classes):
+    """The head GEMM's output pointer is patched per call (a new logits tensor every forward).  With few classes the GEMM has the
+    shared memory for its TMA-store epilogue, whose tensor map is encoded when the schedule is built: the head must not use it
+    (regression: bf16 logits landed in the schedule's placeholder buffer)."""
+    cfg = O.VARIANTS["lemevit_micro"]
+    sd = {k: v for k, v in Wt.make_state_dict(cfg, 8).items() if not k.startswith("head.")}
+    m = L.LeMeViT(depth=list(cfg.depth), embed_dim=list(cfg.embed_dim), head_dim=cfg.head_dim, mlp_ratios=list(cfg.mlp_ratios),
+                  attn_type=list(cfg.attn_type), queries_len=cfg.queries_len, num_classes=num_classes)
+    missing, unexpected = m.load_state_dict(sd, strict=False)      # the head keeps its own random initialisation
+    assert not unexpected and all(k.startswith("head.") for k in missing)
+    with torch.no_grad():
+        m.head.bias.normal_(0.0, 0.5)
+    m = m.to("cuda", torch.bfloat16)
+    m.train(False)
+    x = Wt.make_input(3, 64, 64, 8).cuda().to(torch.bfloat16)
+    y1 = m(x)
+    feat = m.forward_features(x)
+    ref = feat.float() @ m.head.weight.float().t() + m.head.bias.float()
+    assert y1.dtype == torch.bfloat16 and y1.shape == (3, num_classes)
+    assert G.rel_err(y1, ref) < 1e-2
+    y2 = m(x)                        # a second call gets a different output tensor
+    assert y2.data_ptr() != y1.data_ptr() and torch.equal(y1, y2)
+    assert torch.equal(m.forward_features(x), feat)      # and the feature buffer was not overwritten by logits
