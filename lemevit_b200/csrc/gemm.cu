@@ -149,7 +149,9 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* smem = smem_raw + pad;
   SmemCtrl* ctrl = reinterpret_cast<SmemCtrl*>(smem);
   // [ctrl 1 KB][8 x 4 KB transpose buffers][8 x 4 KB output staging (TMA-store epilogue)][resident W: k_blocks x BN x 128 B (w_res)][stage ring]
-  uint8_t* wres = smem + 1024 + kEpiWarps * kStageF32 + (p.tma_out ? kEpiWarps * kStageOut : 0);
+  // (row_epi: the lane = row epilogue needs no transpose buffers)
+  const int stg_bytes = p.row_epi ? 0 : kEpiWarps * kStageF32;
+  uint8_t* wres = smem + 1024 + stg_bytes + (p.tma_out ? kEpiWarps * kStageOut : 0);
   const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2;
   uint8_t* tiles = wres + (p.w_res ? (size_t)p.k_blocks * w_bytes : 0);
   const int stage_bytes = p.stage_bytes;
@@ -281,6 +283,13 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr bool kPackedMath = EPI >= 0;
     // the residual + statistics variant has no registers to spare for a second accumulator chunk in flight
     constexpr bool kPipelineLd = !(EPI >= 0 && (EPI & kEpiRes) != 0 && (EPI & kEpiStats) != 0);
+    // Lane = row epilogue (no transpose): variants without residual / statistics whose output leaves through TMA tile stores
+    // (p.row_epi).  The transpose path moves every accumulator chunk through shared memory twice (fp32 write + read, 2 x 98 KB per
+    // 128 x 192 tile) next to the 240 KB of operand reads + 240 KB of TMA fills the tensor pipe needs for the same tile (K = 384).
+    // Here a lane keeps its row: LayerNorm fold with the lane's own (r, -r mu), per-column constants by warp-uniform loads, and the
+    // only epilogue traffic left in shared memory is the bf16 box the TMA store reads (49 KB per tile).  Same-box A/B at Base b256:
+    // qkv 74.6 -> 67.8 us, stage-4 qkv 40.3 -> 38.9, stage-4 fc1 57.4 -> 55.3 (LMV_GEMM_ROW_EPI=0 switches it off).
+    constexpr bool kRowEpi = EPI >= 0 && (EPI & (kEpiRes | kEpiStats)) == 0;
     const bool vec_ok = (p.ldc % 8 == 0);
     const bool fast_ok = vec_ok && !p.out_fp32;
     float* stg = reinterpret_cast<float*>(smem + 1024 + (size_t)(warp - 2) * kStageF32);
@@ -289,7 +298,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // leave through one cp.async.bulk.tensor store per chunk.  The warp's global stores otherwise queue in the LSU in front of its
     // next bias / colsum / residual loads (profiles/r02_gemm_role_trace.txt: 44 % of the epilogue time sat in the load-issue phase).
     const bool tma_out = p.tma_out != 0;
-    uint8_t* ostg = smem + 1024 + kEpiWarps * kStageF32 + (size_t)(warp - 2) * kStageOut;
+    uint8_t* ostg = smem + 1024 + stg_bytes + (size_t)(warp - 2) * kStageOut;
     int obuf = 0;
     const int lr = lane >> 2, lc = (lane & 3) * 8;   // transposed domain: this lane owns rows it*8 + lr, columns lc .. lc+7
     int as = 0;
@@ -352,10 +361,11 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int col0 = n_blk * p.BN + c0;
         if (col0 >= p.N) break;  // uniform
         const bool fast = fast_ok && col0 + 32 <= p.N;
+        const bool row_path = kRowEpi && p.row_epi != 0 && fast;
         // ---- issue everything that does not depend on the accumulator first (latency hidden behind TMEM/smem) ----
         float bs[8], cs[8];
         uint4 res[4];
-        if (fast) {
+        if (fast && !row_path) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { bs[j] = 0.f; cs[j] = 0.f; }
           if (p.bias) {
@@ -391,6 +401,63 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (p.grp_rows > 0) orow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows);
           epilogue_chunk(p, r, q * 32 + lane < row_valid ? row : p.M, orow, col0, vec_ok, own_r, own_n);
           loaded = false;
+          continue;
+        }
+        if (row_path) {
+          // ---- lane = row: math in place on the lane's 32 columns, 8 at a time (constants: warp-uniform 16-byte loads) ----
+          uint32_t pk[16];
+          const float2 r2 = make_float2(own_r, own_r), n2 = make_float2(own_n, own_n);
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0, s0 = b0, s1 = b0;
+            if (p.bias) {
+              b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8));
+              b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8) + 1);
+            }
+            if (f_ln) {
+              s0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + g8 * 8));
+              s1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + g8 * 8) + 1);
+            }
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+            const float2 cc[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 v = make_float2(__uint_as_float(r[g8 * 8 + 2 * j]), __uint_as_float(r[g8 * 8 + 2 * j + 1]));
+              v = f_ln ? ffma2(r2, v, ffma2(n2, cc[j], bb[j])) : fadd2(v, bb[j]);
+              if (f_gelu) v = gelu_fast2(v);
+              pk[g8 * 4 + j] = pack_bf16x2(v.x, v.y);
+            }
+          }
+          {
+            const int c1 = c0 + 64;
+            const bool more = c1 < p.BN && n_blk * p.BN + c1 < p.N;
+            loaded = more;
+            if (more) {
+              tmem_ld_x32(taddr + (uint32_t)c1, r);   // lands while this chunk is staged and stored
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
+              released = true;
+            }
+          }
+          if (lane == 0) tma_store_wait_read<1>();      // the box staged two chunks ago has been read out
+          __syncwarp();
+          {
+            uint8_t* orow_s = ostg + obuf * (kStageOut / 2) + lane * 64;
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(orow_s + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, ostg + obuf * (kStageOut / 2), col0, row_base + q * 32);   // rows >= M are clipped
+            tma_store_commit();
+          }
+          obuf ^= 1;
+          TR(3)
           continue;
         }
         // ---- transpose the raw fp32 accumulators through the per-warp staging buffer ----
@@ -619,7 +686,12 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   // LMV_GEMM_WRES / LMV_GEMM_TMA_OUT = 0 switch one off (A/B runs).  (Measured and dropped: the per-column epilogue constants staged
   // in shared memory one tile ahead behind a named barrier — qkv 70.8 -> 73.9 us.)
   auto env_on = [](const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); };
-  const int fixed = 2048 + kEpiWarps * kStageF32;
+  //   row_epi     lane = row epilogue (bias / LayerNorm fold / GELU variants with a dense bf16 output): no transpose buffers at all,
+  //               always with tma_out.  LMV_GEMM_ROW_EPI=0 switches it off.
+  const bool tma_ok = !conv && !a.out_patched && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && env_on("LMV_GEMM_TMA_OUT");
+  const bool row_epi = tma_ok && !a.residual && !a.stats_out && (a.act == 0 || a.act == 1) && env_on("LMV_GEMM_ROW_EPI");
+  p.row_epi = row_epi ? 1 : 0;
+  const int fixed = 2048 + (row_epi ? 0 : kEpiWarps * kStageF32);
   const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2;
   const int stages_plain = std::min(kMaxStages, (kSmemLimit - fixed) / stage_bytes);
   const int want = std::min(stages_plain, 4);
@@ -632,8 +704,7 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
     extra += p.k_blocks * w_bytes;
   }
   auto stages_with = [&](int more) { return std::min(kMaxStages, (kSmemLimit - fixed - extra - more) / p.stage_bytes); };
-  bool tma_out = !conv && !a.out_patched && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && env_on("LMV_GEMM_TMA_OUT") &&
-                 stages_with(kEpiWarps * kStageOut) >= (p.w_res ? 4 : want) && stages_with(kEpiWarps * kStageOut) >= 2;
+  bool tma_out = row_epi || (tma_ok && stages_with(kEpiWarps * kStageOut) >= (p.w_res ? 4 : want) && stages_with(kEpiWarps * kStageOut) >= 2);
   p.tma_out = tma_out ? 1 : 0;
   if (tma_out) extra += kEpiWarps * kStageOut;
   p.num_stages = stages_with(0);
