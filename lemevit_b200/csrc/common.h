@@ -150,6 +150,7 @@ struct GemmParams {
   int tile_rows;        // GEMM rows per M tile (128 unless conv)
   uint32_t tx_bytes;    // bytes one pipeline stage receives (A box + W box)
   int row_epi;      // lane = row epilogue (no shared-memory transpose; implies tma_out)
+  int row_res;      // ... with the in-place residual read through TMA boxes (x += A W^T + b)
   int w_res;        // tiles_n == 1 and all K blocks of W fit beside the A ring: W is loaded once per CTA and stays resident
   int stage_bytes;  // bytes of one ring slot (A tile, + W tile unless w_res)
   int tma_out;   // the fast-path epilogue leaves through TMA tile stores (tmC) instead of per-lane global stores

@@ -41,6 +41,7 @@ struct SmemCtrl {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint64_t w_full;      // resident W (p.w_res): all its K blocks have landed
+  uint64_t res_full[kEpiWarps][2];   // lane = row residual epilogue (p.row_res): the warp's residual box has landed in its staging buffer
   uint32_t tmem_base;
 };
 
@@ -168,6 +169,10 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&ctrl->acc_empty[i], kEpiWarps);  // one elected lane per epilogue warp
     }
     mbar_init(&ctrl->w_full, 1);
+    for (int i = 0; i < kEpiWarps; ++i) {
+      mbar_init(&ctrl->res_full[i][0], 1);
+      mbar_init(&ctrl->res_full[i][1], 1);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -300,6 +305,21 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const bool tma_out = p.tma_out != 0;
     uint8_t* ostg = smem + 1024 + stg_bytes + (size_t)(warp - 2) * kStageOut;
     int obuf = 0;
+    // ... and with an in-place residual (x += A W^T + b, proj / fc2; + row statistics): p.row_res.  The residual box of chunk n + 1
+    // is TMA-loaded into the warp's other staging buffer while chunk n is processed (the box is the output box: same tensor map),
+    // the lane adds its row in place and the buffer leaves again as the TMA store — no global loads on the epilogue's critical path,
+    // no shuffles for the statistics (a lane owns its row).
+    constexpr bool kRowRes = EPI >= 0 && (EPI & kEpiRes) != 0 && (EPI & (kEpiLn | kEpiGelu)) == 0;
+    const bool row_res = kRowRes && p.row_res != 0;
+    uint32_t rn = 0;                 // chunks this warp has processed (row_res): staging buffer rn & 1, barrier phase (rn >> 1) & 1
+    float rs1 = 0.f, rs2 = 0.f;      // row statistics of the lane's row over the warp's chunks of a tile (row_res)
+    auto res_issue = [&](int tile, int c0n, uint32_t n) {   // lane 0: residual box of (tile, chunk at column c0n) -> buffer n & 1
+      const int mb = tile / p.tiles_n, nb = tile % p.tiles_n;
+      uint64_t* bar = &ctrl->res_full[warp - 2][n & 1];
+      mbar_expect_tx(bar, (uint32_t)(kStageOut / 2));
+      tma_load_2d(ostg + (n & 1) * (kStageOut / 2), &tmC, bar, nb * p.BN + c0n, mb * BM + q * 32);
+    };
+    if (row_res && lane == 0 && (int)blockIdx.x < num_tiles) res_issue(blockIdx.x, half * 32, 0u);
     const int lr = lane >> 2, lc = (lane & 3) * 8;   // transposed domain: this lane owns rows it*8 + lr, columns lc .. lc+7
     int as = 0;
     uint32_t aphase = 0;
@@ -365,7 +385,7 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // ---- issue everything that does not depend on the accumulator first (latency hidden behind TMEM/smem) ----
         float bs[8], cs[8];
         uint4 res[4];
-        if (fast && !row_path) {
+        if (fast && !row_path && !row_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { bs[j] = 0.f; cs[j] = 0.f; }
           if (p.bias) {
@@ -401,6 +421,75 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (p.grp_rows > 0) orow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows);
           epilogue_chunk(p, r, q * 32 + lane < row_valid ? row : p.M, orow, col0, vec_ok, own_r, own_n);
           loaded = false;
+          continue;
+        }
+        if (row_res) {
+          // ---- lane = row with in-place residual (every chunk is a fast chunk: checked by the host) ----
+          const uint32_t b = rn & 1u;
+          {
+            // prefetch the next chunk's residual box into the other buffer: its last reader was the TMA store of chunk rn - 1
+            const int c1 = c0 + 64;
+            const bool more = c1 < p.BN;
+            const int tn = t + (int)gridDim.x;
+            if (lane == 0 && (more || tn < num_tiles)) {
+              tma_store_wait_read<0>();
+              if (more) res_issue(t, c1, rn + 1u);
+              else res_issue(tn, half * 32, rn + 1u);
+            }
+          }
+          float2 v[16];
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (p.bias) {
+              b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8));
+              b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g8 * 8) + 1);
+            }
+            v[g8 * 4 + 0] = fadd2(make_float2(__uint_as_float(r[g8 * 8 + 0]), __uint_as_float(r[g8 * 8 + 1])), make_float2(b0.x, b0.y));
+            v[g8 * 4 + 1] = fadd2(make_float2(__uint_as_float(r[g8 * 8 + 2]), __uint_as_float(r[g8 * 8 + 3])), make_float2(b0.z, b0.w));
+            v[g8 * 4 + 2] = fadd2(make_float2(__uint_as_float(r[g8 * 8 + 4]), __uint_as_float(r[g8 * 8 + 5])), make_float2(b1.x, b1.y));
+            v[g8 * 4 + 3] = fadd2(make_float2(__uint_as_float(r[g8 * 8 + 6]), __uint_as_float(r[g8 * 8 + 7])), make_float2(b1.z, b1.w));
+          }
+          {
+            const int c1 = c0 + 64;
+            const bool more = c1 < p.BN;
+            loaded = more;
+            if (more) {
+              tmem_ld_x32(taddr + (uint32_t)c1, r);   // lands while this chunk is finished
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
+              released = true;
+            }
+          }
+          mbar_wait(&ctrl->res_full[warp - 2][b], (rn >> 1) & 1u, 6);      // the residual box of this chunk is in the buffer
+          uint8_t* srow = ostg + b * (kStageOut / 2) + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4* slot = reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4));
+            const uint4 rv = *slot;
+            const float2 o0 = fadd2(v[4 * j + 0], unpack_bf16x2(rv.x)), o1 = fadd2(v[4 * j + 1], unpack_bf16x2(rv.y));
+            const float2 o2 = fadd2(v[4 * j + 2], unpack_bf16x2(rv.z)), o3 = fadd2(v[4 * j + 3], unpack_bf16x2(rv.w));
+            uint4 wv;
+            wv.x = pack_bf16x2(o0.x, o0.y); wv.y = pack_bf16x2(o1.x, o1.y); wv.z = pack_bf16x2(o2.x, o2.y); wv.w = pack_bf16x2(o3.x, o3.y);
+            if (f_stats) {   // statistics of the STORED (bf16-rounded) values
+              const float2 f0 = unpack_bf16x2(wv.x), f1 = unpack_bf16x2(wv.y), f2 = unpack_bf16x2(wv.z), f3 = unpack_bf16x2(wv.w);
+              rs1 += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+              rs2 = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, rs2))));
+              rs2 = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, fmaf(f3.x, f3.x, fmaf(f3.y, f3.y, rs2))));
+            }
+            *slot = wv;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, ostg + b * (kStageOut / 2), col0, row_base + q * 32);   // rows >= M are clipped
+            tma_store_commit();
+          }
+          ++rn;
+          TR(3)
           continue;
         }
         if (row_path) {
@@ -559,7 +648,13 @@ gemm_bf16_tn_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctrl->acc_empty[as]);
       }
-      if (f_stats) {
+      if (f_stats && row_res) {
+        // the lane owns its row: one plain store per (row, n tile, half), no shuffles
+        const int parts = 2 * p.tiles_n, part = 2 * n_blk + half;
+        if (q * 32 + lane < row_valid)
+          *reinterpret_cast<float2*>(p.stats_out + ((long long)(row_base + q * 32 + lane) * parts + part) * 2) = make_float2(rs1, rs2);
+        rs1 = 0.f; rs2 = 0.f;
+      } else if (f_stats) {
         // deterministic partials (no atomics): slot (n_blk, half) of every row this warp covers
         const int parts = 2 * p.tiles_n, part = 2 * n_blk + half;
 #pragma unroll
@@ -690,8 +785,12 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
   //               always with tma_out.  LMV_GEMM_ROW_EPI=0 switches it off.
   const bool tma_ok = !conv && !a.out_patched && !a.out_fp32 && a.grp_rows == 0 && a.ldc % 8 == 0 && a.N >= 32 && env_on("LMV_GEMM_TMA_OUT");
   const bool row_epi = tma_ok && !a.residual && !a.stats_out && (a.act == 0 || a.act == 1) && env_on("LMV_GEMM_ROW_EPI");
-  p.row_epi = row_epi ? 1 : 0;
-  const int fixed = 2048 + (row_epi ? 0 : kEpiWarps * kStageF32);
+  // row_res: the same without transposes for `x += A W^T + b` in place (+ row statistics): residual boxes through TMA
+  const bool row_res = tma_ok && a.residual && a.residual == a.out && !a.ln_stats && a.act == 0 && a.N % p.BN == 0 && p.BN >= 64 &&
+                       env_on("LMV_GEMM_ROW_RES");
+  p.row_res = row_res ? 1 : 0;
+  p.row_epi = (row_epi || row_res) ? 1 : 0;      // shared-memory layout without transpose buffers
+  const int fixed = 2048 + (p.row_epi ? 0 : kEpiWarps * kStageF32);
   const int a_bytes = BM * BK * 2, w_bytes = p.BN * BK * 2;
   const int stages_plain = std::min(kMaxStages, (kSmemLimit - fixed) / stage_bytes);
   const int want = std::min(stages_plain, 4);
@@ -704,7 +803,7 @@ int gemm_prepare(const GemmArgs& a, GemmOp* op) {
     extra += p.k_blocks * w_bytes;
   }
   auto stages_with = [&](int more) { return std::min(kMaxStages, (kSmemLimit - fixed - extra - more) / p.stage_bytes); };
-  bool tma_out = row_epi || (tma_ok && stages_with(kEpiWarps * kStageOut) >= (p.w_res ? 4 : want) && stages_with(kEpiWarps * kStageOut) >= 2);
+  bool tma_out = p.row_epi || (tma_ok && stages_with(kEpiWarps * kStageOut) >= (p.w_res ? 4 : want) && stages_with(kEpiWarps * kStageOut) >= 2);
   p.tma_out = tma_out ? 1 : 0;
   if (tma_out) extra += kEpiWarps * kStageOut;
   p.num_stages = stages_with(0);
