@@ -1,15 +1,21 @@
 // out[M,N] = epilogue(A[M,K] · W[N,K]^T)  — the workhorse of the LeMeViT forward: every nn.Linear
-// (reference models/lemevit.py:175,178,241-246,444-448,526-529,730-733,786) and, through im2col,
-// every 3x3/s2 convolution (:702,715) runs through this kernel.
+// (reference models/lemevit.py:175,178,241-246,444-448,526-529,730-733,786) and every 3x3/s2 convolution (:702,715)
+// runs through this kernel.
 //
 // sm_100a design: persistent CTAs (one per SM), warp-specialised:
-//   warp 0      TMA producer   — cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BNx64) tiles
+//   warp 0      TMA producer   — cp.async.bulk.tensor 128B-swizzled A (128x64) and W (BNx64) tiles; for the convolutions
+//                                (GemmArgs::conv_*) the A box is a strided 4-D gather straight from the activation
+//                                (implicit GEMM: one box per (tap, 64-channel slice), padding by out-of-bounds fill)
 //   warp 1      MMA issuer     — one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM
-//   warps 2..9  epilogue       — two warps per TMEM lane quarter (they split the 32-column chunks):
-//                                tcgen05.ld -> [LayerNorm fold] + bias -> [GELU] -> per-warp smem transpose ->
-//                                coalesced (+ residual) bf16 stores, optional per-row (sum, sum^2) output
-// smem ring of `num_stages` (A,W) tiles with full/empty mbarriers; TMEM holds two 256-column
-// accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 2..9  epilogue       — two warps per TMEM lane quarter (they split the 32-column chunks).  Three forms:
+//                                * lane = row (row_epi): tcgen05.ld -> [LayerNorm fold] + bias -> [GELU] -> bf16 row into a
+//                                  64B-swizzled staging box -> TMA store;
+//                                * lane = row with in-place residual (row_res): the residual box is TMA-loaded one chunk
+//                                  ahead into the other staging box, added in place, stored back by TMA, + row statistics;
+//                                * transpose (everything else: convolutions' short tiles, fp32 / strided outputs, the head):
+//                                  per-warp smem transpose -> coalesced (+ residual) stores or TMA boxes.
+// smem ring of `num_stages` (A,W) tiles with full/empty mbarriers (W resident beside an A-only ring when there is one N tile
+// and it fits: w_res); TMEM holds two 256-column accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Fusions carried by the epilogue (north star: "LN fused into the following projection, bias+GELU fused into the
 // MLP GEMM"): LayerNorm (norm1 -> q/kv/qkv*, norm2 -> mlp.0; models/lemevit.py:560-564,600-601,632-635) is folded

@@ -2,12 +2,12 @@
 // Reference: LeMeBlock.pos_embed (models/lemevit.py:510) applied at :546,589,619, followed by norm1 (:513) whose
 // normalisation is folded into the consuming GEMM (gemm.cu) from the (sum, sum^2) emitted here.
 //
-// sm_100a design (memory-bound op, roofline = read x + write x'): one CTA per (TH x TW) output tile of one image.
+// sm_100a design (memory-bound op, roofline = read x + write x'): persistent CTAs over (TH x TW) output tiles of the images.
 //   * one elected thread issues a 4-D TMA load {C, TW+2, TH+2, 1} of the input tile + halo into shared memory; the
 //     tensor map spans a single image plane {C, W, H, B}, so the zero padding of the convolution is TMA's out-of-bounds
 //     fill (negative / overflowing coordinates) — no border branches in the kernel;
-//   * work item = (token, 8-channel vector): 9 x LDS.128 of activations (consecutive lanes -> consecutive 16 B, conflict
-//     free), depthwise taps in registers, fp32 accumulate, one coalesced 16-byte store;
+//   * thread = (tile column, 8-channel vector) streaming the input rows of its column once (3 x LDS.128 per row feed up to three
+//     output rows through rotating accumulators), depthwise taps in registers, packed fp32 FMAs, one 16-byte store per output;
 //   * statistics are reduced in a fixed order through shared memory (deterministic, no atomics).
 // Meta-token rows (t >= H*W of a unified [B, N+M, C] buffer) are passed through by one extra CTA per image.
 #include <algorithm>

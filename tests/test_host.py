@@ -152,3 +152,16 @@ def test_two_rank_sharding_and_max_over_ranks_timing_gloo():
     assert r0[0] != r1[0]                              # different images per rank (no replicated work)
     assert r0[1] == r1[1] == 20.0                      # every rank reports the slowest rank's time
     assert r0[2] == r1[2] == pytest.approx(2 * 256 / 20.0 * 1e3)   # whole-job img/s = all ranks' images / max time
+
+
+def test_uint8_input_layout_codes():
+    """Host logic of the 8-bit input edge: the LMV_DTYPE_* code follows the memory layout of the (NCHW-shaped) tensor."""
+    import torch
+    from lemevit_b200 import _native
+    from lemevit_b200.engine import Engine
+    u8 = torch.zeros(2, 3, 8, 10, dtype=torch.uint8)
+    assert Engine._x_code(u8) == _native.DTYPE_U8
+    assert Engine._x_code(u8.contiguous(memory_format=torch.channels_last)) == _native.DTYPE_U8_NHWC
+    assert Engine._x_code(torch.zeros(2, 8, 10, 3, dtype=torch.uint8).permute(0, 3, 1, 2)) == _native.DTYPE_U8_NHWC
+    assert Engine._x_code(torch.zeros(2, 3, 8, 10, dtype=torch.bfloat16)) == _native.DTYPE_BF16
+    assert Engine._x_code(torch.zeros(2, 3, 8, 10)) == _native.DTYPE_F32
