@@ -437,6 +437,7 @@ def run_ours(args):
         up_done = [torch.cuda.Event() for _ in range(2)]
         buf_free = [torch.cuda.Event() for _ in range(2)]
         out_done = [torch.cuda.Event() for _ in range(2)]
+        d2h_done = [torch.cuda.Event() for _ in range(2)]
 
         def e2e_loop(n):
             for ev in buf_free:
@@ -445,8 +446,14 @@ def run_ours(args):
                 copy_s.wait_event(buf_free[0])
                 dx[0].copy_(hx[0], non_blocking=True)
                 up_done[0].record(copy_s)
+            hold = [None, None]       # device results of steps i - 2 / i - 1: alive until their download has finished
             for i in range(n):
                 cur, nxt = i & 1, (i + 1) & 1
+                if hold[cur] is not None:
+                    # step i - 2 has been read back (it ran under the forward of step i - 1): its host buffer and its device
+                    # tensors may be reused — the allocator then cycles through the same blocks instead of growing in the timed loop
+                    d2h_done[cur].synchronize()
+                    hold[cur] = None
                 if i + 1 < n:
                     with torch.cuda.stream(copy_s):
                         copy_s.wait_event(buf_free[nxt])
@@ -459,12 +466,13 @@ def run_ours(args):
                 with torch.cuda.stream(down_s):
                     down_s.wait_event(out_done[cur])
                     for h, o in zip(hy[cur], out if isinstance(out, (list, tuple)) else [out]):
-                        h.copy_(o, non_blocking=True)      # (same stream every step: the host buffer of step i - 2 is free by then)
-                        o.record_stream(down_s)
+                        h.copy_(o, non_blocking=True)
+                    d2h_done[cur].record(down_s)
+                hold[cur] = out
             torch.cuda.synchronize(dev)
 
         if not args.no_e2e:
-            e2e_loop(max(2, W // 2))
+            e2e_loop(max(4, W))
             barrier()
             t0 = time.perf_counter()
             e2e_loop(K)
